@@ -1,0 +1,63 @@
+"""Parity cases shared by the golden-vector generator and the tests.
+
+Every case is tiny (the real reference finishes it in well under a second on one core) and
+targets one of the edge cases SURVEY.md section 8(c) asks for.  Inputs come from
+``arco_b200.synth.exact_case`` so they are bit-identical on every machine.
+"""
+from arco_b200.synth import CaseSpec
+
+CASES = [
+    # plain 2-D, fresh zero-row bank as train_arco_2d.py:147-154 builds it; two calls so the bank grows
+    CaseSpec("acdc_smc", 2, 2, 4, (24, 24), 8, queries=16, negatives=8, func="smc", steps=2),
+    # antithetic sampler, non-square image, D not a multiple of 8, randn row as train_arco_3d.py:148
+    CaseSpec("acdc_asmc", 2, 2, 4, (20, 28), 12, queries=32, negatives=6, func="asmc",
+             bank_init="randn1", steps=2, seed=2024),
+    # grid-sampler path on both calls (anchor candidates and bank length >= 57)
+    CaseSpec("grid_paths", 3, 3, 4, (32, 32), 8, queries=64, negatives=4, func="smc",
+             bank_init="fill:100", caps=[150, 120, 120, 120], seed=99),
+    CaseSpec("grid_paths_as", 3, 3, 4, (32, 32), 8, queries=64, negatives=4, func="asmc",
+             bank_init="fill:100", caps=[150, 120, 120, 120], seed=98),
+    # 19 classes: exercises the rank window [3,20) with C > 16
+    CaseSpec("city19", 2, 2, 19, (16, 16), 16, queries=8, negatives=16, func="smc",
+             bank_init="fill:40", caps=[64] * 19, steps=2, seed=7),
+    # 3-D volume twin (loss_helper.py); C=2 so no key is ever enqueued (trap 3)
+    CaseSpec("la3d", 1, 1, 2, (8, 8, 6), 16, queries=16, negatives=8, func="asmc",
+             bank_init="randn1", steps=2, seed=11),
+    # class 1 absent: list-position / class-id mismatch (trap 1)
+    CaseSpec("absent_class", 2, 2, 4, (16, 16), 8, func="smc", bank_init="fill:30",
+             caps=[50, 30, 30, 30], label_mode="absent:1", seed=5),
+    # only one class present: zero loss that still depends on rep (trap 5)
+    CaseSpec("single_class", 2, 2, 4, (12, 12), 8, func="smc", label_mode="single:2", seed=6),
+    # class 1 has no confident pixel: empty anchor list, slot skipped but counted (trap 2)
+    CaseSpec("no_anchor", 2, 2, 4, (16, 16), 8, func="smc", bank_init="fill:20",
+             caps=[40, 40, 40, 40], label_mode="noanchor:1", seed=8),
+    # more keys in one call than the queue holds: eviction keeps the newest rows (trap 6)
+    CaseSpec("overflow", 2, 2, 5, (16, 16), 8, func="smc", bank_init="fill:4",
+             caps=[7, 5, 5, 5, 5], mask_frac=0.9, steps=3, seed=13),
+    # any other func string: plain torch.randint (loss_helper_3d.py:335-338)
+    CaseSpec("uniform_func", 2, 2, 4, (16, 16), 8, func="rand", bank_init="fill:25",
+             caps=[40, 40, 40, 40], seed=17),
+    # half of the unlabelled pixels carry the ignore label -1 -> class 0 one-hot (trap 4)
+    CaseSpec("ignore_heavy", 2, 2, 4, (16, 16), 8, func="smc", bank_init="fill:25",
+             caps=[40, 40, 40, 40], ignore_frac=0.5, seed=19),
+    # blocky labels, unequal labelled / unlabelled split, image size not a multiple of 4
+    CaseSpec("blocky_odd", 1, 3, 6, (15, 13), 20, queries=24, negatives=5, func="asmc",
+             bank_init="fill:60", caps=[80] * 6, label_mode="blocky", seed=23),
+    # bf16 representation tensors (config 2); compared at bf16 tolerance
+    CaseSpec("bf16_rep", 2, 2, 4, (16, 16), 16, func="smc", bank_init="fill:25",
+             caps=[40, 40, 40, 40], dtype="bf16", seed=29),
+]
+
+BY_NAME = {c.name: c for c in CASES}
+
+# (func, high, shape, seed) -> reference sampler output, stored in tests/golden/samplers.npz
+SAMPLER_CASES = [
+    (func, high, shape, seed)
+    for func in ("smc", "asmc")
+    for (high, shape, seed) in [
+        (1, 256, 1), (5, 16, 2), (15, 256, 3), (16, 256, 4), (17, 31, 5), (40, 7, 6), (56, 256, 7),
+        (57, 256, 8), (64, 256, 9), (100, 256, 10), (1000, 256, 11), (6133, 256, 12),
+        (300, 2048, 13), (29929, 4096, 14), (30000, 8192, 15), (30000, 131072, 16),
+        (3000, 1, 17), (5000, 20, 18),
+    ]
+]
