@@ -1,0 +1,112 @@
+"""ctypes binding of ``libarco_b200.so`` (declared in ``include/arco_b200.h``).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing, importing this
+module raises with the build command, and every entry point raises :class:`ArcoError` on a
+non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_CLASSES = 32
+TILE = 1024
+F32, BF16 = 0, 1
+LABEL_ONEHOT_I64, LABEL_INDEX_I64 = 0, 1
+FUNC_UNIFORM, FUNC_SMC, FUNC_ASMC = 0, 1, 2
+ST_MULTI_HOT, ST_LABEL_RANGE = 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libarco_b200.so")
+
+
+class ArcoError(RuntimeError):
+    pass
+
+
+class Dims(C.Structure):
+    _fields_ = [
+        ("n_lab", C.c_int32), ("n_unlab", C.c_int32), ("classes", C.c_int32), ("feat", C.c_int32),
+        ("space", C.c_int64), ("queries", C.c_int32), ("negatives", C.c_int32),
+        ("rep_dtype", C.c_int32), ("label_kind", C.c_int32),
+    ]
+
+
+class WsLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "total_bytes", "plan", "codes", "tile_flagged", "cnt_anchor", "cnt_key", "off_anchor", "off_key",
+        "partials", "loss_parts", "sample_scratch")] + [
+        ("n_tiles", C.c_int32), ("tiles_per_image", C.c_int32), ("partial_rows", C.c_int32), ("reserved", C.c_int32)]
+
+
+_U32x = C.c_uint32 * MAX_CLASSES
+_I32x = C.c_int32 * MAX_CLASSES
+_I64x = C.c_int64 * MAX_CLASSES
+
+
+class Plan(C.Structure):
+    _fields_ = [
+        ("lv_count", _U32x), ("n_anchor", _U32x), ("n_key", _U32x),
+        ("n_valid", C.c_int32),
+        ("valid_class", _I32x), ("slot_active", _I32x), ("bank_write_base", _I32x), ("bank_skip", _I32x),
+        ("bank_len", _I32x), ("bank_head", _I32x),
+        ("queue_ptr", _I64x),
+        ("inv_scale", C.c_float), ("status", C.c_uint32), ("scan_done", C.c_uint32), ("loss_done", C.c_uint32),
+    ]
+
+
+class Bank(C.Structure):
+    _fields_ = [
+        ("rows", C.c_void_p), ("head", C.c_void_p), ("len", C.c_void_p), ("queue_ptr", C.c_void_p),
+        ("cap", _I32x), ("row_off", _I64x),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. arco_b200 has no CPU/PyTorch fallback: build the CUDA library first with "
+            f"`python -m arco_b200.build` (needs nvcc, targets sm_100a).")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+    dp, bp = C.POINTER(Dims), C.POINTER(Bank)
+    sigs = {
+        "arco_version": (C.c_char_p, []),
+        "arco_last_error_string": (C.c_char_p, []),
+        "arco_workspace_layout": (C.c_int, [dp, C.POINTER(WsLayout)]),
+        "arco_label_onehot": (C.c_int, [vp, vp, i64, i32, i64, vp]),
+        "arco_classify_count": (C.c_int, [dp, vp, vp, vp, vp, vp, vp, f32, f32, i32, i32, vp, vp]),
+        "arco_scan_plan": (C.c_int, [dp, bp, vp, vp]),
+        "arco_replan_global": (C.c_int, [dp, vp, vp, vp]),
+        "arco_proto_enqueue": (C.c_int, [dp, vp, bp, vp, vp, vp]),
+        "arco_sample": (C.c_int, [dp, i32, u64, u64, vp, vp, vp, vp]),
+        "arco_sample_one": (C.c_int, [i32, i64, i64, u64, u64, vp, vp, i64, vp]),
+        "arco_infonce": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
+        "arco_grad_scatter": (C.c_int, [dp, vp, vp, vp, vp, vp]),
+        "arco_export_list": (C.c_int, [dp, i32, i32, vp, i64, vp, vp, vp]),
+        "arco_bank_read": (C.c_int, [bp, i32, i32, vp, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)      # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    return lib, tuple(sigs)
+
+
+lib, EXPORTS = _load()
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib.arco_last_error_string().decode(errors="replace")
+        raise ArcoError(f"{what} failed with status {status}: {msg}")
+
+
+def version() -> str:
+    return lib.arco_version().decode()
+
+
+def workspace_layout(dims: Dims) -> WsLayout:
+    out = WsLayout()
+    check(lib.arco_workspace_layout(C.byref(dims), C.byref(out)), "arco_workspace_layout")
+    return out

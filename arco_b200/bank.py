@@ -1,0 +1,187 @@
+"""Device-resident ring-buffer memory bank that keeps the reference's list protocol.
+
+The reference trainers own three Python lists (``/root/reference/code/train_arco_2d.py:147-154``,
+``train_arco_3d.py:144-151``)::
+
+    memobank[c]     = [cpu_tensor[n_c, D]]      # rows in FIFO order, newest last
+    queue_ptrlis[c] = LongTensor(1)
+    queue_size[c]   = int                        # 50000 for class 0, 30000 otherwise
+
+and ``dequeue_and_enqueue`` (``loss_helper_3d.py:12-32``) copies every step's keys to the CPU,
+concatenates, and keeps the newest ``queue_size`` rows; the loss then uploads the whole bank again
+(``:466``).  Here the rows live in HBM as one ``[sum(cap), D]`` fp32 ring per class; (head, length,
+pointer) are device scalars updated by ``arco_scan_plan``; nothing crosses PCIe in the step.
+
+The caller's lists are adopted lazily on the first call: ``memobank[c]`` is replaced by a
+:class:`BankSlot` (a ``list`` subclass) whose element 0 still answers ``.shape[0]`` and row indexing in
+logical FIFO order, and ``queue_ptrlis[c][0]`` is refreshed from the device bookkeeping whenever the
+host mirror is settled (:meth:`DeviceMemoryBank.settle`, called at the start of the next step and
+on any inspection).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _cabi
+
+
+class BankSlot(list):
+    """Stands in for ``memobank[c]``.  ``slot[0]`` materialises the class's rows (FIFO order) on the
+    bank's device; ``slot[0] = tensor`` replaces the class's content (as a trainer resetting its bank)."""
+
+    def __init__(self, bank: "DeviceMemoryBank", cls: int):
+        super().__init__([None])
+        self.bank = bank
+        self.cls = cls
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(1))]
+        if i not in (0, -1):
+            raise IndexError("memobank[c] holds exactly one tensor")
+        return self.bank.rows_of(self.cls)
+
+    def __setitem__(self, i, value):
+        if i not in (0, -1):
+            raise IndexError("memobank[c] holds exactly one tensor")
+        self.bank.replace_rows(self.cls, value)
+
+    def __iter__(self):
+        yield self[0]
+
+    def __repr__(self):
+        return f"BankSlot(class={self.cls}, rows={self.bank.length(self.cls)}, cap={self.bank.caps[self.cls]})"
+
+
+class DeviceMemoryBank:
+    def __init__(self, memobank: list, queue_ptrlis: list, queue_size: Sequence[int], feat: int, device):
+        self.device = torch.device(device)
+        self.feat = int(feat)
+        self.classes = len(memobank)
+        if self.classes > _cabi.MAX_CLASSES:
+            raise ValueError(f"at most {_cabi.MAX_CLASSES} classes are supported, got {self.classes}")
+        if len(queue_size) != self.classes or len(queue_ptrlis) != self.classes:
+            raise ValueError("memobank, queue_prtlis and queue_size must have one entry per class")
+        self.caps = [int(q) for q in queue_size]
+        if min(self.caps) <= 0:
+            raise ValueError("queue_size entries must be positive")
+        self.row_off = [0]
+        for cap in self.caps:
+            self.row_off.append(self.row_off[-1] + cap)
+        self.rows = torch.zeros((self.row_off[-1], self.feat), dtype=torch.float32, device=self.device)
+        head = torch.zeros(_cabi.MAX_CLASSES, dtype=torch.int32)
+        length = torch.zeros(_cabi.MAX_CLASSES, dtype=torch.int32)
+        ptr = torch.zeros(_cabi.MAX_CLASSES, dtype=torch.int64)
+        for c in range(self.classes):
+            init = memobank[c][0]
+            if init.dim() != 2 or init.shape[1] != self.feat:
+                raise ValueError(f"memobank[{c}][0] must be [n, {self.feat}], got {tuple(init.shape)}")
+            init = init[-self.caps[c]:] if init.shape[0] > self.caps[c] else init
+            n = init.shape[0]
+            if n:
+                self.rows[self.row_off[c]: self.row_off[c] + n] = init.to(self.device, torch.float32)
+            length[c] = n
+            ptr[c] = int(queue_ptrlis[c].reshape(-1)[0])
+        self.head = head.to(self.device)
+        self.len = length.to(self.device)
+        self.ptr = ptr.to(self.device)
+        self.host_len = [int(x) for x in length[: self.classes]]
+        self.host_ptr = [int(x) for x in ptr[: self.classes]]
+        self._queue_ptrlis = queue_ptrlis
+        self._pending = None            # (event, pinned plan bytes) of the last step
+        self.last_plan: Optional[_cabi.Plan] = None
+        self.keys_by_step = {}          # step -> new_keys of that step (short history for LazyKeys)
+        self.step = 0
+        self.c_struct = _cabi.Bank()
+        self.c_struct.rows = self.rows.data_ptr()
+        self.c_struct.head = self.head.data_ptr()
+        self.c_struct.len = self.len.data_ptr()
+        self.c_struct.queue_ptr = self.ptr.data_ptr()
+        for c in range(self.classes):
+            self.c_struct.cap[c] = self.caps[c]
+            self.c_struct.row_off[c] = self.row_off[c]
+        # adopt: the caller's list now fronts the device bank
+        for c in range(self.classes):
+            memobank[c] = BankSlot(self, c)
+
+    # ------------------------------------------------------------------ adoption
+    @staticmethod
+    def adopt(memobank: list, queue_ptrlis: list, queue_size: Sequence[int], feat: int, device) -> "DeviceMemoryBank":
+        first = memobank[0] if len(memobank) else None
+        if isinstance(first, BankSlot):
+            bank = first.bank
+            if bank.device != torch.device(device) or bank.feat != int(feat) or bank.classes != len(memobank):
+                raise ValueError("memobank was adopted for a different device / feature size / class count")
+            if [int(q) for q in queue_size] != bank.caps:
+                raise ValueError("queue_size changed after the memory bank was adopted")
+            bank._queue_ptrlis = queue_ptrlis
+            return bank
+        return DeviceMemoryBank(memobank, queue_ptrlis, queue_size, feat, device)
+
+    # ------------------------------------------------------------------ host mirror
+    def post_step(self, plan_bytes_dev: torch.Tensor, stream: torch.cuda.Stream) -> None:
+        """Queue an async device->pinned copy of the step's ``arco_plan``; no host sync."""
+        pinned = torch.empty(plan_bytes_dev.numel(), dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(plan_bytes_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self._pending = (ev, pinned)
+        self.step += 1
+
+    def settle(self) -> Optional[_cabi.Plan]:
+        """Wait for the last step's summary (normally long finished) and refresh the host mirrors,
+        including the caller's ``queue_prtlis``.  Raises if the device flagged invalid labels."""
+        if self._pending is None:
+            return self.last_plan
+        ev, pinned = self._pending
+        ev.synchronize()
+        self._pending = None
+        plan = _cabi.Plan.from_buffer_copy(pinned.numpy().tobytes()[: C.sizeof(_cabi.Plan)])
+        self.last_plan = plan
+        self.keys_by_step[self.step] = [int(plan.n_key[c]) for c in range(self.classes)]
+        for old in [k for k in self.keys_by_step if k < self.step - 16]:
+            del self.keys_by_step[old]
+        for c in range(self.classes):
+            self.host_len[c] = int(plan.bank_len[c])
+            self.host_ptr[c] = int(plan.queue_ptr[c])
+            self._queue_ptrlis[c][0] = self.host_ptr[c]
+        if plan.status & _cabi.ST_MULTI_HOT:
+            raise ValueError("label_l/label_u are not one-hot: some pixel has more than one non-zero class entry")
+        if plan.status & _cabi.ST_LABEL_RANGE:
+            raise ValueError("integer label map contains a class id >= num_classes")
+        return plan
+
+    def length(self, cls: int) -> int:
+        self.settle()
+        return self.host_len[cls]
+
+    # ------------------------------------------------------------------ list protocol
+    def rows_of(self, cls: int) -> torch.Tensor:
+        """Rows of class ``cls`` in logical FIFO order, ``[len, D]`` fp32 on the bank's device."""
+        n = self.length(cls)
+        out = torch.empty((self.caps[cls], self.feat), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream()
+            _cabi.check(_cabi.lib.arco_bank_read(C.byref(self.c_struct), cls, self.feat, out.data_ptr(), st.cuda_stream),
+                        "arco_bank_read")
+        return out[:n]
+
+    def replace_rows(self, cls: int, value: torch.Tensor) -> None:
+        self.settle()
+        if value.dim() != 2 or value.shape[1] != self.feat:
+            raise ValueError(f"bank rows must be [n, {self.feat}]")
+        value = value[-self.caps[cls]:] if value.shape[0] > self.caps[cls] else value
+        n = value.shape[0]
+        self.rows[self.row_off[cls]: self.row_off[cls] + n] = value.to(self.device, torch.float32)
+        self.head[cls] = 0
+        self.len[cls] = n
+        self.host_len[cls] = n
+
+
+def synchronize_bank(memobank: list) -> None:
+    """Bring ``queue_prtlis`` and the bank lengths up to date with the device (host sync)."""
+    if len(memobank) and isinstance(memobank[0], BankSlot):
+        memobank[0].bank.settle()

@@ -1,0 +1,272 @@
+"""Drop-in ``compute_contra_memobank_loss`` backed by hand-written sm_100a kernels.
+
+Mirrors the reference operator (same name, positional order, keyword names, return tuple and side
+effects): ``/root/reference/code/loss_helper_3d.py:271-513`` for ``rep [B,D,H,W]`` and
+``/root/reference/code/loss_helper.py:442-686`` for ``rep [B,D,H,W,Z]``; call sites
+``train_arco_2d.py:394-398`` / ``train_arco_3d.py:356-360``.  One implementation serves both: the
+spatial axes are flattened to ``S`` and never permuted.
+
+Pipeline (all on ``torch.cuda.current_stream()``, no host synchronisation in forward or backward):
+
+  arco_classify_count -> arco_scan_plan -> arco_proto_enqueue -> [NCCL all-reduce of the C x (D+1)
+  fp64 prototype sums] -> arco_sample (or injected indices) -> arco_infonce        (forward)
+  arco_grad_scatter                                                                 (backward)
+
+There is no CPU path and no PyTorch fallback: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _cabi
+from .bank import DeviceMemoryBank
+
+DELTA_P = 0.3                  # current_class_threshold, loss_helper_3d.py:316
+LOW_RANK, HIGH_RANK = 3, 20    # loss_helper_3d.py:318
+
+_FUNC = {"smc": _cabi.FUNC_SMC, "asmc": _cabi.FUNC_ASMC}
+
+
+class LazyKeys(list):
+    """``new_keys`` (reference: list of ints, loss_helper_3d.py:404-411) resolved on first access so the
+    step itself never waits for the device."""
+
+    def __init__(self, bank: DeviceMemoryBank, classes: int):
+        super().__init__()
+        self._bank = bank
+        self._classes = classes
+        self._ticket = bank.step
+        self._done = False
+
+    def _resolve(self):
+        if not self._done:
+            if self._ticket not in self._bank.keys_by_step:
+                self._bank.settle()
+            if self._ticket not in self._bank.keys_by_step:
+                raise RuntimeError("new_keys of a step more than 16 steps old is no longer available")
+            super().extend(self._bank.keys_by_step[self._ticket])
+            self._done = True
+
+    def __getitem__(self, i):
+        self._resolve()
+        return super().__getitem__(i)
+
+    def __iter__(self):
+        self._resolve()
+        return super().__iter__()
+
+    def __len__(self):
+        return self._classes
+
+    def __eq__(self, other):
+        self._resolve()
+        return list(self) == list(other)
+
+    def __repr__(self):
+        self._resolve()
+        return super().__repr__()
+
+
+def _flat(t: torch.Tensor, lead: int) -> torch.Tensor:
+    """Contiguous view with the trailing spatial axes flattened (``lead`` leading axes kept)."""
+    t = t.contiguous()
+    return t.view(*t.shape[:lead], -1)
+
+
+class _ContraLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rep, st):
+        dims, bank = st["dims"], st["bank"]
+        dev = rep.device
+        stream = torch.cuda.current_stream(dev)
+        sp = stream.cuda_stream
+        lib = _cabi.lib
+        layout = st["layout"]
+        ws = torch.empty(layout.total_bytes, dtype=torch.uint8, device=dev)
+        wsp = ws.data_ptr()
+        Cn, Q, N, D = dims.classes, dims.queries, dims.negatives, dims.feat
+        d = C.byref(dims)
+        b = C.byref(bank.c_struct)
+
+        _cabi.check(lib.arco_classify_count(
+            d, st["label_l"].data_ptr() if st["label_l"] is not None else None,
+            st["label_u"].data_ptr() if st["label_u"] is not None else None,
+            st["prob_l"].data_ptr() if st["prob_l"] is not None else None,
+            st["prob_u"].data_ptr() if st["prob_u"] is not None else None,
+            st["low_mask"].data_ptr(), st["high_mask"].data_ptr(),
+            DELTA_P, float(st["delta_n"]), LOW_RANK, HIGH_RANK, wsp, sp), "arco_classify_count")
+        _cabi.check(lib.arco_scan_plan(d, b, wsp, sp), "arco_scan_plan")
+        proto_sums = torch.empty((Cn, D + 1), dtype=torch.float64, device=dev)
+        _cabi.check(lib.arco_proto_enqueue(d, st["rep_teacher"].data_ptr(), b, proto_sums.data_ptr(), wsp, sp),
+                    "arco_proto_enqueue")
+        group = st["group"]
+        if group is not None:
+            # the one exchange step of the path: C*(D+1) fp64 sums + counts
+            torch.distributed.all_reduce(proto_sums, group=group)
+            _cabi.check(lib.arco_replan_global(d, proto_sums.data_ptr(), wsp, sp), "arco_replan_global")
+
+        idx_a = torch.empty((Cn, Q), dtype=torch.int32, device=dev)
+        idx_n = torch.empty((Cn, Q * max(N, 1)), dtype=torch.int32, device=dev)
+        plan_view = ws[layout.plan: layout.plan + C.sizeof(_cabi.Plan)]
+        inject = st["inject"]
+        if inject is None:
+            _cabi.check(lib.arco_sample(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(), idx_n.data_ptr(),
+                                        wsp, sp), "arco_sample")
+        else:
+            # parity tests: replay the reference's own indices, one (anchor, negative) pair per active position
+            plan = _cabi.Plan.from_buffer_copy(plan_view.cpu().numpy().tobytes())
+            active = [j for j in range(Cn) if plan.slot_active[j]]
+            if len(inject["anchor"]) != len(active) or len(inject["neg"]) != len(active):
+                raise ValueError(f"_inject carries {len(inject['anchor'])} index sets, the step has {len(active)} "
+                                 f"active positions {active}")
+            idx_a.zero_()
+            idx_n.zero_()
+            for k, j in enumerate(active):
+                idx_a[j] = inject["anchor"][k].to(dev, torch.int32)
+                idx_n[j, : Q * N] = inject["neg"][k].to(dev, torch.int32)
+
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        g_anchor = torch.empty((Cn, Q, D), dtype=torch.float32, device=dev)
+        pix = torch.empty((Cn, Q), dtype=torch.int32, device=dev)
+        debug = st["debug"]
+        logits = torch.zeros((Cn, Q, 1 + N), dtype=torch.float32, device=dev) if debug is not None else None
+        _cabi.check(lib.arco_infonce(
+            d, st["rep_data"].data_ptr(), b, proto_sums.data_ptr(), idx_a.data_ptr(), idx_n.data_ptr(),
+            float(st["temp"]), loss.data_ptr(), g_anchor.data_ptr(), pix.data_ptr(),
+            logits.data_ptr() if logits is not None else None, wsp, sp), "arco_infonce")
+        bank.post_step(plan_view, stream)
+        if debug is not None:
+            debug.update(ws=ws, layout=layout, dims=dims, proto_sums=proto_sums, logits=logits, anchor_pix=pix,
+                         grad_anchor=g_anchor, idx_anchor=idx_a, idx_neg=idx_n)
+        ctx.save_for_backward(g_anchor, pix)
+        ctx.dims = dims
+        ctx.rep_shape = rep.shape
+        ctx.rep_dtype = rep.dtype
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g_anchor, pix = ctx.saved_tensors
+        dev = g_anchor.device
+        grad_rep = torch.empty(ctx.rep_shape, dtype=ctx.rep_dtype, device=dev)
+        go = grad_out.detach().to(torch.float32).contiguous()
+        sp = torch.cuda.current_stream(dev).cuda_stream
+        _cabi.check(_cabi.lib.arco_grad_scatter(C.byref(ctx.dims), g_anchor.data_ptr(), pix.data_ptr(), go.data_ptr(),
+                                                grad_rep.data_ptr(), sp), "arco_grad_scatter")
+        return grad_rep, None
+
+
+def compute_contra_memobank_loss(
+    rep,
+    label_l,
+    label_u,
+    prob_l,
+    prob_u,
+    low_mask,
+    high_mask,
+    memobank,
+    queue_prtlis,
+    queue_size,
+    rep_teacher,
+    momentum_prototype=None,
+    i_iter=0,
+    delta_n=1.0,
+    func="asmc",
+    num_queries=256,
+    num_negatives=512,
+    temp=0.5,
+    *,
+    process_group=None,
+    seed: Optional[int] = None,
+    _inject: Optional[dict] = None,
+    _debug: Optional[dict] = None,
+):
+    """Stratified pixel/voxel contrastive loss with memory bank -- same contract as the reference.
+
+    Arguments 1-18 are the reference's (loss_helper_3d.py:271-290).  ``label_l`` / ``label_u`` are the
+    int64 one-hot maps ``[B_x, C, *S]`` the trainers pass, or -- cheaper, 8 B instead of 8*C B per pixel --
+    plain integer label maps ``[B_x, *S]`` (ignore label -1 is folded into class 0 like the trainers'
+    ``label_onehot``); in that case the number of classes is taken from ``prob_l``.
+    Returns ``(new_keys, loss)`` (``loss.backward()`` yields a dense ``rep.grad``).
+
+    Keyword-only extensions: ``process_group`` (batch-sharded multi-GPU: one all-reduce of the per-class
+    prototype sums), ``seed`` (Philox seed of the in-kernel sampler; defaults to torch's CUDA seed),
+    ``_inject`` / ``_debug`` (parity tests).
+    """
+    if momentum_prototype is not None:
+        raise NotImplementedError(
+            "momentum_prototype (EMA prototypes, loss_helper_3d.py:488-497) is not used by either ARCO trainer "
+            "and is not implemented in arco_b200")
+    if not (torch.is_tensor(rep) and rep.is_cuda):
+        raise RuntimeError("arco_b200.compute_contra_memobank_loss needs CUDA tensors: there is no CPU fallback")
+    if rep.dim() not in (4, 5):
+        raise ValueError(f"rep must be [B,D,H,W] or [B,D,H,W,Z], got {tuple(rep.shape)}")
+    if rep.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError(f"rep must be float32 or bfloat16, got {rep.dtype}")
+    if rep_teacher.shape != rep.shape or rep_teacher.dtype != rep.dtype or rep_teacher.device != rep.device:
+        raise ValueError("rep_teacher must match rep in shape, dtype and device")
+    dev = rep.device
+    B, D = rep.shape[0], rep.shape[1]
+    spatial = tuple(rep.shape[2:])
+    S = 1
+    for s in spatial:
+        S *= int(s)
+    n_lab, n_unlab = int(label_l.shape[0]), int(label_u.shape[0])
+    if n_lab + n_unlab != B:
+        raise ValueError(f"label_l ({n_lab}) + label_u ({n_unlab}) images != rep batch ({B})")
+    Cn = int(prob_l.shape[1]) if prob_l.numel() else int(prob_u.shape[1])
+    if label_l.dim() == rep.dim():
+        label_kind = _cabi.LABEL_ONEHOT_I64
+        if tuple(label_l.shape[1:]) != (Cn,) + spatial or tuple(label_u.shape[1:]) != (Cn,) + spatial:
+            raise ValueError("one-hot labels must be [B_x, C, *spatial] matching prob and rep")
+    elif label_l.dim() == rep.dim() - 1:
+        label_kind = _cabi.LABEL_INDEX_I64
+        if tuple(label_l.shape[1:]) != spatial or tuple(label_u.shape[1:]) != spatial:
+            raise ValueError("integer label maps must be [B_x, *spatial] matching rep")
+    else:
+        raise ValueError("label_l must be one-hot [B_l,C,*S] or an integer map [B_l,*S]")
+    if label_l.dtype != torch.int64 or label_u.dtype != torch.int64:
+        raise ValueError("labels must be int64 (the trainers pass label_onehot(...).long())")
+    for name, t, n in (("prob_l", prob_l, n_lab), ("prob_u", prob_u, n_unlab)):
+        if t.dtype != torch.float32 or tuple(t.shape) != (n, Cn) + spatial:
+            raise ValueError(f"{name} must be float32 [{n},{Cn},*spatial], got {t.dtype} {tuple(t.shape)}")
+    for name, t in (("low_mask", low_mask), ("high_mask", high_mask)):
+        if t.dtype != torch.float32 or tuple(t.shape) != (B, 1) + spatial:
+            raise ValueError(f"{name} must be float32 [B,1,*spatial], got {t.dtype} {tuple(t.shape)}")
+    for t in (label_l, label_u, prob_l, prob_u, low_mask, high_mask):
+        if t.device != dev:
+            raise ValueError("all tensor arguments must live on rep's device")
+    if Cn > _cabi.MAX_CLASSES:
+        raise ValueError(f"at most {_cabi.MAX_CLASSES} classes are supported, got {Cn}")
+    if D % 4 != 0 or D > 512:
+        raise ValueError(f"feature size D must be a multiple of 4 and <= 512, got {D}")
+    if B * S >= 2 ** 31:
+        raise ValueError("more than 2^31 pixels per call")
+    if num_queries <= 0 or num_negatives < 0 or temp <= 0:
+        raise ValueError("num_queries must be > 0, num_negatives >= 0, temp > 0")
+    if len(memobank) != Cn:
+        raise ValueError(f"memobank has {len(memobank)} classes, prob has {Cn}")
+
+    with torch.cuda.device(dev):
+        bank = DeviceMemoryBank.adopt(memobank, queue_prtlis, queue_size, D, dev)
+        bank.settle()                       # last step's summary (long finished): refresh queue_prtlis, surface label errors
+        dims = _cabi.Dims(n_lab, n_unlab, Cn, D, S, int(num_queries), int(num_negatives),
+                          _cabi.BF16 if rep.dtype == torch.bfloat16 else _cabi.F32, label_kind)
+        layout = _cabi.workspace_layout(dims)
+        lead = 2 if label_kind == _cabi.LABEL_ONEHOT_I64 else 1
+        rep_data = rep.detach().contiguous()
+        state = dict(
+            dims=dims, layout=layout, bank=bank,
+            label_l=_flat(label_l, lead) if n_lab else None, label_u=_flat(label_u, lead) if n_unlab else None,
+            prob_l=_flat(prob_l, 2) if n_lab else None, prob_u=_flat(prob_u, 2) if n_unlab else None,
+            low_mask=_flat(low_mask, 2), high_mask=_flat(high_mask, 2),
+            rep_teacher=rep_teacher.detach().contiguous(), rep_data=rep_data,
+            delta_n=delta_n, temp=temp, func=_FUNC.get(func, _cabi.FUNC_UNIFORM),
+            seed=int(seed) if seed is not None else int(torch.cuda.initial_seed()) & (2 ** 63 - 1),
+            group=process_group, inject=_inject, debug=_debug,
+        )
+        loss = _ContraLoss.apply(rep, state)
+    return LazyKeys(bank, Cn), loss

@@ -1,0 +1,253 @@
+// Sub-system 1: fused label decode + confidence thresholds + teacher-rank test + per-tile counts.
+//
+// Replaces (reference, 2-D file; the 3-D twin is loss_helper.py +171 lines):
+//   label one-hot           train_arco_2d.py:492-498          (index-label mode decodes it in-kernel)
+//   low/high valid masks    loss_helper_3d.py:341-342,365-366
+//   anchor / hard masks     loss_helper_3d.py:369-374
+//   sort over classes       loss_helper_3d.py:352-358  -> rank_i = #{p_j > p_i} + #{j<i, p_j == p_i}
+//   class_mask_l/u          loss_helper_3d.py:388-399
+//   per-class totals        loss_helper_3d.py:413-415
+//
+// One CTA per 1024-pixel tile (a tile never straddles an image); 256 threads x 4 consecutive pixels
+// so every global access is a 16-byte vector (int64 labels: two per pixel pair).  HBM-bound:
+// algorithmic bytes = P * (8C + 4C + 8) read + P written.
+#include "arco_common.cuh"
+
+namespace arco {
+
+struct ClassifyParams {
+    const int64_t* label_l;
+    const int64_t* label_u;
+    const float* prob_l;
+    const float* prob_u;
+    const float* low_mask;
+    const float* high_mask;
+    uint8_t* codes;
+    uint32_t* tile_flagged;
+    uint32_t* cnt_anchor;
+    uint32_t* cnt_key;
+    arco_plan* plan;
+    int64_t S;
+    int32_t n_lab, C, tpi, NT;
+    int32_t label_kind, low_rank, high_rank;
+    float delta_p, delta_n;
+};
+
+template <int NV>
+struct PixVec;
+template <>
+struct PixVec<4> {
+    __device__ static void load_f(const float* p, float (&v)[4]) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ static void load_l(const int64_t* p, int64_t (&v)[4]) {
+        longlong2 a = *reinterpret_cast<const longlong2*>(p);
+        longlong2 b = *reinterpret_cast<const longlong2*>(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+};
+template <>
+struct PixVec<1> {
+    __device__ static void load_f(const float* p, float (&v)[1]) { v[0] = *p; }
+    __device__ static void load_l(const int64_t* p, int64_t (&v)[1]) { v[0] = *p; }
+};
+
+// NV = pixels per thread per pass (4: vector path, 1: scalar path for unaligned / odd S)
+template <int NV>
+__global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p) {
+    __shared__ uint32_t s_anchor[ARCO_MAX_CLASSES], s_key[ARCO_MAX_CLASSES], s_lv[ARCO_MAX_CLASSES];
+    __shared__ uint32_t s_flagged, s_status;
+    const int tid = threadIdx.x;
+    if (tid < ARCO_MAX_CLASSES) { s_anchor[tid] = 0; s_key[tid] = 0; s_lv[tid] = 0; }
+    if (tid == 0) { s_flagged = 0; s_status = 0; }
+    __syncthreads();
+
+    const int tile = blockIdx.x;
+    const int b = tile / p.tpi;
+    const int64_t s0 = (int64_t)(tile % p.tpi) * ARCO_TILE;
+    const bool labelled = b < p.n_lab;
+    const int bx = labelled ? b : b - p.n_lab;
+    const int C = p.C;
+    const int64_t S = p.S;
+    const int64_t* lab_base = labelled ? p.label_l : p.label_u;
+    const float* prob_base = (labelled ? p.prob_l : p.prob_u) + (int64_t)bx * C * S;
+    constexpr int PASSES = 4 / NV;
+
+#pragma unroll 1
+    for (int pass = 0; pass < PASSES; ++pass) {
+        const int64_t s = (NV == 4) ? s0 + 4 * tid : s0 + tid + 256 * pass;
+        const bool in_range = s < S;          // NV==4 requires S % 4 == 0, so the group is all-in or all-out
+        int istar[NV];
+        float pstar[NV], lm[NV], hm[NV];
+        uint32_t status = 0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { istar[v] = -1; pstar[v] = 0.f; lm[v] = 0.f; hm[v] = 0.f; }
+
+        if (in_range) {
+            if (p.label_kind == ARCO_LABEL_ONEHOT_I64) {
+                const int64_t* lp = lab_base + (int64_t)bx * C * S + s;
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) {
+                    int64_t x[NV];
+                    PixVec<NV>::load_l(lp + (int64_t)c * S, x);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        if (x[v] != 0) {
+                            if (istar[v] < 0) istar[v] = c; else status |= ARCO_ST_MULTI_HOT;
+                        }
+                    }
+                }
+            } else {
+                int64_t x[NV];
+                PixVec<NV>::load_l(lab_base + (int64_t)bx * S + s, x);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    int64_t l = x[v] < 0 ? 0 : x[v];             // relu: ignore label -1 -> class 0 (trap 4)
+                    if (l >= C) { status |= ARCO_ST_LABEL_RANGE; istar[v] = -1; } else istar[v] = (int)l;
+                }
+            }
+            PixVec<NV>::load_f(p.low_mask + (int64_t)b * S + s, lm);
+            PixVec<NV>::load_f(p.high_mask + (int64_t)b * S + s, hm);
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (istar[v] >= 0) pstar[v] = __ldg(prob_base + (int64_t)istar[v] * S + s + v);
+        }
+
+        bool lv[NV], anchor[NV], hard[NV], key[NV];
+        bool any_hard = false;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const bool has = istar[v] >= 0;
+            lv[v] = has && (lm[v] != 0.f);
+            anchor[v] = lv[v] && (pstar[v] > p.delta_p);
+            // labelled images can never yield a key: the hard mask needs label_l[:,i]=1 while
+            // class_mask_l is multiplied by label_l[:,i]==0 (trap 3, loss_helper_3d.py:372-374,397-399)
+            hard[v] = has && !labelled && (hm[v] != 0.f) && (pstar[v] < p.delta_n);
+            key[v] = false;
+            any_hard |= hard[v];
+        }
+        // teacher rank of the labelled class, only where a hard pixel needs it (warp-uniform skip)
+        if (__any_sync(0xffffffffu, any_hard)) {
+            if (any_hard) {
+                int rank[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) rank[v] = 0;
+                const float* pp = prob_base + s;
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) {
+                    float q[NV];
+                    PixVec<NV>::load_f(pp + (int64_t)c * S, q);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        rank[v] += (q[v] > pstar[v]) || (q[v] == pstar[v] && c < istar[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    key[v] = hard[v] && rank[v] >= p.low_rank && rank[v] < p.high_rank;
+            }
+        }
+
+        uint32_t packed = 0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            uint32_t code = 0;
+            if (istar[v] >= 0)
+                code = (uint32_t)istar[v] | (lv[v] ? CODE_LV : 0u) | (anchor[v] ? CODE_ANCHOR : 0u) |
+                       (key[v] ? CODE_KEY : 0u);
+            packed |= code << (8 * v);
+            // warp-aggregated counting: one shared atomic per distinct code value in the warp
+            const uint32_t flags = code & (CODE_LV | CODE_ANCHOR | CODE_KEY);
+            const uint32_t peers = __match_any_sync(0xffffffffu, code);
+            if (flags && (__ffs(peers) - 1) == (tid & 31)) {
+                const uint32_t n = __popc(peers), c = code & CODE_CLS_MASK;
+                if (flags & CODE_LV) atomicAdd(&s_lv[c], n);
+                if (flags & CODE_ANCHOR) atomicAdd(&s_anchor[c], n);
+                if (flags & CODE_KEY) atomicAdd(&s_key[c], n);
+                if (flags & (CODE_LV | CODE_KEY)) atomicAdd(&s_flagged, n);
+            }
+        }
+        if (in_range) {
+            const int64_t gp = (int64_t)b * S + s;
+            if (NV == 4) *reinterpret_cast<uint32_t*>(p.codes + gp) = packed;
+            else p.codes[gp] = (uint8_t)packed;
+        }
+        if (status) atomicOr(&s_status, status);
+    }
+    __syncthreads();
+    if (tid < C) {
+        p.cnt_anchor[(int64_t)tid * p.NT + tile] = s_anchor[tid];
+        p.cnt_key[(int64_t)tid * p.NT + tile] = s_key[tid];
+        if (s_lv[tid]) atomicAdd(&p.plan->lv_count[tid], s_lv[tid]);
+    }
+    if (tid == 0) {
+        p.tile_flagged[tile] = s_flagged;
+        if (s_status) atomicOr(&p.plan->status, s_status);
+    }
+}
+
+// (a1) stand-alone drop-in for the trainers' label_onehot
+__global__ void label_onehot_kernel(const int64_t* __restrict__ labels, float* __restrict__ out, int64_t batch,
+                                    int classes, int64_t space) {
+    const int64_t total = batch * classes * space;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = i % space;
+        const int64_t c = (i / space) % classes;
+        const int64_t b = i / (space * classes);
+        int64_t l = labels[b * space + s];
+        l = l < 0 ? 0 : l;
+        out[i] = (l == c) ? 1.f : 0.f;
+    }
+}
+
+}  // namespace arco
+
+extern "C" int arco_label_onehot(const int64_t* labels, float* out, int64_t batch, int32_t classes, int64_t space,
+                                 void* stream) {
+    ARCO_REQUIRE(labels && out && batch > 0 && classes > 0 && space > 0, "arco_label_onehot: bad argument");
+    const int64_t total = batch * classes * space;
+    int blocks = (int)((total + 255) / 256);
+    const int cap = arco::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    arco::label_onehot_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(labels, out, batch, classes, space);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}
+
+extern "C" int arco_classify_count(const arco_dims* dims, const int64_t* label_l, const int64_t* label_u,
+                                   const float* prob_l, const float* prob_u, const float* low_mask,
+                                   const float* high_mask, float delta_p, float delta_n, int32_t low_rank,
+                                   int32_t high_rank, void* workspace, void* stream) {
+    ARCO_REQUIRE(dims && workspace, "arco_classify_count: NULL dims/workspace");
+    const arco_dims& d = *dims;
+    ARCO_REQUIRE(d.classes >= 1 && d.classes <= ARCO_MAX_CLASSES, "classes must be in [1, 32]");
+    ARCO_REQUIRE(d.n_lab >= 0 && d.n_unlab >= 0 && d.n_lab + d.n_unlab > 0 && d.space > 0, "bad batch/space");
+    ARCO_REQUIRE((d.n_lab == 0 || (label_l && prob_l)) && (d.n_unlab == 0 || (label_u && prob_u)) && low_mask &&
+                     high_mask, "NULL input tensor");
+    ARCO_REQUIRE(((int64_t)d.n_lab + d.n_unlab) * d.space < (int64_t)0x7fffffff, "more than 2^31 pixels");
+    arco_ws_layout L;
+    arco::compute_layout(d, &L);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    ARCO_CUDA_CHECK(cudaMemsetAsync(ws + L.plan, 0, sizeof(arco_plan), st));
+
+    arco::ClassifyParams p;
+    p.label_l = label_l; p.label_u = label_u; p.prob_l = prob_l; p.prob_u = prob_u;
+    p.low_mask = low_mask; p.high_mask = high_mask;
+    p.codes = (uint8_t*)(ws + L.codes);
+    p.tile_flagged = (uint32_t*)(ws + L.tile_flagged);
+    p.cnt_anchor = (uint32_t*)(ws + L.cnt_anchor);
+    p.cnt_key = (uint32_t*)(ws + L.cnt_key);
+    p.plan = (arco_plan*)(ws + L.plan);
+    p.S = d.space; p.n_lab = d.n_lab; p.C = d.classes; p.tpi = L.tiles_per_image; p.NT = L.n_tiles;
+    p.label_kind = d.label_kind; p.low_rank = low_rank; p.high_rank = high_rank;
+    p.delta_p = delta_p; p.delta_n = delta_n;
+
+    auto aligned16 = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
+    const bool vec = (d.space % 4 == 0) && aligned16(label_l) && aligned16(label_u) && aligned16(prob_l) &&
+                     aligned16(prob_u) && aligned16(low_mask) && aligned16(high_mask);
+    if (vec) arco::classify_kernel<4><<<L.n_tiles, 256, 0, st>>>(p);
+    else arco::classify_kernel<1><<<L.n_tiles, 256, 0, st>>>(p);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}

@@ -1,0 +1,70 @@
+// (a10) backward of the contrastive loss w.r.t. `rep`.
+//
+// The autograd contract forces a dense grad_rep [B,D,S]; the reference gets it from autograd's
+// index backward (zeros + index_put_(accumulate=True) for the rows picked at loss_helper_3d.py:377,
+// 455-457).  Here: one streaming zero-fill (P*D*e_g bytes written, the mandatory HBM term) and one
+// scatter of grad_out * grad_anchor into the <= C*Q anchor pixels.  Duplicated anchors (sampling
+// with replacement, trap 8) accumulate through atomics.
+#include "arco_common.cuh"
+
+namespace arco {
+
+__global__ void __launch_bounds__(256) fill_zero_kernel(uint4* __restrict__ dst, int64_t n16, unsigned char* tail,
+                                                         int tail_bytes) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = z;
+    if (blockIdx.x == 0 && threadIdx.x < tail_bytes) tail[threadIdx.x] = 0;
+}
+
+template <typename T>
+__device__ __forceinline__ void atomic_add_elem(T* p, float v);
+template <>
+__device__ __forceinline__ void atomic_add_elem<float>(float* p, float v) { atomicAdd(p, v); }
+template <>
+__device__ __forceinline__ void atomic_add_elem<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+    atomicAdd(p, __float2bfloat16(v));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) grad_scatter_kernel(const float* __restrict__ g_anchor,
+                                                            const int32_t* __restrict__ anchor_pix,
+                                                            const float* __restrict__ grad_out, T* __restrict__ grad_rep,
+                                                            int D, int64_t S) {
+    const int row = blockIdx.x;
+    const int pix = anchor_pix[row];
+    if (pix < 0) return;
+    const float go = *grad_out;
+    const int64_t b = pix / S, s = pix - b * S;
+    for (int d = threadIdx.x; d < D; d += blockDim.x)
+        atomic_add_elem<T>(grad_rep + (b * D + d) * S + s, go * g_anchor[(int64_t)row * D + d]);
+}
+
+}  // namespace arco
+
+extern "C" int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
+                                 const float* grad_out, void* grad_rep, void* stream) {
+    ARCO_REQUIRE(dims && grad_anchor && anchor_pix && grad_out && grad_rep, "arco_grad_scatter: NULL argument");
+    const arco_dims& d = *dims;
+    ARCO_REQUIRE(((uintptr_t)grad_rep & 15) == 0, "grad_rep must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t elems = ((int64_t)d.n_lab + d.n_unlab) * d.feat * d.space;
+    const int64_t bytes = elems * (d.rep_dtype == ARCO_BF16 ? 2 : 4);
+    const int64_t n16 = bytes / 16;
+    const int tail = (int)(bytes - n16 * 16);
+    int64_t blocks = (n16 + 256 * 8 - 1) / (256 * 8);
+    const int64_t cap = (int64_t)arco::sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    arco::fill_zero_kernel<<<(int)blocks, 256, 0, st>>>((uint4*)grad_rep, n16, (unsigned char*)grad_rep + n16 * 16, tail);
+    ARCO_LAUNCH_CHECK();
+    const int rows = d.classes * d.queries;
+    if (d.rep_dtype == ARCO_BF16)
+        arco::grad_scatter_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(grad_anchor, anchor_pix, grad_out,
+                                                                        (__nv_bfloat16*)grad_rep, d.feat, d.space);
+    else
+        arco::grad_scatter_kernel<float><<<rows, 128, 0, st>>>(grad_anchor, anchor_pix, grad_out, (float*)grad_rep,
+                                                                d.feat, d.space);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}

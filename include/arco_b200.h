@@ -1,0 +1,190 @@
+/*
+ * arco_b200.h -- C ABI of libarco_b200.so: the B200 (sm_100a) implementation of ARCO's
+ * stratified pixel/voxel contrastive loss.
+ *
+ * The reference has no FFI: its "plugin interface" is the Python function
+ *   compute_contra_memobank_loss(rep, label_l, label_u, prob_l, prob_u, low_mask, high_mask,
+ *                                memobank, queue_prtlis, queue_size, rep_teacher, ...)
+ * (/root/reference/code/loss_helper_3d.py:271-290 for 2-D images, loss_helper.py:442-461 for 3-D
+ * volumes), star-imported by train_arco_2d.py:24 / train_arco_3d.py:22 and called at
+ * train_arco_2d.py:394-398 / train_arco_3d.py:356-360.  arco_b200/contra.py keeps that Python
+ * signature and drives the entry points below through ctypes with raw device pointers.
+ *
+ * Conventions: every function returns 0 on success and a negative arco_status on failure, never
+ * throws, never synchronises the device, and launches on the cudaStream_t passed as `stream`
+ * (as void*).  All pointers are DEVICE pointers unless the name says `host_`.  Tensors are
+ * contiguous; `rep`-like tensors are [B, D, S] (channel-first, S = flattened H*W or H*W*Z, the
+ * layout the reference's trainers produce), probabilities [B_x, C, S] f32, masks [B, S] f32,
+ * one-hot labels [B_x, C, S] int64 or plain integer label maps [B_x, S] int64.
+ */
+#ifndef ARCO_B200_H_
+#define ARCO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ARCO_API __attribute__((visibility("default")))
+#else
+#define ARCO_API
+#endif
+
+#define ARCO_MAX_CLASSES 32
+#define ARCO_TILE 1024            /* pixels per counting tile (never straddles an image) */
+
+typedef enum arco_status {
+    ARCO_OK = 0,
+    ARCO_ERR_INVALID = -1,        /* bad argument (shape, alignment, NULL) */
+    ARCO_ERR_CUDA = -2,           /* a CUDA runtime call failed; see arco_last_error_string() */
+    ARCO_ERR_UNSUPPORTED = -3
+} arco_status;
+
+enum { ARCO_F32 = 0, ARCO_BF16 = 1 };
+enum { ARCO_LABEL_ONEHOT_I64 = 0, ARCO_LABEL_INDEX_I64 = 1 };
+/* sampler kinds: reference `func` argument, loss_helper_3d.py:327-338 */
+enum { ARCO_FUNC_UNIFORM = 0, ARCO_FUNC_SMC = 1, ARCO_FUNC_ASMC = 2 };
+/* device status bits (arco_plan.status) */
+enum { ARCO_ST_MULTI_HOT = 1, ARCO_ST_LABEL_RANGE = 2 };
+
+/* Problem geometry.  Mirrors the shapes at the reference call site. */
+typedef struct arco_dims {
+    int32_t n_lab;        /* labelled images, first in the batch (label_l.shape[0])       */
+    int32_t n_unlab;      /* unlabelled images                                             */
+    int32_t classes;      /* C  (label_l.shape[1]), <= ARCO_MAX_CLASSES                    */
+    int32_t feat;         /* D  (rep.shape[1]), multiple of 4                              */
+    int64_t space;        /* S  = prod(rep.shape[2:])                                      */
+    int32_t queries;      /* Q  num_queries                                                */
+    int32_t negatives;    /* N  num_negatives                                              */
+    int32_t rep_dtype;    /* ARCO_F32 | ARCO_BF16 for rep, rep_teacher and grad_rep        */
+    int32_t label_kind;   /* ARCO_LABEL_ONEHOT_I64 (reference call) | ARCO_LABEL_INDEX_I64 */
+} arco_dims;
+
+/* Byte offsets of the regions inside the caller-allocated workspace (256-B aligned base). */
+typedef struct arco_ws_layout {
+    int64_t total_bytes;
+    int64_t plan;          /* arco_plan                                   */
+    int64_t codes;         /* uint8  [B*S]   packed per-pixel class/flags */
+    int64_t tile_flagged;  /* uint32 [NT]                                 */
+    int64_t cnt_anchor;    /* uint32 [C][NT]                              */
+    int64_t cnt_key;       /* uint32 [C][NT]                              */
+    int64_t off_anchor;    /* uint32 [C][NT+1] exclusive scan             */
+    int64_t off_key;       /* uint32 [C][NT+1]                            */
+    int64_t partials;      /* float  [rows][C][D] prototype partial sums  */
+    int64_t loss_parts;    /* float  [C*Q]                                */
+    int64_t sample_scratch;/* int32  sampler staging                      */
+    int32_t n_tiles;       /* NT = B * ceil(S / ARCO_TILE)                */
+    int32_t tiles_per_image;
+    int32_t partial_rows;
+    int32_t reserved;
+} arco_ws_layout;
+
+/* Device-resident step summary written by arco_scan_plan (and read by every later stage).
+ * The Python layer copies it to pinned host memory asynchronously to serve `new_keys`,
+ * `memobank[c][0].shape[0]` and `queue_prtlis[c][0]` lazily (reference: loss_helper_3d.py:19-32,
+ * :404-415). */
+typedef struct arco_plan {
+    uint32_t lv_count[ARCO_MAX_CLASSES];     /* low-valid pixels per class  (seg_num_list, :413-415) */
+    uint32_t n_anchor[ARCO_MAX_CLASSES];     /* anchor candidates per class (len(seg_feat_low_entropy_list[c])) */
+    uint32_t n_key[ARCO_MAX_CLASSES];        /* new_keys[c]                                           */
+    int32_t  n_valid;                        /* valid_seg = len(valid_classes)                        */
+    int32_t  valid_class[ARCO_MAX_CLASSES];  /* valid_classes[pos]                                    */
+    int32_t  slot_active[ARCO_MAX_CLASSES];  /* LOOP-2 position pos runs (not skipped as "easy")      */
+    int32_t  bank_write_base[ARCO_MAX_CLASSES]; /* ring position of this call's first key             */
+    int32_t  bank_skip[ARCO_MAX_CLASSES];    /* leading keys dropped because n_key > capacity         */
+    int32_t  bank_len[ARCO_MAX_CLASSES];     /* bank rows after this call                             */
+    int32_t  bank_head[ARCO_MAX_CLASSES];    /* ring position of logical row 0 after this call        */
+    int64_t  queue_ptr[ARCO_MAX_CLASSES];    /* reference pointer bookkeeping (:24-30)                */
+    float    inv_scale;                      /* 1 / (Q * valid_seg), 0 when valid_seg <= 1            */
+    uint32_t status;                         /* ARCO_ST_* bits                                        */
+    uint32_t scan_done;                      /* internal tickets                                      */
+    uint32_t loss_done;
+} arco_plan;
+
+/* Device-resident ring-buffer memory bank (replaces the CPU list memobank[c] = [tensor[n,D]],
+ * train_arco_2d.py:147-154).  Row r of class c lives at rows[(row_off[c] + (head[c]+r) % cap[c]) * D]. */
+typedef struct arco_bank {
+    float*   rows;                            /* [sum(cap), D] f32                    */
+    int32_t* head;                            /* [C] device, updated by arco_scan_plan */
+    int32_t* len;                             /* [C] device                            */
+    int64_t* queue_ptr;                       /* [C] device                            */
+    int32_t  cap[ARCO_MAX_CLASSES];           /* queue_size[c]                         */
+    int64_t  row_off[ARCO_MAX_CLASSES];
+} arco_bank;
+
+ARCO_API const char* arco_version(void);
+ARCO_API const char* arco_last_error_string(void);
+
+/* Workspace geometry for `dims` on the current device. */
+ARCO_API int arco_workspace_layout(const arco_dims* dims, arco_ws_layout* out);
+
+/* (a1) drop-in for the trainers' label_onehot (train_arco_2d.py:492-498): int64 labels [B,S] ->
+ * float32 one-hot [B,C,S], ignore label -1 -> class 0. */
+ARCO_API int arco_label_onehot(const int64_t* labels, float* out, int64_t batch, int32_t classes, int64_t space,
+                      void* stream);
+
+/* (a1-a3) fused one-hot decode, confidence thresholds and teacher-rank test -> per-pixel code byte
+ * (bits 0-4 class, bit 5 low-valid, bit 6 anchor candidate, bit 7 negative key), per-tile per-class
+ * anchor/key counts and per-class low-valid totals.  Replaces loss_helper_3d.py:341-342,352-374,
+ * 388-401,413-415.  `label_*` are one-hot int64 [B_x,C,S] or index maps [B_x,S] per dims->label_kind. */
+ARCO_API int arco_classify_count(const arco_dims* dims,
+                        const int64_t* label_l, const int64_t* label_u,
+                        const float* prob_l, const float* prob_u,
+                        const float* low_mask, const float* high_mask,
+                        float delta_p, float delta_n, int32_t low_rank, int32_t high_rank,
+                        void* workspace, void* stream);
+
+/* (a4,a6) exclusive scans of the tile counts (ordered compaction offsets), valid-class list,
+ * slot activity, ring-buffer bookkeeping (dequeue_and_enqueue, loss_helper_3d.py:12-32). */
+ARCO_API int arco_scan_plan(const arco_dims* dims, const arco_bank* bank, void* workspace, void* stream);
+
+/* Multi-GPU only: recompute valid_classes / slot activity from the all-reduced
+ * proto_sums[C, D+1] counts so every rank runs the same LOOP-2 positions. */
+ARCO_API int arco_replan_global(const arco_dims* dims, const double* proto_sums, void* workspace, void* stream);
+
+/* (a5,a6) one pass over rep_teacher: per-class feature sums of low-valid pixels (prototype numerators,
+ * :380-384) and ordered tail-only enqueue of the negative keys into the ring (:403-411).
+ * proto_sums: float64 [C, D+1] = (sum over pixels, count) -- the buffer a multi-GPU caller all-reduces. */
+ARCO_API int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher, const arco_bank* bank,
+                       double* proto_sums, void* workspace, void* stream);
+
+/* (a7) in-kernel Philox restatement of grid_monte_carlo_sample / grid_as_monte_carlo_sample and their
+ * fallbacks (loss_helper_3d.py:35-268): idx_anchor int32 [C,Q], idx_neg int32 [C,Q*N], for every
+ * active LOOP-2 position. */
+ARCO_API int arco_sample(const arco_dims* dims, int32_t func, uint64_t seed, uint64_t step,
+                int32_t* idx_anchor, int32_t* idx_neg, void* workspace, void* stream);
+
+/* Stand-alone sampler: out[i] for i < shape drawn exactly like the reference sampler `func` called
+ * with (high, shape).  Used by the drop-in sampler functions and the distribution tests. */
+ARCO_API int arco_sample_one(int32_t func, int64_t high, int64_t shape, uint64_t seed, uint64_t stream_id,
+                    int32_t* out, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* (a8-a10) anchor rank-select + gather, memory-bank negative gather, cosine similarity, temperature
+ * scaled InfoNCE and its gradient w.r.t. the anchor rows (loss_helper_3d.py:435-511).
+ * Outputs: loss f32[1]; grad_anchor f32 [C,Q,D] (already scaled by 1/(Q*valid_seg));
+ * anchor_pix int32 [C,Q] flat pixel id b*S+s or -1; logits f32 [C,Q,1+N] (optional, may be NULL). */
+ARCO_API int arco_infonce(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
+                 const int32_t* idx_anchor, const int32_t* idx_neg, float temp,
+                 float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits,
+                 void* workspace, void* stream);
+
+/* (a10) backward: grad_rep[B,D,S] = 0, then += grad_out * grad_anchor at the anchor pixels
+ * (duplicates accumulate, trap 8).  grad_out: device f32 scalar. */
+ARCO_API int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
+                      const float* grad_out, void* grad_rep, void* stream);
+
+/* Parity / inspection helpers (not on the hot path). */
+/* kind: 0 anchor candidates, 1 negative keys, 2 low-valid; writes the raster-ordered flat pixel ids of
+ * class `cls` to out (capacity out_cap) and the count to *count_dev. */
+ARCO_API int arco_export_list(const arco_dims* dims, int32_t kind, int32_t cls, int32_t* out, int64_t out_cap,
+                     uint32_t* count_dev, void* workspace, void* stream);
+/* Copy class `cls` of the ring to `out` in logical FIFO order ([cap, D], rows >= len untouched). */
+ARCO_API int arco_bank_read(const arco_bank* bank, int32_t cls, int32_t feat, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARCO_B200_H_ */
