@@ -44,51 +44,61 @@ __device__ __forceinline__ float load_scalar(const __nv_bfloat16* p) {
 }
 
 // NCH: 16-byte chunks per staged pixel row (D-chunk = 4*NCH dims).  8 warps, 256 threads.
+// Each warp carries PXS = 32/NCH independent pixel STREAMS (a stream = NCH lanes, lane <-> 4 feature dims);
+// stream s owns pixels [s*R, (s+1)*R) of every staged sub-tile and a private accumulator copy in shared
+// memory, so there are no atomics and no cross-lane combines.  Consecutive pixels of one class are summed
+// in registers and flushed on a class change (run merging).
 template <typename T, int NCH>
 __global__ void __launch_bounds__(256) proto_enqueue_kernel(ProtoParams p) {
-    constexpr int PXS = 32 / NCH;            // pixels processed per warp step
+    constexpr int PXS = 32 / NCH;            // streams per warp
+    constexpr int NS = 8 * PXS;              // streams per CTA
     constexpr int SP = 2048 / NCH;           // pixels per staged sub-tile (32 KB of fp32)
     constexpr int NSUB = ARCO_TILE / SP;
-    constexpr int WR = SP / 8;               // pixel range per warp
+    constexpr int R = SP / NS;               // pixels per stream per sub-tile (= 8)
     constexpr int PER16 = Elem<T>::PER16;
     constexpr int ROT = (PER16 == 4) ? 2 : 3;  // rotation granularity keeps the 16-B stores conflict free
     constexpr int BLOCKS = NCH * (SP / PER16) / 256;
-    static_assert(BLOCKS >= 1, "tile too small");
+    static_assert(BLOCKS >= 1 && R == 8, "tile geometry");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* tile = reinterpret_cast<float4*>(smem_raw);                       // [SP][NCH]
-    float4* acc = tile + SP * NCH;                                            // [8][C][NCH]
-    uint32_t* sc_words = reinterpret_cast<uint32_t*>(acc + 8 * p.C * NCH);    // [SP/4]
+    float4* acc = tile + SP * NCH;                                            // [NS][C][NCH]
+    uint32_t* sc_words = reinterpret_cast<uint32_t*>(acc + NS * p.C * NCH);   // [SP/4]
     uint32_t* wrun = sc_words + SP / 4;                                       // [8][32]
     __shared__ int32_t s_skip[ARCO_MAX_CLASSES], s_base[ARCO_MAX_CLASSES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = lane / NCH, ci = lane % NCH;
+    const int stream = warp * PXS + slot;
     const int C = p.C, D = p.D;
     const int64_t S = p.S;
     const int dchunk = blockIdx.x % p.NDC, grp = blockIdx.x / p.NDC, ngrp = gridDim.x / p.NDC;
     const int d0 = dchunk * NCH * 4;
     const int nch_real = min(NCH, (D - d0) / 4);
-    const uint8_t* sc = reinterpret_cast<const uint8_t*>(sc_words);
+    const bool lane_on = ci < nch_real;
     const T* rep = reinterpret_cast<const T*>(p.rep_t);
+    float4* my_acc = acc + (size_t)stream * C * NCH + ci;
 
-    for (int i = tid; i < 8 * C * NCH; i += 256) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < NS * C * NCH; i += 256) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < ARCO_MAX_CLASSES) {
         s_skip[tid] = p.plan->bank_skip[tid];
         s_base[tid] = p.plan->bank_write_base[tid];
     }
     __syncthreads();
 
+    int cur = -1;                                                            // class of the open run
+    float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+
     for (int t = grp; t < p.NT; t += ngrp) {
-        if (p.tile_flagged[t] == 0) continue;                      // CTA-uniform
+        if (p.tile_flagged[t] == 0) continue;                                // CTA-uniform
         const int b = t / p.tpi;
         const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
         if (lane < C) wrun[warp * 32 + lane] = p.off_key[(int64_t)lane * (p.NT + 1) + t];
         for (int sub = 0; sub < NSUB; ++sub) {
             const int64_t s_sub = s_tile + (int64_t)sub * SP;
-            if (s_sub >= S) break;                                 // CTA-uniform
+            if (s_sub >= S) break;                                           // CTA-uniform
             const int64_t gpx = (int64_t)b * S + s_sub;
-            // ---- stage the code bytes of this sub-tile; find out whether anything is flagged ----
+            // ---- stage the code bytes of this sub-tile; find out what is flagged ----
             uint32_t cw = 0;
             if (tid < SP / 4) {
                 const int64_t s4 = s_sub + 4 * tid;
@@ -101,7 +111,7 @@ __global__ void __launch_bounds__(256) proto_enqueue_kernel(ProtoParams p) {
                 }
                 sc_words[tid] = cw;
             }
-            const int any = __syncthreads_or(cw & 0xA0A0A0A0u);     // low-valid or key anywhere?
+            const int any = __syncthreads_or(cw & 0xA0A0A0A0u);     // boolean: low-valid or key anywhere?
             if (any) {
                 // ---- global -> registers -> transposed, swizzled shared tile ----
                 if (p.vec_ok) {
@@ -122,22 +132,22 @@ __global__ void __launch_bounds__(256) proto_enqueue_kernel(ProtoParams p) {
                     for (int it = 0; it < BLOCKS; ++it) {
                         const int id = it * 256 + tid;
                         const int pg = id % (SP / PER16), bc = id / (SP / PER16);
+                        const uint32_t* r0 = &raw[it][0].x; const uint32_t* r1 = &raw[it][1].x;
+                        const uint32_t* r2 = &raw[it][2].x; const uint32_t* r3 = &raw[it][3].x;
 #pragma unroll
                         for (int k = 0; k < PER16; ++k) {
                             float4 v;
                             if (PER16 == 4) {
-                                const uint32_t* r0 = &raw[it][0].x; const uint32_t* r1 = &raw[it][1].x;
-                                const uint32_t* r2 = &raw[it][2].x; const uint32_t* r3 = &raw[it][3].x;
                                 v = make_float4(__uint_as_float(r0[k]), __uint_as_float(r1[k]),
                                                 __uint_as_float(r2[k]), __uint_as_float(r3[k]));
                             } else {
-                                const uint32_t* r0 = &raw[it][0].x; const uint32_t* r1 = &raw[it][1].x;
-                                const uint32_t* r2 = &raw[it][2].x; const uint32_t* r3 = &raw[it][3].x;
-                                const int w = k >> 1, sh = (k & 1) * 16;
-                                v = make_float4(bf16_bits_to_float((r0[w] >> sh) & 0xffffu),
-                                                bf16_bits_to_float((r1[w] >> sh) & 0xffffu),
-                                                bf16_bits_to_float((r2[w] >> sh) & 0xffffu),
-                                                bf16_bits_to_float((r3[w] >> sh) & 0xffffu));
+                                const int w = k >> 1;
+                                if (k & 1)
+                                    v = make_float4(__uint_as_float(r0[w] & 0xffff0000u), __uint_as_float(r1[w] & 0xffff0000u),
+                                                    __uint_as_float(r2[w] & 0xffff0000u), __uint_as_float(r3[w] & 0xffff0000u));
+                                else
+                                    v = make_float4(__uint_as_float(r0[w] << 16), __uint_as_float(r1[w] << 16),
+                                                    __uint_as_float(r2[w] << 16), __uint_as_float(r3[w] << 16));
                             }
                             const int pxl = pg * PER16 + k;
                             tile[pxl * NCH + ((bc + (pxl >> ROT)) & (NCH - 1))] = v;
@@ -158,111 +168,357 @@ __global__ void __launch_bounds__(256) proto_enqueue_kernel(ProtoParams p) {
             }
             __syncthreads();
             if (any) {
-                const int px0 = warp * WR;                                  // this warp's pixel range
-                const uint32_t mycode = lane < WR ? sc[px0 + lane] : 0u;
-                uint32_t lvmask = __ballot_sync(0xffffffffu, mycode & CODE_LV);
-                uint32_t keymask = __ballot_sync(0xffffffffu, mycode & CODE_KEY);
-                // ---- prototype accumulation: PXS pixels per step, lanes own chunk ci ----
-                while (lvmask) {
-                    int pj = -1;
-#pragma unroll
-                    for (int j = 0; j < PXS; ++j) {
-                        const int q = lvmask ? __ffs(lvmask) - 1 : -1;
-                        if (lvmask) lvmask &= lvmask - 1;
-                        if (j == slot) pj = q;
-                    }
-                    const uint32_t code = __shfl_sync(0xffffffffu, mycode, pj < 0 ? 0 : pj);
-                    int cls = pj < 0 ? -1 : (int)(code & CODE_CLS_MASK);
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (pj >= 0 && ci < nch_real) {
-                        const int pxl = px0 + pj;
-                        v = tile[pxl * NCH + ((ci + (pxl >> ROT)) & (NCH - 1))];
-                    }
-                    bool leader = cls >= 0;
-                    if (PXS > 1) {
-                        // fold slots that hit the same class into the lowest such slot (fixed order)
-#pragma unroll
-                        for (int j = 0; j < PXS; ++j) {
-                            const int src = j * NCH + ci;
-                            const int oc = __shfl_sync(0xffffffffu, cls, src);
-                            const float ox = __shfl_sync(0xffffffffu, v.x, src);
-                            const float oy = __shfl_sync(0xffffffffu, v.y, src);
-                            const float oz = __shfl_sync(0xffffffffu, v.z, src);
-                            const float ow = __shfl_sync(0xffffffffu, v.w, src);
-                            if (oc == cls && cls >= 0) {
-                                if (j < slot) leader = false;
-                                else if (j > slot) { v.x += ox; v.y += oy; v.z += oz; v.w += ow; }
+                // what kind of work does the sub-tile hold (every warp derives the same answer)
+                uint32_t agg = 0;
+                for (int wq = lane; wq < SP / 4; wq += 32) agg |= sc_words[wq];
+                const int flags = (__any_sync(0xffffffffu, agg & 0x20202020u) ? 1 : 0) |
+                                  (__any_sync(0xffffffffu, agg & 0x80808080u) ? 2 : 0);
+                // ---- this stream's 8 code bytes ----
+                const int px0 = stream * R;
+                const uint32_t w0 = sc_words[px0 / 4], w1 = sc_words[px0 / 4 + 1];
+                if (flags & 1) {
+                    // prototype accumulation: walk the low-valid pixels of the stream, merge same-class runs
+                    uint32_t lv = ((w0 >> 5) & 1u) | ((w0 >> 12) & 2u) | ((w0 >> 19) & 4u) | ((w0 >> 26) & 8u) |
+                                  ((w1 << 4 >> 5) & 16u) | ((w1 >> 8) & 32u) | ((w1 >> 15) & 64u) | ((w1 >> 22) & 128u);
+                    while (lv) {
+                        const int k = __ffs(lv) - 1;
+                        lv &= lv - 1;
+                        const uint32_t wsel = (k & 4) ? w1 : w0;
+                        const int cls = (int)((wsel >> (8 * (k & 3))) & CODE_CLS_MASK);
+                        const int pxl = px0 + k;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (lane_on) v = tile[pxl * NCH + ((ci + (pxl >> ROT)) & (NCH - 1))];
+                        if (cls == cur) {
+                            racc.x += v.x; racc.y += v.y; racc.z += v.z; racc.w += v.w;
+                        } else {
+                            if (cur >= 0 && lane_on) {
+                                float4* a = my_acc + (size_t)cur * NCH;
+                                float4 o = *a;
+                                o.x += racc.x; o.y += racc.y; o.z += racc.z; o.w += racc.w;
+                                *a = o;
                             }
+                            cur = cls;
+                            racc = v;
                         }
                     }
-                    if (leader && ci < nch_real) {
-                        float4* a = acc + ((warp * C + cls) * NCH + ci);
-                        float4 o = *a;
-                        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
-                        *a = o;
-                    }
-                    __syncwarp();
                 }
-                // ---- negative keys: ordered ring-buffer enqueue (FIFO order == raster order) ----
-                if (__any_sync(0xffffffffu, keymask != 0)) {
-                    uint32_t km = keymask;
-                    while (km) {
-                        const int pk = __ffs(km) - 1;
-                        km &= km - 1;
-                        const int cls = (int)(__shfl_sync(0xffffffffu, mycode, pk) & CODE_CLS_MASK);
-                        const int target = px0 + pk;
-                        // keys of the same class earlier in this sub-tile
+                if (flags & 2) {
+                    // ---- negative keys: ordered ring-buffer enqueue (FIFO order == raster order) ----
+                    uint32_t kb = ((w0 >> 7) & 1u) | ((w0 >> 14) & 2u) | ((w0 >> 21) & 4u) | ((w0 >> 28) & 8u) |
+                                  ((w1 << 4 >> 7) & 16u) | ((w1 >> 10) & 32u) | ((w1 >> 17) & 64u) | ((w1 >> 24) & 128u);
+                    while (__any_sync(0xffffffffu, kb != 0)) {               // warp-uniform trip count
+                        const bool have = kb != 0;
+                        const int k = have ? __ffs(kb) - 1 : 0;
+                        if (have) kb &= kb - 1;
+                        const uint32_t wsel = (k & 4) ? w1 : w0;
+                        const int cls = (int)((wsel >> (8 * (k & 3))) & CODE_CLS_MASK);
+                        const int target = px0 + k;
+                        // keys of the same class earlier in this sub-tile (counted by the stream's NCH lanes)
                         int mine = 0;
-                        for (int wq = lane; wq < SP / 4; wq += 32) {
+                        for (int wq = ci; wq < SP / 4; wq += NCH) {
                             const uint32_t w4 = sc_words[wq];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t cd = (w4 >> (8 * k)) & 0xffu;
-                                mine += ((cd & CODE_KEY) && (int)(cd & CODE_CLS_MASK) == cls && (4 * wq + k) < target);
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t cd = (w4 >> (8 * q)) & 0xffu;
+                                mine += ((cd & CODE_KEY) && (int)(cd & CODE_CLS_MASK) == cls && (4 * wq + q) < target);
                             }
                         }
-                        const int before = __reduce_add_sync(0xffffffffu, mine);
-                        const int64_t ord = (int64_t)wrun[warp * 32 + cls] + before;
-                        if (ord >= s_skip[cls] && lane < nch_real) {
-                            const int64_t pos = ((int64_t)s_base[cls] + ord) % p.cap[cls];
-                            const float4 v = tile[target * NCH + ((lane + (target >> ROT)) & (NCH - 1))];
-                            float4* dst = reinterpret_cast<float4*>(p.bank_rows + (p.row_off[cls] + pos) * D + d0) + lane;
-                            *dst = v;
+#pragma unroll
+                        for (int o = NCH / 2; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+                        if (have && lane_on) {
+                            const int64_t ord = (int64_t)wrun[warp * 32 + cls] + mine;
+                            if (ord >= s_skip[cls]) {
+                                const int64_t pos = ((int64_t)s_base[cls] + ord) % p.cap[cls];
+                                const float4 v = tile[target * NCH + ((ci + (target >> ROT)) & (NCH - 1))];
+                                reinterpret_cast<float4*>(p.bank_rows + (p.row_off[cls] + pos) * D + d0)[ci] = v;
+                            }
+                        }
+                    }
+                    // advance the per-warp running key ordinals by this sub-tile's keys (all warps agree)
+                    __syncwarp();
+                    for (int wq = lane; wq < SP / 4; wq += 32) {
+                        const uint32_t w4 = sc_words[wq];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t cd = (w4 >> (8 * q)) & 0xffu;
+                            const bool is_key = cd & CODE_KEY;
+                            const uint32_t peers = __match_any_sync(0xffffffffu, is_key ? (cd & CODE_CLS_MASK) : 0xffffu);
+                            if (is_key && (__ffs(peers) - 1) == lane) wrun[warp * 32 + (cd & CODE_CLS_MASK)] += __popc(peers);
+                            __syncwarp();
                         }
                     }
                 }
-            }
-            // ---- advance the per-warp running key ordinals by this sub-tile's keys (all warps agree) ----
-            if (any) {
-                __syncwarp();
-                for (int wq = lane; wq < SP / 4; wq += 32) {
-                    const uint32_t w4 = sc_words[wq];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t cd = (w4 >> (8 * k)) & 0xffu;
-                        const bool is_key = cd & CODE_KEY;
-                        const uint32_t peers = __match_any_sync(__activemask(), is_key ? (cd & CODE_CLS_MASK) : 0xffffu);
-                        if (is_key && (__ffs(peers) - 1) == lane) wrun[warp * 32 + (cd & CODE_CLS_MASK)] += __popc(peers);
-                        __syncwarp(__activemask());
-                    }
-                }
-                __syncwarp();
             }
             __syncthreads();
         }
     }
+    // ---- close the open runs, fold the stream-private accumulators (fixed order), publish the partial row ----
+    if (cur >= 0 && lane_on) {
+        float4* a = my_acc + (size_t)cur * NCH;
+        float4 o = *a;
+        o.x += racc.x; o.y += racc.y; o.z += racc.z; o.w += racc.w;
+        *a = o;
+    }
     __syncthreads();
-    // ---- fold the 8 warp-private accumulators (fixed order) and publish this CTA's partial row ----
     for (int i = tid; i < C * NCH; i += 256) {
         const int c = i / NCH, k = i % NCH;
         if (k >= nch_real) continue;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const float4 a = acc[(w * C + c) * NCH + k];
+#pragma unroll 4
+        for (int w = 0; w < NS; ++w) {
+            const float4 a = acc[((size_t)w * C + c) * NCH + k];
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
         *reinterpret_cast<float4*>(p.partials + ((int64_t)grp * C + c) * D + d0 + 4 * k) = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 8-dims-per-lane variant (C <= 8): each lane owns 8 feature dims of its stream's pixel, which halves
+// the per-pixel bookkeeping per element.  fp32 data is staged as two float4 planes, bf16 data stays
+// PACKED in shared memory (one uint4 = 8 dims) and is widened only when it is accumulated.
+// D-chunk = 8*NCH dims; tile = 32 KB; stream-private accumulators = 8 KB * C.
+// ---------------------------------------------------------------------------------------------------
+template <typename T> struct Wide;
+template <> struct Wide<float> { static constexpr int LW = 2, PER16 = 4; };
+template <> struct Wide<__nv_bfloat16> { static constexpr int LW = 1, PER16 = 8; };
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
+    constexpr int LW = Wide<T>::LW;          // 16-byte words per (pixel, lane)
+    constexpr int PER16 = Wide<T>::PER16;    // pixels per 16-byte global load
+    constexpr int PXS = 32 / NCH;
+    constexpr int NS = 8 * PXS;
+    constexpr int SP = 2048 / (NCH * LW);    // pixels per staged sub-tile (32 KB)
+    constexpr int NSUB = ARCO_TILE / SP;
+    constexpr int R = SP / NS;               // pixels per stream per sub-tile (4 for fp32, 8 for bf16)
+    constexpr int RW = R / 4;                // code words per stream
+    constexpr int ROT = (PER16 == 4) ? 2 : 3;
+    constexpr int PLANE = SP * NCH;          // uint4 elements per plane
+    static_assert(NCH * (SP / PER16) == 256, "one (8 rows x PER16 px) block per thread");
+    static_assert(R == 4 || R == 8, "stream geometry");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* tile = reinterpret_cast<uint4*>(smem_raw);                         // [LW][SP][NCH]
+    float4* acc = reinterpret_cast<float4*>(tile + LW * PLANE);               // [2][NS][C][NCH]  (dims 0-3 / 4-7 planes)
+    uint32_t* sc_tile = reinterpret_cast<uint32_t*>(acc + 2 * NS * p.C * NCH);   // [2][256] code words of a tile, double buffered
+    uint32_t* wrun = sc_tile + 2 * (ARCO_TILE / 4);                            // [8][32]
+    __shared__ int32_t s_skip[ARCO_MAX_CLASSES], s_base[ARCO_MAX_CLASSES], s_cap[ARCO_MAX_CLASSES];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = lane / NCH, ci = lane % NCH;
+    const int stream = warp * PXS + slot;
+    const int C = p.C, D = p.D;
+    const int64_t S = p.S;
+    const int dchunk = blockIdx.x % p.NDC, grp = blockIdx.x / p.NDC, ngrp = gridDim.x / p.NDC;
+    const int d0 = dchunk * NCH * 8;
+    const int dreal = min(NCH * 8, D - d0);                                   // multiple of 4
+    const int rows_on = max(0, min(8, dreal - 8 * ci));                       // 0, 4 or 8 real dims in this lane
+    const T* rep = reinterpret_cast<const T*>(p.rep_t);
+    const int acc_plane = NS * C * NCH;
+    float4* my_acc = acc + (size_t)stream * C * NCH + ci;
+
+    // loader role of this thread: rows [8*bc, 8*bc+8) x pixels [pg*PER16, +PER16) of every sub-tile
+    const int pg = tid % (SP / PER16), bc = tid / (SP / PER16);
+    const int ld_rows = max(0, min(8, dreal - 8 * bc));
+
+    for (int i = tid; i < 2 * acc_plane; i += 256) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < ARCO_MAX_CLASSES) {
+        s_skip[tid] = p.plan->bank_skip[tid];
+        s_base[tid] = p.plan->bank_write_base[tid];
+        s_cap[tid] = p.cap[tid];
+    }
+
+    int cur = -1;
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+
+    auto flush = [&]() {
+        if (cur >= 0 && rows_on > 0) {
+            float4* a = my_acc + (size_t)cur * NCH;
+            float4 o = a[0];
+            o.x += ra.x; o.y += ra.y; o.z += ra.z; o.w += ra.w;
+            a[0] = o;
+            if (rows_on > 4) {
+                o = a[acc_plane];
+                o.x += rb.x; o.y += rb.y; o.z += rb.z; o.w += rb.w;
+                a[acc_plane] = o;
+            }
+        }
+    };
+    // the 8 dims of (pixel pxl, this lane) as two float4
+    auto fetch = [&](int pxl, float4& lo, float4& hi) {
+        const int idx = pxl * NCH + ((ci + (pxl >> ROT)) & (NCH - 1));
+        if (LW == 2) {
+            const uint4 u = tile[idx], w = tile[PLANE + idx];
+            lo = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+            hi = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+        } else {
+            const uint4 u = tile[idx];        // 8 packed bf16: dims (0,1) (2,3) (4,5) (6,7)
+            lo = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                             __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+            hi = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u),
+                             __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+        }
+    };
+
+    // ---- software pipeline over this CTA's (tile, sub-tile) sequence ----
+    // stage A (issue):   global loads of a sub-tile into registers (+ the tile's 1024 code bytes at sub 0)
+    // stage B (commit):  registers -> transposed, swizzled shared tile
+    // stage C (compute): per-stream accumulation and key enqueue
+    // The loads of sub-tile i+1 are in flight while sub-tile i is computed.
+    int t_next = grp, sub_next = 0, par_next = 0;           // iterator of the issue stage
+    auto skip_unflagged = [&]() {
+        while (t_next < p.NT && p.tile_flagged[t_next] == 0) t_next += ngrp;
+    };
+    skip_unflagged();
+    uint4 raw[8];
+    uint32_t cw_reg = 0;
+    int t_ld = -1, sub_ld = 0, par_ld = 0;                   // what `raw` currently holds
+    auto issue = [&]() {
+        t_ld = t_next; sub_ld = sub_next; par_ld = par_next;
+        if (t_next >= p.NT) { t_ld = -1; return; }
+        const int b = t_next / p.tpi;
+        const int64_t s_tile = (int64_t)(t_next % p.tpi) * ARCO_TILE;
+        const int64_t s = s_tile + (int64_t)sub_next * SP + (int64_t)pg * PER16;
+        const T* rowp = rep + ((int64_t)b * D + d0 + 8 * bc) * S + s;
+        const bool in = s < S;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            raw[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < ld_rows && in) raw[j] = ldg_nc_u4(rowp + (int64_t)j * S);
+        }
+        if (sub_next == 0) {
+            const int64_t s4 = s_tile + 4 * tid;
+            cw_reg = s4 < S ? *reinterpret_cast<const uint32_t*>(p.codes + (int64_t)b * S + s4) : 0u;
+        }
+        // advance the iterator
+        ++sub_next;
+        if (sub_next == NSUB || s_tile + (int64_t)sub_next * SP >= S) {
+            sub_next = 0;
+            par_next ^= 1;
+            t_next += ngrp;
+            skip_unflagged();
+        }
+    };
+    issue();
+    __syncthreads();                                         // accumulators zeroed, s_* visible
+    while (t_ld >= 0) {
+        const int t = t_ld, sub = sub_ld, par = par_ld;
+        // ---- stage B: commit registers to the shared tile ----
+#pragma unroll
+        for (int k = 0; k < PER16; ++k) {
+            const int pxl = pg * PER16 + k;
+            const int idx = pxl * NCH + ((bc + (pxl >> ROT)) & (NCH - 1));
+            const uint32_t* r0 = &raw[0].x; const uint32_t* r1 = &raw[1].x; const uint32_t* r2 = &raw[2].x;
+            const uint32_t* r3 = &raw[3].x; const uint32_t* r4 = &raw[4].x; const uint32_t* r5 = &raw[5].x;
+            const uint32_t* r6 = &raw[6].x; const uint32_t* r7 = &raw[7].x;
+            if (LW == 2) {
+                tile[idx] = make_uint4(r0[k], r1[k], r2[k], r3[k]);
+                tile[PLANE + idx] = make_uint4(r4[k], r5[k], r6[k], r7[k]);
+            } else {
+                const int w = k >> 1;
+                const uint32_t sel = (k & 1) ? 0x7632u : 0x5410u;             // pick the k-th bf16 of two rows
+                tile[idx] = make_uint4(__byte_perm(r0[w], r1[w], sel), __byte_perm(r2[w], r3[w], sel),
+                                       __byte_perm(r4[w], r5[w], sel), __byte_perm(r6[w], r7[w], sel));
+            }
+        }
+        if (sub == 0) sc_tile[par * (ARCO_TILE / 4) + tid] = cw_reg;
+        __syncthreads();
+        // ---- stage A for the next sub-tile: loads stay in flight during the compute below ----
+        issue();
+        // ---- stage C ----
+        const uint32_t* sc_words = sc_tile + par * (ARCO_TILE / 4) + sub * (SP / 4);
+        if (sub == 0 && lane < C) wrun[warp * 32 + lane] = p.off_key[(int64_t)lane * (p.NT + 1) + t];
+        __syncwarp();
+        uint32_t agg = 0;
+        for (int wq = lane; wq < SP / 4; wq += 32) agg |= sc_words[wq];
+        const bool has_lv = __any_sync(0xffffffffu, agg & 0x20202020u);
+        const bool has_key = __any_sync(0xffffffffu, agg & 0x80808080u);
+        const int px0 = stream * R;
+        const uint32_t w0 = sc_words[px0 / 4];
+        const uint32_t w1 = RW == 2 ? sc_words[px0 / 4 + 1] : 0u;
+        if (has_lv) {
+            uint32_t lv = ((w0 >> 5) & 1u) | ((w0 >> 12) & 2u) | ((w0 >> 19) & 4u) | ((w0 >> 26) & 8u) |
+                          ((w1 >> 1) & 16u) | ((w1 >> 8) & 32u) | ((w1 >> 15) & 64u) | ((w1 >> 22) & 128u);
+            while (lv) {
+                const int k = __ffs(lv) - 1;
+                lv &= lv - 1;
+                const uint32_t wsel = (k & 4) ? w1 : w0;
+                const int cls = (int)((wsel >> (8 * (k & 3))) & CODE_CLS_MASK);
+                float4 lo, hi;
+                fetch(px0 + k, lo, hi);
+                if (cls != cur) {
+                    flush();
+                    cur = cls;
+                    ra = lo; rb = hi;
+                } else {
+                    ra.x += lo.x; ra.y += lo.y; ra.z += lo.z; ra.w += lo.w;
+                    rb.x += hi.x; rb.y += hi.y; rb.z += hi.z; rb.w += hi.w;
+                }
+            }
+        }
+        if (has_key) {
+            uint32_t kb = ((w0 >> 7) & 1u) | ((w0 >> 14) & 2u) | ((w0 >> 21) & 4u) | ((w0 >> 28) & 8u) |
+                          ((w1 >> 3) & 16u) | ((w1 >> 10) & 32u) | ((w1 >> 17) & 64u) | ((w1 >> 24) & 128u);
+            while (__any_sync(0xffffffffu, kb != 0)) {                       // warp-uniform trip count
+                const bool have = kb != 0;
+                const int k = have ? __ffs(kb) - 1 : 0;
+                if (have) kb &= kb - 1;
+                const uint32_t wsel = (k & 4) ? w1 : w0;
+                const int cls = (int)((wsel >> (8 * (k & 3))) & CODE_CLS_MASK);
+                const int target = px0 + k;
+                // keys of the same class earlier in this sub-tile (counted by the stream's NCH lanes)
+                const uint32_t want = CODE_KEY | (uint32_t)cls;
+                int mine = 0;
+                for (int wq = ci; wq < SP / 4; wq += NCH) {
+                    const uint32_t w4 = sc_words[wq];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        mine += (((w4 >> (8 * q)) & (CODE_KEY | CODE_CLS_MASK)) == want) && (4 * wq + q) < target;
+                }
+#pragma unroll
+                for (int o = NCH / 2; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+                if (have && rows_on > 0) {
+                    const uint32_t ord = wrun[warp * 32 + cls] + (uint32_t)mine;
+                    if (ord >= (uint32_t)s_skip[cls]) {
+                        const uint32_t cap = (uint32_t)s_cap[cls];
+                        const uint32_t pos = ((uint32_t)s_base[cls] + ord % cap) % cap;
+                        float4 lo, hi;
+                        fetch(target, lo, hi);
+                        float4* dst = reinterpret_cast<float4*>(p.bank_rows + (p.row_off[cls] + pos) * D + d0 + 8 * ci);
+                        dst[0] = lo;
+                        if (rows_on > 4) dst[1] = hi;
+                    }
+                }
+            }
+            // advance the per-warp running key ordinals by this sub-tile's keys (all warps agree)
+            __syncwarp();
+            for (int wq = lane; wq < SP / 4; wq += 32) {
+                const uint32_t w4 = sc_words[wq];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t cd = (w4 >> (8 * q)) & 0xffu;
+                    const bool is_key = cd & CODE_KEY;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, is_key ? (cd & CODE_CLS_MASK) : 0xffffu);
+                    if (is_key && (__ffs(peers) - 1) == lane) wrun[warp * 32 + (cd & CODE_CLS_MASK)] += __popc(peers);
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();                                     // tile and code buffer free for the next commit
+    }
+    flush();
+    __syncthreads();
+    for (int i = tid; i < C * NCH * 2; i += 256) {
+        const int h = i / (C * NCH), c = (i / NCH) % C, k = i % NCH;
+        if (8 * k + 4 * h >= dreal) continue;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int w = 0; w < NS; ++w) {
+            const float4 a = acc[(size_t)h * acc_plane + ((size_t)w * C + c) * NCH + k];
+            sum.x += a.x; sum.y += a.y; sum.z += a.z; sum.w += a.w;
+        }
+        *reinterpret_cast<float4*>(p.partials + ((int64_t)grp * C + c) * D + d0 + 8 * k + 4 * h) = sum;
     }
 }
 
@@ -277,21 +533,66 @@ __global__ void proto_finalize_kernel(const float* __restrict__ partials, int ro
     proto_sums[i] = s;
 }
 
-static int proto_nch(const arco_dims& d) { return d.feat <= 32 ? 8 : 16; }
+// Kernel variant for a problem: the 8-dims-per-lane kernel needs 16-byte vector loads and its 8 KB * C
+// stream accumulators to fit beside the tile; otherwise the 4-dims-per-lane kernel (4 KB * C) runs.
+struct ProtoCfg {
+    bool wide;        // proto8_kernel
+    int nch;          // lanes per stream
+    int dchunk;       // feature dims per CTA
+    size_t smem;
+};
 
-static size_t proto_smem_bytes(const arco_dims& d, int nch) {
-    const int sp = 2048 / nch;
-    return (size_t)sp * nch * 16 + (size_t)8 * d.classes * nch * 16 + sp + 8 * 32 * 4;
+static bool proto_vec_ok(const arco_dims& d) {
+    const int per16 = d.rep_dtype == ARCO_BF16 ? 8 : 4;
+    return d.space % per16 == 0;
 }
 
-// grid geometry shared by the workspace layout and the launch
+static ProtoCfg proto_cfg(const arco_dims& d) {
+    ProtoCfg c;
+    c.wide = d.classes <= 8 && d.feat >= 32 && proto_vec_ok(d);
+    if (c.wide) {
+        c.nch = d.feat <= 64 ? 8 : 16;
+        c.dchunk = c.nch * 8;
+        const int lw = d.rep_dtype == ARCO_BF16 ? 1 : 2;
+        const int sp = 2048 / (c.nch * lw);
+        c.smem = (size_t)32768 + (size_t)8 * (32 / c.nch) * d.classes * c.nch * 32 + 2 * ARCO_TILE + 8 * 32 * 4;
+        (void)sp;
+    } else {
+        c.nch = d.feat <= 32 ? 8 : 16;
+        c.dchunk = c.nch * 4;
+        const int sp = 2048 / c.nch;
+        c.smem = (size_t)32768 + (size_t)8 * (32 / c.nch) * d.classes * c.nch * 16 + sp + 8 * 32 * 4;
+    }
+    return c;
+}
+
+template <typename K>
+static int kernel_occupancy(K kernel, size_t smem) {
+    int occ = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess) {
+        cudaGetLastError();
+        occ = 0;
+    }
+    return occ;
+}
+
+// grid geometry shared by the workspace layout and the launch: one resident wave of persistent CTAs
 static void proto_grid(const arco_dims& d, int* ndc, int* groups) {
-    const int nch = proto_nch(d);
-    *ndc = (d.feat + nch * 4 - 1) / (nch * 4);
-    // occupancy is bounded by shared memory: 32 KB tile + C*NCH*128 B accumulators
-    const size_t smem = proto_smem_bytes(d, nch);
-    int occ = (int)((size_t)(227 * 1024) / (smem + 1024));
-    if (occ > 6) occ = 6;
+    const ProtoCfg c = proto_cfg(d);
+    *ndc = (d.feat + c.dchunk - 1) / c.dchunk;
+    const bool bf = d.rep_dtype == ARCO_BF16;
+    int occ;
+    if (c.wide) {
+        if (bf) occ = c.nch == 16 ? kernel_occupancy(proto8_kernel<__nv_bfloat16, 16>, c.smem) : kernel_occupancy(proto8_kernel<__nv_bfloat16, 8>, c.smem);
+        else occ = c.nch == 16 ? kernel_occupancy(proto8_kernel<float, 16>, c.smem) : kernel_occupancy(proto8_kernel<float, 8>, c.smem);
+    } else {
+        if (bf) occ = c.nch == 16 ? kernel_occupancy(proto_enqueue_kernel<__nv_bfloat16, 16>, c.smem) : kernel_occupancy(proto_enqueue_kernel<__nv_bfloat16, 8>, c.smem);
+        else occ = c.nch == 16 ? kernel_occupancy(proto_enqueue_kernel<float, 16>, c.smem) : kernel_occupancy(proto_enqueue_kernel<float, 8>, c.smem);
+    }
+    // without a device (CPU-only build box) assume the shared-memory bound
+    if (occ <= 0) occ = (int)((size_t)(227 * 1024) / (c.smem + 1024));
+    if (occ > 8) occ = 8;
     if (occ < 1) occ = 1;
     int g = sm_count() * occ / *ndc;
     if (g < 1) g = 1;
@@ -306,15 +607,14 @@ int proto_partial_rows(const arco_dims& d) {
 
 template <typename T>
 static int launch_proto(const arco_dims& d, const ProtoParams& p, int groups, cudaStream_t st) {
-    const int nch = proto_nch(d);
-    const size_t smem = proto_smem_bytes(d, nch);
+    const ProtoCfg c = proto_cfg(d);
     const int grid = groups * p.NDC;
-    if (nch == 16) {
-        ARCO_CUDA_CHECK(cudaFuncSetAttribute(proto_enqueue_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        proto_enqueue_kernel<T, 16><<<grid, 256, smem, st>>>(p);
+    if (c.wide) {
+        if (c.nch == 16) proto8_kernel<T, 16><<<grid, 256, c.smem, st>>>(p);
+        else proto8_kernel<T, 8><<<grid, 256, c.smem, st>>>(p);
     } else {
-        ARCO_CUDA_CHECK(cudaFuncSetAttribute(proto_enqueue_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        proto_enqueue_kernel<T, 8><<<grid, 256, smem, st>>>(p);
+        if (c.nch == 16) proto_enqueue_kernel<T, 16><<<grid, 256, c.smem, st>>>(p);
+        else proto_enqueue_kernel<T, 8><<<grid, 256, c.smem, st>>>(p);
     }
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
@@ -345,8 +645,8 @@ extern "C" int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher
     int ndc, groups;
     arco::proto_grid(d, &ndc, &groups);
     p.NDC = ndc;
-    const int per16 = d.rep_dtype == ARCO_BF16 ? 8 : 4;
-    p.vec_ok = (d.space % per16 == 0) && (((uintptr_t)rep_teacher & 15) == 0);
+    ARCO_REQUIRE(((uintptr_t)rep_teacher & 15) == 0, "rep_teacher must be 16-byte aligned");
+    p.vec_ok = arco::proto_vec_ok(d);
     int rc = d.rep_dtype == ARCO_BF16 ? arco::launch_proto<__nv_bfloat16>(d, p, groups, st)
                                       : arco::launch_proto<float>(d, p, groups, st);
     if (rc != ARCO_OK) return rc;

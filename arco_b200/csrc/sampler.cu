@@ -22,7 +22,9 @@ namespace arco {
 
 constexpr int kClusterSize = 8;
 constexpr int kThreads = 1024;
-constexpr int kItems = 4;                   // draws per thread per round
+constexpr int kItems = 4;                   // draws per thread per round (scan kernel)
+constexpr int kEmitThreads = 256;
+constexpr int kEmitItems = 4;
 constexpr int kMinGridEdge = 8;             // reference falls back below this (probe: high <= 56)
 constexpr int kPatch = 16;
 
@@ -30,6 +32,8 @@ struct SampleParams {
     const arco_plan* plan;                  // fused mode: calls derived from the plan; else direct mode
     int32_t* idx_anchor;
     int32_t* idx_neg;
+    int32_t* scratch;                       // per call: [0] = survivors of the bottom block row, [4..] their values
+    int64_t scratch_stride;                 // int32 elements per call
     int32_t C, Q, N;
     // direct mode
     int64_t high, shape;
@@ -40,17 +44,6 @@ struct SampleParams {
 
 enum { PURPOSE_DRAW = 0, PURPOSE_PAD = 1, PURPOSE_UNIFORM = 2, PURPOSE_PERM = 3 };
 
-struct GridGeom {
-    uint32_t edge, step, per_block, half;
-    bool anti;
-    __device__ void block_rect(uint32_t k, uint32_t& r0, uint32_t& c0, uint32_t& nr, uint32_t& nc) const {
-        const uint32_t bi = k >> 2, bj = k & 3;
-        r0 = bi * step; c0 = bj * step;
-        nr = (bi == 3) ? edge - r0 : step;            // last block row/column absorbs the remainder (:146-153)
-        nc = (bj == 3) ? edge - c0 : step;
-    }
-};
-
 __device__ __forceinline__ uint32_t round_sqrt(uint64_t high) {
     uint64_t e = (uint64_t)sqrt((double)high);
     while (e * e > high) --e;
@@ -59,114 +52,101 @@ __device__ __forceinline__ uint32_t round_sqrt(uint64_t high) {
     return (uint32_t)e;
 }
 
+// Everything a thread needs to know about one sampler call (all fields are call-uniform).
+struct Call {
+    int64_t high, shape;
+    int32_t* out;
+    int32_t* scratch;
+    uint64_t stream;
+    uint32_t edge, step, per_block, half;
+    bool active, anti, uniform, strata, drops;
+};
+
+__device__ __forceinline__ Call decode_call(const SampleParams& p, int call) {
+    Call c;
+    c.active = true;
+    c.stream = p.stream;
+    if (p.plan) {
+        const int j = call >> 1;
+        const bool neg = call & 1;
+        c.active = p.plan->slot_active[j] != 0;                            // skipped positions draw nothing
+        if (neg) {
+            const int vc = p.plan->valid_class[j];
+            c.high = c.active ? p.plan->bank_len[vc] : 0;                  // len(negative_feat), :471-473
+            c.shape = (int64_t)p.Q * p.N;
+            c.out = p.idx_neg + (int64_t)j * p.Q * p.N;
+        } else {
+            c.high = p.plan->n_anchor[j];                                  // len(seg_feat_low_entropy_list[i]), :444-446
+            c.shape = p.Q;
+            c.out = p.idx_anchor + (int64_t)j * p.Q;
+        }
+        c.stream = p.stream * 64ull + (uint64_t)call;
+    } else {
+        c.high = p.high; c.shape = p.shape; c.out = p.out;
+    }
+    c.scratch = p.scratch + (int64_t)call * p.scratch_stride;
+    if (c.high <= 0 || c.shape <= 0) c.active = false;
+    const bool structured = p.func == ARCO_FUNC_SMC || p.func == ARCO_FUNC_ASMC;
+    c.anti = p.func == ARCO_FUNC_ASMC;
+    c.edge = (structured && c.active) ? round_sqrt((uint64_t)c.high) : 0;
+    c.strata = structured && c.edge < kMinGridEdge;
+    // torch.randint(high, (shape,))  (:336 and :84-85 / :36-37)
+    c.uniform = !structured || (c.strata && (c.high / kPatch > c.shape || c.high < kPatch));
+    c.step = c.edge / 4;
+    c.per_block = 0; c.half = 0; c.drops = false;
+    if (c.active && !c.uniform && !c.strata) {
+        c.per_block = (uint32_t)((uint64_t)c.shape * c.edge * c.edge / (uint64_t)c.high / 16ull);
+        c.half = c.per_block / 2;
+        if (c.anti) c.per_block = 2 * c.half;
+        c.drops = (uint64_t)c.edge * c.edge > (uint64_t)c.high;           // only then can a draw be >= high (:165)
+    }
+    return c;
+}
+
+// value of canonical draw w (0 <= w < per_block) of grid block k; returns -1 if it is dropped (>= high)
+__device__ __forceinline__ int32_t grid_draw(const Call& c, const Philox& rng, uint32_t k, uint32_t w) {
+    const uint32_t bi = k >> 2, bj = k & 3;
+    const uint32_t r0 = bi * c.step, c0 = bj * c.step;
+    const uint32_t nr = (bi == 3) ? c.edge - r0 : c.step;                 // last block row/column absorbs the remainder (:146-153)
+    const uint32_t nc = (bj == 3) ? c.edge - c0 : c.step;
+    const bool mirror = c.anti && w >= c.half;
+    const uint32_t m = mirror ? w - c.half : w;
+    const uint32_t r = bounded(rng(k * c.per_block + m, PURPOSE_DRAW, (uint32_t)c.stream, (uint32_t)(c.stream >> 32)).x, nr * nc);
+    int64_t v = (int64_t)(r0 + r / nc) * c.edge + (c0 + r % nc);
+    if (mirror) v = ((int64_t)(2 * r0 + nr - 1) * c.edge + (2 * c0 + nc - 1)) - v;   // center - x, center = int(2*mean(block))
+    v = (int64_t)(float)v;                                                // torch.Tensor(...) float32 round trip (:163,:245)
+    return v < c.high ? (int32_t)v : -1;                                  // mask = cur_list < high (:165)
+}
+
+// Kernel 1 (only does work when edge^2 > high): order-preserving compaction of the bottom block row's
+// draws -- the only ones that can fall outside [0, high) -- scanned across an 8-CTA cluster through DSMEM.
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
-sample_kernel(SampleParams p) {
+sample_scan_kernel(SampleParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank();
     const int call = blockIdx.x / kClusterSize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
-
-    // ---- decode the call (cluster-uniform) ----
-    int64_t high, shape;
-    int32_t* out;
-    uint64_t stream = p.stream;
-    if (p.plan) {
-        const int j = call >> 1;
-        const bool neg = call & 1;
-        if (!p.plan->slot_active[j]) return;                              // skipped positions draw nothing
-        if (neg) {
-            high = p.plan->bank_len[p.plan->valid_class[j]];              // len(negative_feat), :471-473
-            shape = (int64_t)p.Q * p.N;
-            out = p.idx_neg + (int64_t)j * p.Q * p.N;
-        } else {
-            high = p.plan->n_anchor[j];                                   // len(seg_feat_low_entropy_list[i]), :444-446
-            shape = p.Q;
-            out = p.idx_anchor + (int64_t)j * p.Q;
-        }
-        stream = p.stream * 64ull + (uint64_t)call;
-    } else {
-        high = p.high; shape = p.shape; out = p.out;
-    }
-    if (high <= 0 || shape <= 0) return;
+    const Call c = decode_call(p, call);
+    if (!c.active || c.uniform || c.strata || !c.drops) return;          // cluster-uniform
     const Philox rng(p.seed);
-    const uint32_t st_lo = (uint32_t)stream, st_hi = (uint32_t)(stream >> 32);
     const uint32_t gthread = rank * kThreads + tid;
     const uint32_t gstride = kClusterSize * kThreads;
-    const uint32_t H = (uint32_t)high;
-
-    const bool structured = p.func == ARCO_FUNC_SMC || p.func == ARCO_FUNC_ASMC;
-    const bool anti = p.func == ARCO_FUNC_ASMC;
-    const uint32_t edge = structured ? round_sqrt((uint64_t)high) : 0;
-
-    if (!structured || (edge < kMinGridEdge && (high / kPatch > shape || high < kPatch))) {
-        // torch.randint(high, (shape,))  (:336 and :84-85 / :36-37)
-        for (int64_t i = gthread; i < shape; i += gstride)
-            out[i] = (int32_t)bounded(rng((uint32_t)i, PURPOSE_UNIFORM, st_lo, st_hi).x, H);
-        return;
-    }
-    const uint4 ka = rng(0, PURPOSE_PERM, st_lo, st_hi), kb = rng(1, PURPOSE_PERM, st_lo, st_hi);
-
-    if (edge < kMinGridEdge) {
-        // 1-D strata of 16 (:83-117 / :35-80): structured draws, uniform pads, shuffle of ALL `shape` entries
-        const uint32_t strata = (uint32_t)(high / kPatch);
-        uint32_t per = (uint32_t)(shape / strata);
-        const uint32_t half = per / 2;
-        if (anti) per = 2 * half;
-        const uint64_t n_struct = (uint64_t)strata * per;
-        const FeistelPerm perm((uint32_t)shape, ka, kb);
-        for (int64_t i = gthread; i < shape; i += gstride) {
-            const uint32_t u = perm((uint32_t)i);
-            int32_t v;
-            if (u < n_struct) {
-                const uint32_t k = u / per, w = u % per;
-                const uint32_t m = anti ? w % half : w;
-                const uint32_t x = k * kPatch + bounded(rng(k * per + m, PURPOSE_DRAW, st_lo, st_hi).x, kPatch);
-                v = (anti && w >= half) ? (int32_t)((2 * k + 1) * kPatch - 1 - x) : (int32_t)x;
-            } else {
-                v = (int32_t)bounded(rng(u, PURPOSE_PAD, st_lo, st_hi).x, H);
-            }
-            out[i] = v;
-        }
-        return;
-    }
-
-    // ---- 4x4 grid of blocks over an edge x edge image (:136-182 / :203-265) ----
-    GridGeom g;
-    g.edge = edge; g.step = edge / 4; g.anti = anti;
-    g.per_block = (uint32_t)((uint64_t)shape * edge * edge / (uint64_t)high / 16ull);
-    g.half = g.per_block / 2;
-    if (anti) g.per_block = 2 * g.half;
-    const uint64_t n_tot64 = 16ull * g.per_block;
-    const uint32_t n_tot = (uint32_t)n_tot64;
-    const FeistelPerm perm(n_tot, ka, kb);
-
-    uint32_t carry = 0;                                                   // survivors emitted so far
-    for (uint32_t base = 0; base < n_tot; base += gstride * kItems) {
+    const uint32_t n_bottom = 4u * c.per_block;                           // blocks 12..15, canonical order
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_bottom; base += gstride * kItems) {
         int32_t vals[kItems];
         uint32_t cnt = 0;
 #pragma unroll
         for (int i = 0; i < kItems; ++i) {
-            const uint32_t t = base + gthread * kItems + i;
+            const uint32_t u = base + gthread * kItems + i;
             vals[i] = -1;
-            if (t < n_tot) {
-                const uint32_t u = perm(t);                               // canonical draw behind shuffled slot t
-                const uint32_t k = u / g.per_block, w = u % g.per_block;
-                const uint32_t m = anti ? w % g.half : w;
-                uint32_t r0, c0, nr, nc;
-                g.block_rect(k, r0, c0, nr, nc);
-                const uint32_t r = bounded(rng(k * g.per_block + m, PURPOSE_DRAW, st_lo, st_hi).x, nr * nc);
-                int64_t v = (int64_t)(r0 + r / nc) * edge + (c0 + r % nc);
-                if (anti && w >= g.half) {
-                    const int64_t center = (int64_t)(2 * r0 + nr - 1) * edge + (2 * c0 + nc - 1);   // int(2*mean(block))
-                    v = center - v;
-                }
-                v = (int64_t)(float)v;                                    // torch.Tensor(...) float32 round trip (:163,:245)
-                if (v < high) { vals[i] = (int32_t)v; ++cnt; }            // mask = cur_list < high (:165)
+            if (u < n_bottom) {
+                vals[i] = grid_draw(c, rng, 12u + u / c.per_block, u % c.per_block);
+                cnt += vals[i] >= 0;
             }
         }
-        // block-level exclusive scan of cnt
         uint32_t incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -188,7 +168,6 @@ sample_kernel(SampleParams p) {
         }
         __syncthreads();
         uint32_t pos = s_warp[warp] + incl - cnt;
-        // cluster-level scan through distributed shared memory
         cluster.sync();
         uint32_t before = 0, round_total = 0;
         for (uint32_t r = 0; r < kClusterSize; ++r) {
@@ -200,21 +179,94 @@ sample_kernel(SampleParams p) {
         pos += carry + before;
 #pragma unroll
         for (int i = 0; i < kItems; ++i)
-            if (vals[i] >= 0) { if (pos < shape) out[pos] = vals[i]; ++pos; }   // truncate (:179-180)
+            if (vals[i] >= 0) c.scratch[4 + pos++] = vals[i];
         carry += round_total;
     }
-    // iid uniform pads (:176-177)
-    for (int64_t i = (int64_t)carry + gthread; i < shape; i += gstride)
-        out[i] = (int32_t)bounded(rng((uint32_t)i, PURPOSE_PAD, st_lo, st_hi).x, H);
+    if (gthread == 0) c.scratch[0] = (int32_t)carry;
 }
 
-static int launch_sampler(const SampleParams& p, int calls, cudaStream_t st) {
+// Kernel 2: every output position independently.  survivors S = (blocks 0..11 verbatim) ++ (compacted bottom
+// row); out[t] = S[perm(t)] for t < min(|S|, shape), iid uniform pads after that (:170-180).
+__global__ void __launch_bounds__(kEmitThreads) sample_emit_kernel(SampleParams p) {
+    const int call = blockIdx.y;
+    const Call c = decode_call(p, call);
+    if (!c.active) return;
+    const int64_t t0 = ((int64_t)blockIdx.x * kEmitThreads + threadIdx.x) * kEmitItems;
+    if (t0 >= c.shape) return;
+    const Philox rng(p.seed);
+    const uint32_t st_lo = (uint32_t)c.stream, st_hi = (uint32_t)(c.stream >> 32);
+    const uint32_t H = (uint32_t)c.high;
+    int32_t res[kEmitItems];
+    if (c.uniform) {
+#pragma unroll
+        for (int i = 0; i < kEmitItems; ++i)
+            res[i] = (int32_t)bounded(rng((uint32_t)(t0 + i), PURPOSE_UNIFORM, st_lo, st_hi).x, H);
+    } else {
+        const uint4 ka = rng(0, PURPOSE_PERM, st_lo, st_hi), kb = rng(1, PURPOSE_PERM, st_lo, st_hi);
+        if (c.strata) {
+            // 1-D strata of 16 (:83-117 / :35-80): structured draws, uniform pads, shuffle of ALL `shape` entries
+            const uint32_t strata = (uint32_t)(c.high / kPatch);
+            uint32_t per = (uint32_t)(c.shape / strata);
+            const uint32_t half = per / 2;
+            if (c.anti) per = 2 * half;
+            const uint64_t n_struct = (uint64_t)strata * per;
+            const FeistelPerm perm((uint32_t)c.shape, ka, kb);
+#pragma unroll
+            for (int i = 0; i < kEmitItems; ++i) {
+                const int64_t t = t0 + i;
+                res[i] = 0;
+                if (t >= c.shape) continue;
+                const uint32_t u = perm((uint32_t)t);
+                if (u < n_struct) {
+                    const uint32_t k = u / per, w = u % per;
+                    const bool mirror = c.anti && w >= half;
+                    const uint32_t m = mirror ? w - half : w;
+                    const uint32_t x = k * kPatch + bounded(rng(k * per + m, PURPOSE_DRAW, st_lo, st_hi).x, kPatch);
+                    res[i] = mirror ? (int32_t)((2 * k + 1) * kPatch - 1 - x) : (int32_t)x;
+                } else {
+                    res[i] = (int32_t)bounded(rng(u, PURPOSE_PAD, st_lo, st_hi).x, H);
+                }
+            }
+        } else {
+            const uint32_t top = 12u * c.per_block;
+            const uint32_t n_bottom = c.drops ? (uint32_t)c.scratch[0] : 4u * c.per_block;
+            const uint32_t M = top + n_bottom;
+            const FeistelPerm perm(M, ka, kb);
+#pragma unroll
+            for (int i = 0; i < kEmitItems; ++i) {
+                const int64_t t = t0 + i;
+                res[i] = 0;
+                if (t >= c.shape) continue;
+                if (t < M) {
+                    const uint32_t rho = perm((uint32_t)t);
+                    if (rho < top || !c.drops) res[i] = grid_draw(c, rng, rho / c.per_block, rho % c.per_block);
+                    else res[i] = c.scratch[4 + (rho - top)];
+                } else {
+                    res[i] = (int32_t)bounded(rng((uint32_t)t, PURPOSE_PAD, st_lo, st_hi).x, H);   // (:176-177)
+                }
+            }
+        }
+    }
+    if (t0 + kEmitItems <= c.shape && (((uintptr_t)(c.out + t0)) & 15) == 0) {
+        *reinterpret_cast<int4*>(c.out + t0) = make_int4(res[0], res[1], res[2], res[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kEmitItems; ++i)
+            if (t0 + i < c.shape) c.out[t0 + i] = res[i];
+    }
+}
+
+static int launch_sampler(const SampleParams& p, int calls, int64_t max_shape, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(calls * kClusterSize);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
-    ARCO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sample_kernel, p));
+    ARCO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sample_scan_kernel, p));
+    const int64_t per_cta = (int64_t)kEmitThreads * kEmitItems;
+    dim3 grid((unsigned)((max_shape + per_cta - 1) / per_cta), (unsigned)calls);
+    sample_emit_kernel<<<grid, kEmitThreads, 0, st>>>(p);
+    ARCO_LAUNCH_CHECK();
     return ARCO_OK;
 }
 
@@ -230,18 +282,23 @@ extern "C" int arco_sample(const arco_dims* dims, int32_t func, uint64_t seed, u
     arco::SampleParams p = {};
     p.plan = (const arco_plan*)((char*)workspace + L.plan);
     p.idx_anchor = idx_anchor; p.idx_neg = idx_neg;
+    p.scratch = (int32_t*)((char*)workspace + L.sample_scratch);
+    const int64_t draws = (int64_t)d.queries * (d.negatives > 0 ? d.negatives : 1);
+    p.scratch_stride = draws + draws / 4 + 4096;
     p.C = d.classes; p.Q = d.queries; p.N = d.negatives;
     p.func = func; p.seed = seed; p.stream = step;
-    return arco::launch_sampler(p, 2 * d.classes, (cudaStream_t)stream);
+    return arco::launch_sampler(p, 2 * d.classes, draws > d.queries ? draws : d.queries, (cudaStream_t)stream);
 }
 
 extern "C" int arco_sample_one(int32_t func, int64_t high, int64_t shape, uint64_t seed, uint64_t stream_id,
                                int32_t* out, void* scratch, int64_t scratch_bytes, void* stream) {
-    (void)scratch; (void)scratch_bytes;
     ARCO_REQUIRE(out && high > 0 && high < ((int64_t)1 << 31) && shape > 0 && shape < ((int64_t)1 << 30),
                  "arco_sample_one: bad argument");
+    ARCO_REQUIRE(scratch && scratch_bytes >= (shape / 2 + 4096) * 4, "arco_sample_one: scratch too small (need (shape/2+4096)*4 bytes)");
     arco::SampleParams p = {};
     p.plan = nullptr;
+    p.scratch = (int32_t*)scratch;
+    p.scratch_stride = 0;
     p.high = high; p.shape = shape; p.out = out; p.func = func; p.seed = seed; p.stream = stream_id;
-    return arco::launch_sampler(p, 1, (cudaStream_t)stream);
+    return arco::launch_sampler(p, 1, shape, (cudaStream_t)stream);
 }

@@ -27,16 +27,19 @@ def _device(device):
     return torch.device(device)
 
 
-def _sample(func: int, high: int, shape: int, device=None, seed=None) -> torch.Tensor:
+def _sample(func: int, high: int, shape: int, device=None, seed=None, stream_id=None) -> torch.Tensor:
     high, shape = int(high), int(shape)
     if high <= 0 or shape <= 0:
         raise ValueError("high and shape must be positive")
     dev = _device(device)
     out = torch.empty(shape, dtype=torch.int32, device=dev)
+    scratch = torch.empty(shape // 2 + 4096, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         sd = int(seed) if seed is not None else int(torch.cuda.initial_seed()) & (2 ** 63 - 1)
-        _cabi.check(_cabi.lib.arco_sample_one(func, high, shape, sd, (1 << 40) + next(_counter), out.data_ptr(), None, 0,
-                                              torch.cuda.current_stream().cuda_stream), "arco_sample_one")
+        sid = (1 << 40) + next(_counter) if stream_id is None else int(stream_id)
+        _cabi.check(_cabi.lib.arco_sample_one(func, high, shape, sd, sid, out.data_ptr(), scratch.data_ptr(),
+                                              scratch.numel() * 4, torch.cuda.current_stream().cuda_stream),
+                    "arco_sample_one")
     return out.long()
 
 

@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""Benchmark of the ARCO stratified contrastive loss hot path (fwd+bwd) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+Contract (one JSON line on rank 0):
+  metric/unit  BASELINE.json's metric: contrastive-loss fwd+bwd throughput in Mpixels/s (ms in ms_per_step)
+  value        whole-job pixels / device time, inputs already resident in HBM
+  e2e          same metric through the public op with HOST (pinned) buffers: H2D of every input and D2H of
+               the loss inside the timed region
+  roofline     dominant kernel (one-pass prototype reduce + key enqueue over rep_teacher) against the
+               measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline the oracle port (oracle/contra_oracle.py, torch CPU ops, all host threads) on a bounded sample
+A "step" is one forward+backward of the loss over one synthetic batch.  Workloads: SURVEY.md section 8(d).
+The default is BASELINE.json configs[1]'s shape (ACDC 2-D train step: batch 24 = 12 labelled + 12 unlabelled,
+4 classes, 256x256, D=496 representation head, bf16 rep tensors); the U-Net stays in PyTorch and is not
+part of the hot path.  Multi-GPU is weak scaling over the batch with one all-reduce of the prototype sums.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "contrastive_loss_fwd_bwd_throughput"
+UNIT = "Mpixels/s"
+KERNELS_PER_STEP = 9        # classify, scan_plan, proto_enqueue, proto_finalize, sample_scan, sample_emit, infonce, fill_zero, grad_scatter
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="acdc2d_trainstep",
+                    choices=["acdc2d_loss", "acdc2d_trainstep", "la3d", "cityscapes"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--func", default="smc")
+    ap.add_argument("--blocky", action="store_true", help="labels constant on 16-pixel tiles instead of iid")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock / throttle-reason sampler running in a thread DURING the timed region (NVML, 5 ms period;
+    falls back to one nvidia-smi query if pynvml is unavailable)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+            while not self.stop_flag:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.005)
+        except Exception:
+            pass
+
+    def start(self):
+        import threading
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(v) for v in out.strip().split(",")[:2]]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the run"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "source": "NVML thread, 5 ms period, during the timed region"}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference / CPU arm: the oracle port on host cores, bounded sample of the same workload
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_spec(workload):
+    from arco_b200.synth import WORKLOADS
+    cfg = dict(WORKLOADS[workload])
+    cfg["n_lab"], cfg["n_unlab"] = 1, 1          # bounded sample: one labelled + one unlabelled image/volume
+    return cfg
+
+
+def run_cpu(workload, steps, warmup, func):
+    import numpy as np
+    import torch
+
+    import oracle
+    from arco_b200.synth import CaseSpec, bench_bank, bench_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = cpu_sample_spec(workload)
+    spec, x = bench_inputs(workload, torch.device("cpu"), seed=1337, n_lab=cfg["n_lab"], n_unlab=cfg["n_unlab"])
+    memobank, ptrs, caps = bench_bank(spec)
+    sampler = {"smc": oracle.grid_strata_sample, "asmc": oracle.grid_antithetic_sample}.get(func)
+    rep = x["rep"].float().requires_grad_(True)           # CPU bf16 kernels are not what the reference ran on
+    teacher = x["rep_teacher"].float()
+    times = []
+    for i in range(warmup + steps):
+        rep.grad = None
+        t0 = time.perf_counter()
+        res = oracle.contra_memobank_loss(
+            rep, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"],
+            memobank, ptrs, caps, teacher, delta_n=0.97, sampler=sampler, num_queries=spec.queries,
+            num_negatives=spec.negatives, temp=0.5)
+        res.loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    px = spec.pixels
+    sample = (f"{workload} shape with batch reduced to 1 labelled + 1 unlabelled "
+              f"({px} pixels/step, D={spec.feat}, C={spec.classes}, Q=256, N=512, fp32 on CPU), "
+              f"{steps} timed steps after {warmup} warm-up, oracle port (torch CPU ops)")
+    return dict(value=px / (ms * 1e-3) / 1e6, unit=UNIT, cores=cores, kind="port", sample=sample, ms_per_step=ms,
+                threads=torch.get_num_threads()), spec
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, spec = run_cpu(args.workload, max(1, args.steps), max(0, args.warmup), args.func)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": "CPU arm: oracle port of the reference loss on host cores; "
+                   "the Python reference itself cannot travel to the GPU box", "sample": base["sample"]},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun exactly as the driver would
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU; there is no CPU fallback"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    import arco_b200
+    from arco_b200 import _cabi
+    from arco_b200.synth import bench_bank, bench_inputs
+
+    spec, x = bench_inputs(args.workload, dev, seed=1337 + rank, blocky=args.blocky)
+    memobank, ptrs, caps = bench_bank(spec, seed=1337 + rank)
+    rep = x["rep"].requires_grad_(True)
+    P = spec.pixels
+    kw = dict(delta_n=0.97, func=args.func, num_queries=spec.queries, num_negatives=spec.negatives, temp=0.5,
+              process_group=group, seed=1337)
+
+    def step(inputs=x, rep_t=rep):
+        rep_t.grad = None
+        _, loss = arco_b200.compute_contra_memobank_loss(
+            rep_t, inputs["label_l"], inputs["label_u"], inputs["prob_l"], inputs["prob_u"], inputs["low_mask"],
+            inputs["high_mask"], memobank, ptrs, caps, inputs["rep_teacher"], **kw)
+        loss.backward()
+        return loss
+
+    in_bytes = sum(x[k].numel() * x[k].element_size() for k in
+                   ("rep", "rep_teacher", "label_l", "label_u", "prob_l", "prob_u", "low_mask", "high_mask"))
+    flush = None
+    l2_note = "inputs (%.0f MB) exceed the 126 MB L2" % (in_bytes / 1e6)
+    if in_bytes < 400e6:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        l2_note = "L2 flushed (256 MB write) between timed steps"
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sync_all()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        starts[i].record()
+        step()
+        ends[i].record()
+    sync_all()
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * P * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ------------------------------------------------------------------ per-stage timing + roofline (rank 0 view)
+    stages, roof = stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush)
+
+    # ------------------------------------------------------------------ end-to-end with host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(torch, arco_b200, spec, x, memobank, ptrs, caps, dev, kw, world,
+                      args.e2e_steps or max(3, args.steps // 4), sync_all)
+        if world > 1:
+            tt = torch.tensor([e2e["_total_ms"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e["_total_ms"] = float(tt.item())
+        e2e["value"] = world * P * e2e["steps"] / (e2e.pop("_total_ms") * 1e-3) / 1e6
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = run_cpu(args.workload, 5, 1, args.func)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "batch_per_gpu": spec.batch, "labelled_per_gpu": spec.n_lab,
+                "classes": spec.classes, "spatial": list(spec.spatial), "feat": spec.feat, "rep_storage": spec.dtype,
+                "queries": spec.queries, "negatives": spec.negatives, "func": args.func,
+                "labels": "blocky16" if args.blocky else "iid", "banks": "pre-filled to capacity (50000/30000 rows)",
+                "pixels_per_gpu": P, "parallelism": f"batch-shard x{world}, 1 all-reduce of C*(D+1) fp64" if world > 1 else "single GPU",
+                "l2": l2_note, "timing": "CUDA events per step on the launching stream, max over ranks",
+            },
+            "clocks": clk, "gpu_launches": args.steps * (KERNELS_PER_STEP + (1 if world > 1 else 0)),
+            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "stages": stages,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush, iters=10):
+    """Time every C-ABI stage on its own (CUDA events on the launching stream) and build the roofline
+    entry of the dominant kernel from the algorithmic bytes of SURVEY.md section 8(d)."""
+    C = ctypes
+    lib = _cabi.lib
+    bank = memobank[0].bank
+    bank.settle()
+    rep_dtype = _cabi.BF16 if spec.dtype == "bf16" else _cabi.F32
+    S = 1
+    for s in spec.spatial:
+        S *= s
+    dims = _cabi.Dims(spec.n_lab, spec.n_unlab, spec.classes, spec.feat, S, spec.queries, spec.negatives, rep_dtype, 0)
+    L = _cabi.workspace_layout(dims)
+    ws = torch.empty(L.total_bytes, dtype=torch.uint8, device=dev)
+    Cn, Q, N, D = spec.classes, spec.queries, spec.negatives, spec.feat
+    proto = torch.empty((Cn, D + 1), dtype=torch.float64, device=dev)
+    idx_a = torch.empty((Cn, Q), dtype=torch.int32, device=dev)
+    idx_n = torch.empty((Cn, Q * N), dtype=torch.int32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    g_anchor = torch.empty((Cn, Q, D), dtype=torch.float32, device=dev)
+    pix = torch.empty((Cn, Q), dtype=torch.int32, device=dev)
+    grad = torch.empty_like(x["rep"])
+    go = torch.ones(1, dtype=torch.float32, device=dev)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    d, b = C.byref(dims), C.byref(bank.c_struct)
+    fl = lambda t: t.contiguous().view(t.shape[0], t.shape[1], -1)
+    ll, lu, pl, pu = fl(x["label_l"]), fl(x["label_u"]), fl(x["prob_l"]), fl(x["prob_u"])
+    lm, hm = fl(x["low_mask"]), fl(x["high_mask"])
+    rt, rs = x["rep_teacher"].contiguous(), x["rep"].detach().contiguous()
+    calls = [
+        ("classify_count", lambda: lib.arco_classify_count(d, ll.data_ptr(), lu.data_ptr(), pl.data_ptr(), pu.data_ptr(),
+                                                           lm.data_ptr(), hm.data_ptr(), 0.3, 0.97, 3, 20, ws.data_ptr(), sp)),
+        ("scan_plan", lambda: lib.arco_scan_plan(d, b, ws.data_ptr(), sp)),
+        ("proto_enqueue", lambda: lib.arco_proto_enqueue(d, rt.data_ptr(), b, proto.data_ptr(), ws.data_ptr(), sp)),
+        ("sample", lambda: lib.arco_sample(d, _cabi.FUNC_SMC, 1337, 7, idx_a.data_ptr(), idx_n.data_ptr(), ws.data_ptr(), sp)),
+        ("infonce", lambda: lib.arco_infonce(d, rs.data_ptr(), b, proto.data_ptr(), idx_a.data_ptr(), idx_n.data_ptr(), 0.5,
+                                             loss.data_ptr(), g_anchor.data_ptr(), pix.data_ptr(), None, ws.data_ptr(), sp)),
+        ("grad_scatter", lambda: lib.arco_grad_scatter(d, g_anchor.data_ptr(), pix.data_ptr(), go.data_ptr(), grad.data_ptr(), sp)),
+    ]
+    acc = {name: 0.0 for name, _ in calls}
+    for it in range(iters + 2):
+        for name, fn in calls:
+            if flush is not None:
+                flush.fill_(it & 0xff)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn()
+            e1.record()
+            _cabi.check(rc, name)
+            e1.synchronize()
+            if it >= 2:
+                acc[name] += e0.elapsed_time(e1)
+    ms = {k: v / iters for k, v in acc.items()}
+    plan = _cabi.Plan.from_buffer_copy(ws[L.plan: L.plan + C.sizeof(_cabi.Plan)].cpu().numpy().tobytes())
+    P = spec.pixels
+    e_t = 2 if spec.dtype == "bf16" else 4
+    P_lv = sum(int(plan.lv_count[c]) for c in range(Cn))
+    K = sum(min(int(plan.n_key[c]), caps[c]) for c in range(Cn))
+    Cv = sum(1 for j in range(Cn) if plan.slot_active[j])
+    alg = {
+        "classify_count": P * (8 * Cn + 4 * Cn + 8) + P,
+        "scan_plan": 2 * Cn * L.n_tiles * 8,
+        "proto_enqueue": P_lv * D * e_t + K * D * (e_t + 4) + P,
+        "sample": Cv * (Q + Q * N) * 4,
+        "infonce": Cv * Q * D * e_t + Cv * Q * N * D * 4 + Cv * Q * D * 4,
+        "grad_scatter": P * D * e_t + Cv * Q * D * (4 + 2 * e_t),
+    }
+    peak, peak_src = peaks()
+    stages = {k: {"ms": ms[k], "alg_bytes": alg[k], "gbs": alg[k] / (ms[k] * 1e-3) / 1e9,
+                  "frac_hbm": alg[k] / (ms[k] * 1e-3) / 1e9 / peak} for k in ms}
+    stages["_measured"] = {"P_lv": P_lv, "K": K, "C_v": Cv, "sum_ms": sum(ms.values())}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(spec.name, {}).get("proto_enqueue")
+        except Exception:
+            traffic = None
+    k = "proto_enqueue"
+    roof = {"kernel": "arco::proto_enqueue_kernel (+ proto_finalize, <1% of the call)", "bound": "hbm",
+            "achieved": stages[k]["gbs"], "peak": peak, "unit": "GB/s", "frac": stages[k]["frac_hbm"],
+            "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg[k], "ms_per_launch": ms[k],
+            "bytes_formula": "P_lv*D*e_t + K*D*(e_t+4) + P  (SURVEY.md section 8(d) teacher-read and key terms + 1 code byte per pixel)"}
+    return stages, roof
+
+
+def run_e2e(torch, arco_b200, spec, x, memobank, ptrs, caps, dev, kw, world, steps, sync_all):
+    names = ("rep", "rep_teacher", "label_l", "label_u", "prob_l", "prob_u", "low_mask", "high_mask")
+    host = {k: torch.empty(x[k].shape, dtype=x[k].dtype, pin_memory=True).copy_(x[k].detach()) for k in names}
+    stage = {k: torch.empty_like(x[k].detach()) for k in names}
+    host_loss = torch.empty(1, dtype=torch.float32, pin_memory=True)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in names)
+
+    def one():
+        for k in names:
+            stage[k].copy_(host[k], non_blocking=True)
+        rep = stage["rep"].requires_grad_(True)
+        rep.grad = None
+        _, loss = arco_b200.compute_contra_memobank_loss(
+            rep, stage["label_l"], stage["label_u"], stage["prob_l"], stage["prob_u"], stage["low_mask"],
+            stage["high_mask"], memobank, ptrs, caps, stage["rep_teacher"], **kw)
+        loss.backward()
+        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        stage["rep"] = rep.detach()
+
+    one()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    sync_all()
+    return {"value": None, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": steps,
+            "_total_ms": e0.elapsed_time(e1),
+            "note": "public op arco_b200.compute_contra_memobank_loss; every input copied from pinned host memory "
+                    "each step, loss read back; grad_rep stays on the device as in training"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -75,11 +75,11 @@ def classify_pixels(label_l, label_u, prob_l, prob_u, low_mask, high_mask, delta
     # rank of every class under a stable descending sort (pinned tie rule, see module docstring)
     order = torch.sort(prob, dim=1, descending=True, stable=True).indices   # [B,C,S]
     rank = torch.empty_like(order)
-    rank.scatter_(1, order, torch.arange(C).view(1, C, 1).expand_as(order))
+    rank.scatter_(1, order, torch.arange(C, device=prob.device).view(1, C, 1).expand_as(order))
 
     in_top = rank < LOW_RANK                                        # class sits in ranks [0,3)   (:395)
     in_mid = (rank >= LOW_RANK) & (rank < HIGH_RANK)                # class sits in ranks [3,20)  (:388-390)
-    is_lab = torch.arange(B).view(B, 1, 1) < n_lab
+    is_lab = torch.arange(B, device=prob.device).view(B, 1, 1) < n_lab
     # labelled images: top-3 AND the pixel is NOT labelled with this class (:397-399) -- combined with
     # the hard mask (which needs the label) this is always empty (trap 3); kept for fidelity.
     class_mask = torch.where(is_lab, in_top & (lab == 0), in_mid)
@@ -135,7 +135,7 @@ def contra_memobank_loss(
     res = OracleResult(new_keys=[], loss=None, classes=px)
 
     anchor_feats, protos = [], []
-    local = torch.zeros(C, D + 1, dtype=torch.float64)
+    local = torch.zeros(C, D + 1, dtype=torch.float64, device=rep.device)
     for c in range(C):
         a_idx = torch.nonzero(px.anchor[c]).flatten()
         k_idx = torch.nonzero(px.key[c]).flatten()
@@ -166,8 +166,8 @@ def contra_memobank_loss(
         return res
 
     n_slots = len(present)
-    total = torch.tensor(0.0)
-    proto_out = torch.zeros(C, num_queries, 1, D)
+    total = torch.tensor(0.0, device=rep.device)
+    proto_out = torch.zeros(C, num_queries, 1, D, device=rep.device)
     for pos in range(n_slots):
         # trap 1: anchors and prototype are addressed by loop POSITION, the bank by CLASS ID (:437-438,:455,:466,:481)
         bank_class = present[pos]
@@ -180,10 +180,10 @@ def contra_memobank_loss(
             continue
         slot["active"] = True
         idx_a = sampler(n_anchor, num_queries)
-        queries = anchor_feats[pos][idx_a]                                   # [Q,D] trap 8: duplicates allowed
+        queries = anchor_feats[pos][idx_a.to(rep.device)]                    # [Q,D] trap 8: duplicates allowed
         with torch.no_grad():
             idx_n = sampler(bank.shape[0], num_queries * num_negatives)
-            negatives = bank[idx_n].reshape(num_queries, num_negatives, D)
+            negatives = bank[idx_n].reshape(num_queries, num_negatives, D).to(queries.device)   # .cuda() at :466
             positive = res.proto[pos].view(1, 1, D).repeat(num_queries, 1, 1)
             if momentum_prototype is not None:                               # a11 (:488-497)
                 if not (momentum_prototype == 0).all():
@@ -192,7 +192,7 @@ def contra_memobank_loss(
                 proto_out[bank_class] = positive.clone()
             keys = torch.cat((positive, negatives), dim=1)                   # [Q,1+N,D]
         logits = torch.cosine_similarity(queries.unsqueeze(1), keys, dim=2)  # (:503-505)
-        total = total + F.cross_entropy(logits / temp, torch.zeros(num_queries, dtype=torch.long))
+        total = total + F.cross_entropy(logits / temp, torch.zeros(num_queries, dtype=torch.long, device=logits.device))
         slot.update(idx_a=idx_a, idx_n=idx_n, logits=logits.detach())
     res.loss = total / n_slots                                               # (:511)
     if momentum_prototype is not None:
