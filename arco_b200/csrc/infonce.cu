@@ -5,7 +5,7 @@
 //   anchor_feat   = seg_feat_low_entropy_list[i][idx_a]            (:455-457)  -> rank-select on the
 //                   per-tile anchor offsets + in-tile select on the code bytes (no compacted list exists)
 //   negative_feat = memobank[valid_classes[i]][0][idx_n]           (:466-479)  -> ring-buffer rows fetched
-//                   with cp.async.bulk (TMA 1-D bulk copies) into warp-private double-buffered stages
+//                   with cp.async.bulk (TMA 1-D bulk copies) into warp-private stages (one per warp; occupancy hides the wait)
 //   all_feat / cosine_similarity / cross_entropy                   (:480-509)  -> online softmax; the
 //                   [Q,1+N,D] tensor is never materialised
 //   d loss / d anchor = (1/|a|) (Gw - (a_hat . Gw) a_hat),  Gw = sum_k w_k k_hat,  w_k = (p_k - [k=0])/temp
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
     float* a_hat = reinterpret_cast<float*>(smem_raw);            // [D]
     float* k0hat = a_hat + D;                                     // [D]
     float* gbuf = k0hat + D;                                      // [4][D]
-    float* stage = gbuf + 4 * D;                                  // [4][2][KC*RS]
-    __shared__ __align__(8) uint64_t bars[4][2];
+    float* stage = gbuf + 4 * D;                                  // [4][KC*RS]  one stage per warp
+    __shared__ __align__(8) uint64_t bars[4];
     __shared__ float s_red[4][2];
     __shared__ float s_stats[4][3];
     __shared__ int s_pix;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         const float* bank = p.bank_rows + p.row_off[bank_cls] * D;
         const float inv_scale = pl->inv_scale;
 
-        if (tid < 8) mbar_init(&bars[tid >> 1][tid & 1], 1);
+        if (tid < 4) mbar_init(&bars[tid], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
         // ---- anchor rank-select: idx-th anchor candidate of class j (... anchors by POSITION j) ----
@@ -199,21 +199,21 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         const int cnt = n_end - n_begin;
         const int nchunks = (cnt + KC - 1) / KC;
         const int32_t* my_idx = p.idx_n + ((int64_t)j * p.Q + q) * p.N + n_begin;
-        float* wstage = stage + (size_t)warp * 2 * KC * RS;
+        float* wstage = stage + (size_t)warp * KC * RS;
         const uint32_t row_bytes = (uint32_t)D * 4u;
 
+        // Occupancy instead of double buffering: a warp owns ONE stage (<= 9 KB); with ~5 CTAs (20 warps) per
+        // SM the other warps' gathers and math hide this warp's wait.
         auto issue = [&](int chunk) {
-            const int buf = chunk & 1;
             const int nv = min(KC, cnt - chunk * KC);
-            if (lane == 0) mbar_expect_tx(&bars[warp][buf], (uint32_t)nv * row_bytes);
+            if (lane == 0) mbar_expect_tx(&bars[warp], (uint32_t)nv * row_bytes);
             __syncwarp();
             if (lane < nv) {
                 int r = my_idx[chunk * KC + lane];
                 r = min(max(r, 0), blen - 1);
                 int phys = bhead + r;
                 if (phys >= cap) phys -= cap;
-                bulk_g2s(wstage + (size_t)buf * KC * RS + (size_t)lane * RS, bank + (int64_t)phys * D, row_bytes,
-                         &bars[warp][buf]);
+                bulk_g2s(wstage + (size_t)lane * RS, bank + (int64_t)phys * D, row_bytes, &bars[warp]);
             }
         };
 
@@ -228,22 +228,23 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         for (int it = 0; it < MAXIT; ++it) G[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4* a4 = reinterpret_cast<const float4*>(a_hat);
 
-        if (nchunks > 0) issue(0);
         for (int chunk = 0; chunk < nchunks; ++chunk) {
-            if (chunk + 1 < nchunks) issue(chunk + 1);
-            const int buf = chunk & 1;
-            mbar_wait(&bars[warp][buf], (uint32_t)((chunk >> 1) & 1));
+            issue(chunk);
+            mbar_wait(&bars[warp], (uint32_t)(chunk & 1));
             const int nv = min(KC, cnt - chunk * KC);
-            const float* rows = wstage + (size_t)buf * KC * RS;
+            const float* rows = wstage;
             // pass 1: lane (key kq, segment seg) -> dot and squared norm
             float dot = 0.f, n2 = 0.f;
             if (kq < nv) {
                 const float4* r4 = reinterpret_cast<const float4*>(rows + (size_t)kq * RS);
+                float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = d4;   // 8 independent FMA chains
                 for (int ch = seg; ch < CPL; ch += DSEG) {
                     const float4 kv = r4[ch], av = a4[ch];
-                    dot += kv.x * av.x + kv.y * av.y + kv.z * av.z + kv.w * av.w;
-                    n2 += kv.x * kv.x + kv.y * kv.y + kv.z * kv.z + kv.w * kv.w;
+                    d4.x += kv.x * av.x; d4.y += kv.y * av.y; d4.z += kv.z * av.z; d4.w += kv.w * av.w;
+                    n4.x += kv.x * kv.x; n4.y += kv.y * kv.y; n4.z += kv.z * kv.z; n4.w += kv.w * kv.w;
                 }
+                dot = (d4.x + d4.y) + (d4.z + d4.w);
+                n2 = (n4.x + n4.y) + (n4.z + n4.w);
             }
             for (int o = KC; o < 32; o <<= 1) {
                 dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -387,7 +388,7 @@ extern "C" int arco_infonce(const arco_dims* dims, const void* rep, const arco_b
     int rs4 = cpl;
     if (kc >= 8) { while ((rs4 & 1) == 0) ++rs4; } else { while ((rs4 & 3) != 2) ++rs4; }
     p.KC = kc; p.RS = rs4 * 4;
-    const size_t smem = (size_t)6 * d.feat * 4 + (size_t)4 * 2 * kc * p.RS * 4;
+    const size_t smem = (size_t)6 * d.feat * 4 + (size_t)4 * kc * p.RS * 4;
     const int grid = d.classes * d.queries;
     cudaStream_t st = (cudaStream_t)stream;
     if (d.feat <= 128) {

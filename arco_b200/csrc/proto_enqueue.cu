@@ -381,11 +381,16 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
         const int64_t s_tile = (int64_t)(t_next % p.tpi) * ARCO_TILE;
         const int64_t s = s_tile + (int64_t)sub_next * SP + (int64_t)pg * PER16;
         const T* rowp = rep + ((int64_t)b * D + d0 + 8 * bc) * S + s;
-        const bool in = s < S;
+        if (ld_rows == 8 && s < S) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            raw[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (j < ld_rows && in) raw[j] = ldg_nc_u4(rowp + (int64_t)j * S);
+            for (int j = 0; j < 8; ++j) { raw[j] = ldg_nc_u4(rowp); rowp += S; }
+        } else {
+            const bool in = s < S;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                raw[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (j < ld_rows && in) raw[j] = ldg_nc_u4(rowp + (int64_t)j * S);
+            }
         }
         if (sub_next == 0) {
             const int64_t s4 = s_tile + 4 * tid;
@@ -438,22 +443,35 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
         const uint32_t w0 = sc_words[px0 / 4];
         const uint32_t w1 = RW == 2 ? sc_words[px0 / 4 + 1] : 0u;
         if (has_lv) {
-            uint32_t lv = ((w0 >> 5) & 1u) | ((w0 >> 12) & 2u) | ((w0 >> 19) & 4u) | ((w0 >> 26) & 8u) |
-                          ((w1 >> 1) & 16u) | ((w1 >> 8) & 32u) | ((w1 >> 15) & 64u) | ((w1 >> 22) & 128u);
-            while (lv) {
-                const int k = __ffs(lv) - 1;
-                lv &= lv - 1;
+            // R pixels per stream, unrolled: bit tests, class extraction and the tile offset are compile-time
+            // constants (px0 is a multiple of R, so the swizzle rotation of all R pixels equals `stream`).
+            const uint4* trow = tile + px0 * NCH + ((ci + stream) & (NCH - 1));
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
                 const uint32_t wsel = (k & 4) ? w1 : w0;
-                const int cls = (int)((wsel >> (8 * (k & 3))) & CODE_CLS_MASK);
-                float4 lo, hi;
-                fetch(px0 + k, lo, hi);
-                if (cls != cur) {
-                    flush();
-                    cur = cls;
-                    ra = lo; rb = hi;
-                } else {
-                    ra.x += lo.x; ra.y += lo.y; ra.z += lo.z; ra.w += lo.w;
-                    rb.x += hi.x; rb.y += hi.y; rb.z += hi.z; rb.w += hi.w;
+                const uint32_t code = wsel >> (8 * (k & 3));
+                if (code & CODE_LV) {
+                    const int cls = (int)(code & CODE_CLS_MASK);
+                    float4 lo, hi;
+                    if (LW == 2) {
+                        const uint4 u = trow[k * NCH], w = trow[PLANE + k * NCH];
+                        lo = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+                        hi = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+                    } else {
+                        const uint4 u = trow[k * NCH];
+                        lo = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                                         __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+                        hi = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u),
+                                         __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+                    }
+                    if (cls != cur) {
+                        flush();
+                        cur = cls;
+                        ra = lo; rb = hi;
+                    } else {
+                        ra.x += lo.x; ra.y += lo.y; ra.z += lo.z; ra.w += lo.w;
+                        rb.x += hi.x; rb.y += hi.y; rb.z += hi.z; rb.w += hi.w;
+                    }
                 }
             }
         }
@@ -522,6 +540,74 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Small-problem variant (C <= 3, D in {16, 32}; LA 3-D V-Net: C=2, D=16).  With C <= low_rank=3 no class
+// can ever rank in [3,20), so no key exists (trap 3) and the pass is a pure masked reduction: thread <->
+// 16-byte pixel group, all D rows of the group in flight at once, C*D register accumulators, no shared
+// memory staging and no barrier in the streaming loop.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int CC, int DD>
+__global__ void __launch_bounds__(256) proto_small_kernel(ProtoParams p) {
+    constexpr int PER16 = Wide<T>::PER16;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t S = p.S;
+    const int64_t gps = S / PER16;                        // pixel groups per image
+    const int64_t groups = (int64_t)p.B * gps;
+    const T* rep = reinterpret_cast<const T*>(p.rep_t);
+    float acc[CC][DD];
+#pragma unroll
+    for (int c = 0; c < CC; ++c)
+#pragma unroll
+        for (int d = 0; d < DD; ++d) acc[c][d] = 0.f;
+
+    for (int64_t g = (int64_t)blockIdx.x * 256 + tid; g < groups; g += (int64_t)gridDim.x * 256) {
+        const int64_t b = g / gps, s = (g - b * gps) * PER16;
+        // code bytes and all D rows are requested together (no dependent round trip); with the iid / 20 % masks
+        // of this workload every 32-byte sector holds a low-valid pixel anyway
+        uint32_t cw[PER16 / 4];
+#pragma unroll
+        for (int q = 0; q < PER16 / 4; ++q) cw[q] = *reinterpret_cast<const uint32_t*>(p.codes + b * S + s + 4 * q);
+        const T* rowp = rep + b * DD * S + s;
+        uint4 raw[DD];
+#pragma unroll
+        for (int d = 0; d < DD; ++d) { raw[d] = ldg_nc_u4(rowp); rowp += S; }
+#pragma unroll
+        for (int k = 0; k < PER16; ++k) {
+            const uint32_t code = cw[k >> 2] >> (8 * (k & 3));
+            const bool lv = code & CODE_LV;
+            const int cls = (int)(code & CODE_CLS_MASK);
+#pragma unroll
+            for (int d = 0; d < DD; ++d) {
+                const uint32_t* r = &raw[d].x;
+                float x;
+                if (PER16 == 4) x = __uint_as_float(r[k]);
+                else x = (k & 1) ? __uint_as_float(r[k >> 1] & 0xffff0000u) : __uint_as_float(r[k >> 1] << 16);
+#pragma unroll
+                for (int c = 0; c < CC; ++c)
+                    if (lv && cls == c) acc[c][d] += x;
+            }
+        }
+    }
+    // deterministic block reduction: lanes, then warps in fixed order
+    __shared__ float s_part[8][CC * DD];
+#pragma unroll
+    for (int c = 0; c < CC; ++c)
+#pragma unroll
+        for (int d = 0; d < DD; ++d) {
+            float v = acc[c][d];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_part[warp][c * DD + d] = v;
+        }
+    __syncthreads();
+    if (tid < CC * DD) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += s_part[w][tid];
+        p.partials[(int64_t)blockIdx.x * CC * DD + tid] = v;
+    }
+}
+
 __global__ void proto_finalize_kernel(const float* __restrict__ partials, int rows, int C, int D,
                                       const arco_plan* __restrict__ plan, double* __restrict__ proto_sums) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -536,6 +622,7 @@ __global__ void proto_finalize_kernel(const float* __restrict__ partials, int ro
 // Kernel variant for a problem: the 8-dims-per-lane kernel needs 16-byte vector loads and its 8 KB * C
 // stream accumulators to fit beside the tile; otherwise the 4-dims-per-lane kernel (4 KB * C) runs.
 struct ProtoCfg {
+    bool small;       // proto_small_kernel (C <= 3, D in {16,32}: no keys can exist)
     bool wide;        // proto8_kernel
     int nch;          // lanes per stream
     int dchunk;       // feature dims per CTA
@@ -549,6 +636,8 @@ static bool proto_vec_ok(const arco_dims& d) {
 
 static ProtoCfg proto_cfg(const arco_dims& d) {
     ProtoCfg c;
+    c.small = d.classes <= 3 && (d.feat == 16 || d.feat == 32) && proto_vec_ok(d);
+    if (c.small) { c.wide = false; c.nch = 0; c.dchunk = d.feat; c.smem = 0; return c; }
     c.wide = d.classes <= 8 && d.feat >= 32 && proto_vec_ok(d);
     if (c.wide) {
         c.nch = d.feat <= 64 ? 8 : 16;
@@ -580,6 +669,7 @@ static int kernel_occupancy(K kernel, size_t smem) {
 // grid geometry shared by the workspace layout and the launch: one resident wave of persistent CTAs
 static void proto_grid(const arco_dims& d, int* ndc, int* groups) {
     const ProtoCfg c = proto_cfg(d);
+    if (c.small) { *ndc = 1; *groups = sm_count() * 4; return; }
     *ndc = (d.feat + c.dchunk - 1) / c.dchunk;
     const bool bf = d.rep_dtype == ARCO_BF16;
     int occ;
@@ -609,7 +699,12 @@ template <typename T>
 static int launch_proto(const arco_dims& d, const ProtoParams& p, int groups, cudaStream_t st) {
     const ProtoCfg c = proto_cfg(d);
     const int grid = groups * p.NDC;
-    if (c.wide) {
+    if (c.small) {
+#define ARCO_SMALL(CC, DD) proto_small_kernel<T, CC, DD><<<grid, 256, 0, st>>>(p)
+        if (d.feat == 16) { if (d.classes == 1) ARCO_SMALL(1, 16); else if (d.classes == 2) ARCO_SMALL(2, 16); else ARCO_SMALL(3, 16); }
+        else { if (d.classes == 1) ARCO_SMALL(1, 32); else if (d.classes == 2) ARCO_SMALL(2, 32); else ARCO_SMALL(3, 32); }
+#undef ARCO_SMALL
+    } else if (c.wide) {
         if (c.nch == 16) proto8_kernel<T, 16><<<grid, 256, c.smem, st>>>(p);
         else proto8_kernel<T, 8><<<grid, 256, c.smem, st>>>(p);
     } else {
