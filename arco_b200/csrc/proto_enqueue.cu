@@ -274,34 +274,42 @@ __global__ void __launch_bounds__(256) proto_enqueue_kernel(ProtoParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// 8-dims-per-lane variant (C <= 8): each lane owns 8 feature dims of its stream's pixel, which halves
-// the per-pixel bookkeeping per element.  fp32 data is staged as two float4 planes, bf16 data stays
-// PACKED in shared memory (one uint4 = 8 dims) and is widened only when it is accumulated.
-// D-chunk = 8*NCH dims; tile = 32 KB; stream-private accumulators = 8 KB * C.
+// Software-pipelined main kernel.  EPL = feature dims per lane:
+//   EPL = 8 (C <= 8): fp32 data is staged as two float4 planes, bf16 data stays PACKED in shared memory
+//                     (one uint4 = 8 dims) and is widened only when it is accumulated; D-chunk = 8*NCH;
+//                     stream-private accumulators = 8 KB * C.
+//   EPL = 4 (C  > 8): one float4 plane (bf16 widened at commit); D-chunk = 4*NCH; accumulators = 4 KB * C.
+// Tile = 32 KB.  Stages: A (issue) global loads of sub-tile i+1 into registers, B (commit) registers ->
+// transposed + rotation-swizzled shared tile, C (compute) per-stream accumulation and key enqueue of
+// sub-tile i.  The loads of A stay in flight during C.
 // ---------------------------------------------------------------------------------------------------
 template <typename T> struct Wide;
-template <> struct Wide<float> { static constexpr int LW = 2, PER16 = 4; };
-template <> struct Wide<__nv_bfloat16> { static constexpr int LW = 1, PER16 = 8; };
+template <> struct Wide<float> { static constexpr int PER16 = 4; };
+template <> struct Wide<__nv_bfloat16> { static constexpr int PER16 = 8; };
 
-template <typename T, int NCH>
-__global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
-    constexpr int LW = Wide<T>::LW;          // 16-byte words per (pixel, lane)
+template <typename T, int NCH, int EPL>
+__global__ void __launch_bounds__(256, 2) proto_pipe_kernel(ProtoParams p) {
     constexpr int PER16 = Wide<T>::PER16;    // pixels per 16-byte global load
+    constexpr bool PACKED = (EPL == 8 && PER16 == 8);            // bf16 kept packed in shared memory
+    constexpr int LW = (EPL == 8 && PER16 == 4) ? 2 : 1;        // 16-byte words per (pixel, lane)
     constexpr int PXS = 32 / NCH;
     constexpr int NS = 8 * PXS;
     constexpr int SP = 2048 / (NCH * LW);    // pixels per staged sub-tile (32 KB)
     constexpr int NSUB = ARCO_TILE / SP;
-    constexpr int R = SP / NS;               // pixels per stream per sub-tile (4 for fp32, 8 for bf16)
+    constexpr int R = SP / NS;               // pixels per stream per sub-tile (4 or 8)
     constexpr int RW = R / 4;                // code words per stream
-    constexpr int ROT = (PER16 == 4) ? 2 : 3;
+    constexpr int ROT = (PER16 == 4) ? 2 : 3;   // swizzle rotation = pixel >> ROT: conflict-free 16-byte commits
+    constexpr int RG = (R >> ROT) > 0 ? (R >> ROT) : 1;         // rotation groups inside a stream's R pixels
     constexpr int PLANE = SP * NCH;          // uint4 elements per plane
-    static_assert(NCH * (SP / PER16) == 256, "one (8 rows x PER16 px) block per thread");
+    constexpr int NBLK = NCH * (SP / PER16) / 256;              // (EPL rows x PER16 px) loader blocks per thread
+    constexpr int AP = EPL / 4;              // accumulator planes (float4 each)
+    static_assert(NBLK * 256 == NCH * (SP / PER16) && NBLK * EPL == 8 || (NBLK == 1 && EPL == 4), "loader geometry");
     static_assert(R == 4 || R == 8, "stream geometry");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* tile = reinterpret_cast<uint4*>(smem_raw);                         // [LW][SP][NCH]
-    float4* acc = reinterpret_cast<float4*>(tile + LW * PLANE);               // [2][NS][C][NCH]  (dims 0-3 / 4-7 planes)
-    uint32_t* sc_tile = reinterpret_cast<uint32_t*>(acc + 2 * NS * p.C * NCH);   // [2][256] code words of a tile, double buffered
+    float4* acc = reinterpret_cast<float4*>(tile + LW * PLANE);               // [AP][NS][C][NCH]
+    uint32_t* sc_tile = reinterpret_cast<uint32_t*>(acc + AP * NS * p.C * NCH);  // [2][256] code words of a tile, double buffered
     uint32_t* wrun = sc_tile + 2 * (ARCO_TILE / 4);                            // [8][32]
     __shared__ int32_t s_skip[ARCO_MAX_CLASSES], s_base[ARCO_MAX_CLASSES], s_cap[ARCO_MAX_CLASSES];
 
@@ -311,18 +319,14 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
     const int C = p.C, D = p.D;
     const int64_t S = p.S;
     const int dchunk = blockIdx.x % p.NDC, grp = blockIdx.x / p.NDC, ngrp = gridDim.x / p.NDC;
-    const int d0 = dchunk * NCH * 8;
-    const int dreal = min(NCH * 8, D - d0);                                   // multiple of 4
-    const int rows_on = max(0, min(8, dreal - 8 * ci));                       // 0, 4 or 8 real dims in this lane
+    const int d0 = dchunk * NCH * EPL;
+    const int dreal = min(NCH * EPL, D - d0);                                 // multiple of 4
+    const int rows_on = max(0, min(EPL, dreal - EPL * ci));                   // real dims in this lane (0, 4 or 8)
     const T* rep = reinterpret_cast<const T*>(p.rep_t);
     const int acc_plane = NS * C * NCH;
     float4* my_acc = acc + (size_t)stream * C * NCH + ci;
 
-    // loader role of this thread: rows [8*bc, 8*bc+8) x pixels [pg*PER16, +PER16) of every sub-tile
-    const int pg = tid % (SP / PER16), bc = tid / (SP / PER16);
-    const int ld_rows = max(0, min(8, dreal - 8 * bc));
-
-    for (int i = tid; i < 2 * acc_plane; i += 256) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < AP * acc_plane; i += 256) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < ARCO_MAX_CLASSES) {
         s_skip[tid] = p.plan->bank_skip[tid];
         s_base[tid] = p.plan->bank_write_base[tid];
@@ -338,40 +342,38 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
             float4 o = a[0];
             o.x += ra.x; o.y += ra.y; o.z += ra.z; o.w += ra.w;
             a[0] = o;
-            if (rows_on > 4) {
+            if (EPL == 8 && rows_on > 4) {
                 o = a[acc_plane];
                 o.x += rb.x; o.y += rb.y; o.z += rb.z; o.w += rb.w;
                 a[acc_plane] = o;
             }
         }
     };
-    // the 8 dims of (pixel pxl, this lane) as two float4
-    auto fetch = [&](int pxl, float4& lo, float4& hi) {
-        const int idx = pxl * NCH + ((ci + (pxl >> ROT)) & (NCH - 1));
-        if (LW == 2) {
-            const uint4 u = tile[idx], w = tile[PLANE + idx];
-            lo = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
-            hi = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
-        } else {
-            const uint4 u = tile[idx];        // 8 packed bf16: dims (0,1) (2,3) (4,5) (6,7)
+    // the EPL dims of a staged (pixel, lane) cell as float4 lo (dims 0-3) and hi (dims 4-7, EPL == 8 only)
+    auto widen = [&](const uint4* cell, float4& lo, float4& hi) {
+        const uint4 u = cell[0];
+        if (PACKED) {                                  // 8 packed bf16: dims (0,1) (2,3) (4,5) (6,7)
             lo = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
                              __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
             hi = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u),
                              __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+        } else {
+            lo = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+            hi = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (LW == 2) {
+                const uint4 w = cell[PLANE];
+                hi = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+            }
         }
     };
+    auto cell_of = [&](int pxl) { return tile + pxl * NCH + ((ci + (pxl >> ROT)) & (NCH - 1)); };
 
-    // ---- software pipeline over this CTA's (tile, sub-tile) sequence ----
-    // stage A (issue):   global loads of a sub-tile into registers (+ the tile's 1024 code bytes at sub 0)
-    // stage B (commit):  registers -> transposed, swizzled shared tile
-    // stage C (compute): per-stream accumulation and key enqueue
-    // The loads of sub-tile i+1 are in flight while sub-tile i is computed.
     int t_next = grp, sub_next = 0, par_next = 0;           // iterator of the issue stage
     auto skip_unflagged = [&]() {
         while (t_next < p.NT && p.tile_flagged[t_next] == 0) t_next += ngrp;
     };
     skip_unflagged();
-    uint4 raw[8];
+    uint4 raw[NBLK * EPL];
     uint32_t cw_reg = 0;
     int t_ld = -1, sub_ld = 0, par_ld = 0;                   // what `raw` currently holds
     auto issue = [&]() {
@@ -379,24 +381,30 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
         if (t_next >= p.NT) { t_ld = -1; return; }
         const int b = t_next / p.tpi;
         const int64_t s_tile = (int64_t)(t_next % p.tpi) * ARCO_TILE;
-        const int64_t s = s_tile + (int64_t)sub_next * SP + (int64_t)pg * PER16;
-        const T* rowp = rep + ((int64_t)b * D + d0 + 8 * bc) * S + s;
-        if (ld_rows == 8 && s < S) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { raw[j] = ldg_nc_u4(rowp); rowp += S; }
-        } else {
-            const bool in = s < S;
+        for (int blk = 0; blk < NBLK; ++blk) {
+            // loader block: rows [EPL*bc, +EPL) x pixels [pg*PER16, +PER16) of the sub-tile
+            const int id = blk * 256 + tid;
+            const int pg = id % (SP / PER16), bc = id / (SP / PER16);
+            const int ld_rows = max(0, min(EPL, dreal - EPL * bc));
+            const int64_t s = s_tile + (int64_t)sub_next * SP + (int64_t)pg * PER16;
+            const T* rowp = rep + ((int64_t)b * D + d0 + EPL * bc) * S + s;
+            if (ld_rows == EPL && s < S) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                raw[j] = make_uint4(0u, 0u, 0u, 0u);
-                if (j < ld_rows && in) raw[j] = ldg_nc_u4(rowp + (int64_t)j * S);
+                for (int j = 0; j < EPL; ++j) { raw[blk * EPL + j] = ldg_nc_u4(rowp); rowp += S; }
+            } else {
+                const bool in = s < S;
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    raw[blk * EPL + j] = make_uint4(0u, 0u, 0u, 0u);
+                    if (j < ld_rows && in) raw[blk * EPL + j] = ldg_nc_u4(rowp + (int64_t)j * S);
+                }
             }
         }
         if (sub_next == 0) {
             const int64_t s4 = s_tile + 4 * tid;
             cw_reg = s4 < S ? *reinterpret_cast<const uint32_t*>(p.codes + (int64_t)b * S + s4) : 0u;
         }
-        // advance the iterator
         ++sub_next;
         if (sub_next == NSUB || s_tile + (int64_t)sub_next * SP >= S) {
             sub_next = 0;
@@ -411,20 +419,34 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
         const int t = t_ld, sub = sub_ld, par = par_ld;
         // ---- stage B: commit registers to the shared tile ----
 #pragma unroll
-        for (int k = 0; k < PER16; ++k) {
-            const int pxl = pg * PER16 + k;
-            const int idx = pxl * NCH + ((bc + (pxl >> ROT)) & (NCH - 1));
-            const uint32_t* r0 = &raw[0].x; const uint32_t* r1 = &raw[1].x; const uint32_t* r2 = &raw[2].x;
-            const uint32_t* r3 = &raw[3].x; const uint32_t* r4 = &raw[4].x; const uint32_t* r5 = &raw[5].x;
-            const uint32_t* r6 = &raw[6].x; const uint32_t* r7 = &raw[7].x;
-            if (LW == 2) {
-                tile[idx] = make_uint4(r0[k], r1[k], r2[k], r3[k]);
-                tile[PLANE + idx] = make_uint4(r4[k], r5[k], r6[k], r7[k]);
-            } else {
-                const int w = k >> 1;
-                const uint32_t sel = (k & 1) ? 0x7632u : 0x5410u;             // pick the k-th bf16 of two rows
-                tile[idx] = make_uint4(__byte_perm(r0[w], r1[w], sel), __byte_perm(r2[w], r3[w], sel),
-                                       __byte_perm(r4[w], r5[w], sel), __byte_perm(r6[w], r7[w], sel));
+        for (int blk = 0; blk < NBLK; ++blk) {
+            const int id = blk * 256 + tid;
+            const int pg = id % (SP / PER16), bc = id / (SP / PER16);
+            const uint32_t* r0 = &raw[blk * EPL + 0].x; const uint32_t* r1 = &raw[blk * EPL + 1].x;
+            const uint32_t* r2 = &raw[blk * EPL + 2].x; const uint32_t* r3 = &raw[blk * EPL + 3].x;
+#pragma unroll
+            for (int k = 0; k < PER16; ++k) {
+                const int pxl = pg * PER16 + k;
+                const int idx = pxl * NCH + ((bc + (pxl >> ROT)) & (NCH - 1));
+                if (EPL == 8) {
+                    const uint32_t* r4 = &raw[blk * EPL + (EPL == 8 ? 4 : 0)].x; const uint32_t* r5 = &raw[blk * EPL + (EPL == 8 ? 5 : 0)].x;
+                    const uint32_t* r6 = &raw[blk * EPL + (EPL == 8 ? 6 : 0)].x; const uint32_t* r7 = &raw[blk * EPL + (EPL == 8 ? 7 : 0)].x;
+                    if (PACKED) {
+                        const int w = k >> 1;
+                        const uint32_t sel = (k & 1) ? 0x7632u : 0x5410u;         // pick the k-th bf16 of two rows
+                        tile[idx] = make_uint4(__byte_perm(r0[w], r1[w], sel), __byte_perm(r2[w], r3[w], sel),
+                                               __byte_perm(r4[w], r5[w], sel), __byte_perm(r6[w], r7[w], sel));
+                    } else {
+                        tile[idx] = make_uint4(r0[k], r1[k], r2[k], r3[k]);
+                        tile[PLANE + idx] = make_uint4(r4[k], r5[k], r6[k], r7[k]);
+                    }
+                } else if (PER16 == 4) {
+                    tile[idx] = make_uint4(r0[k], r1[k], r2[k], r3[k]);
+                } else {
+                    const int w = k >> 1;                                          // widen bf16 -> fp32 bits
+                    if (k & 1) tile[idx] = make_uint4(r0[w] & 0xffff0000u, r1[w] & 0xffff0000u, r2[w] & 0xffff0000u, r3[w] & 0xffff0000u);
+                    else tile[idx] = make_uint4(r0[w] << 16, r1[w] << 16, r2[w] << 16, r3[w] << 16);
+                }
             }
         }
         if (sub == 0) sc_tile[par * (ARCO_TILE / 4) + tid] = cw_reg;
@@ -443,9 +465,11 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
         const uint32_t w0 = sc_words[px0 / 4];
         const uint32_t w1 = RW == 2 ? sc_words[px0 / 4 + 1] : 0u;
         if (has_lv) {
-            // R pixels per stream, unrolled: bit tests, class extraction and the tile offset are compile-time
-            // constants (px0 is a multiple of R, so the swizzle rotation of all R pixels equals `stream`).
-            const uint4* trow = tile + px0 * NCH + ((ci + stream) & (NCH - 1));
+            // R pixels per stream, unrolled: bit tests, class extraction and the tile offsets are compile-time
+            // constants relative to RG per-stream base pointers (pixels of one rotation group share a rotation).
+            const uint4* tbase[RG];
+#pragma unroll
+            for (int g = 0; g < RG; ++g) tbase[g] = cell_of(px0 + (g << ROT));
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 const uint32_t wsel = (k & 4) ? w1 : w0;
@@ -453,24 +477,14 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
                 if (code & CODE_LV) {
                     const int cls = (int)(code & CODE_CLS_MASK);
                     float4 lo, hi;
-                    if (LW == 2) {
-                        const uint4 u = trow[k * NCH], w = trow[PLANE + k * NCH];
-                        lo = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
-                        hi = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
-                    } else {
-                        const uint4 u = trow[k * NCH];
-                        lo = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
-                                         __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
-                        hi = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u),
-                                         __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
-                    }
+                    widen(tbase[RG == 1 ? 0 : (k >> ROT)] + (RG == 1 ? k : (k & ((1 << ROT) - 1))) * NCH, lo, hi);
                     if (cls != cur) {
                         flush();
                         cur = cls;
                         ra = lo; rb = hi;
                     } else {
                         ra.x += lo.x; ra.y += lo.y; ra.z += lo.z; ra.w += lo.w;
-                        rb.x += hi.x; rb.y += hi.y; rb.z += hi.z; rb.w += hi.w;
+                        if (EPL == 8) { rb.x += hi.x; rb.y += hi.y; rb.z += hi.z; rb.w += hi.w; }
                     }
                 }
             }
@@ -502,10 +516,10 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
                         const uint32_t cap = (uint32_t)s_cap[cls];
                         const uint32_t pos = ((uint32_t)s_base[cls] + ord % cap) % cap;
                         float4 lo, hi;
-                        fetch(target, lo, hi);
-                        float4* dst = reinterpret_cast<float4*>(p.bank_rows + (p.row_off[cls] + pos) * D + d0 + 8 * ci);
+                        widen(cell_of(target), lo, hi);
+                        float4* dst = reinterpret_cast<float4*>(p.bank_rows + (p.row_off[cls] + pos) * D + d0 + EPL * ci);
                         dst[0] = lo;
-                        if (rows_on > 4) dst[1] = hi;
+                        if (EPL == 8 && rows_on > 4) dst[1] = hi;
                     }
                 }
             }
@@ -527,16 +541,16 @@ __global__ void __launch_bounds__(256, 2) proto8_kernel(ProtoParams p) {
     }
     flush();
     __syncthreads();
-    for (int i = tid; i < C * NCH * 2; i += 256) {
+    for (int i = tid; i < C * NCH * AP; i += 256) {
         const int h = i / (C * NCH), c = (i / NCH) % C, k = i % NCH;
-        if (8 * k + 4 * h >= dreal) continue;
+        if (EPL * k + 4 * h >= dreal) continue;
         float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
         for (int w = 0; w < NS; ++w) {
             const float4 a = acc[(size_t)h * acc_plane + ((size_t)w * C + c) * NCH + k];
             sum.x += a.x; sum.y += a.y; sum.z += a.z; sum.w += a.w;
         }
-        *reinterpret_cast<float4*>(p.partials + ((int64_t)grp * C + c) * D + d0 + 8 * k + 4 * h) = sum;
+        *reinterpret_cast<float4*>(p.partials + ((int64_t)grp * C + c) * D + d0 + EPL * k + 4 * h) = sum;
     }
 }
 
@@ -608,23 +622,32 @@ __global__ void __launch_bounds__(256) proto_small_kernel(ProtoParams p) {
     }
 }
 
-__global__ void proto_finalize_kernel(const float* __restrict__ partials, int rows, int C, int D,
-                                      const arco_plan* __restrict__ plan, double* __restrict__ proto_sums) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per output element: lanes stride over the partial rows (independent loads in flight), then a
+// fixed-order shuffle tree in fp64 -- deterministic, and the fp64 buffer is what a multi-GPU caller all-reduces.
+__global__ void __launch_bounds__(128) proto_finalize_kernel(const float* __restrict__ partials, int rows, int C, int D,
+                                                            const arco_plan* __restrict__ plan,
+                                                            double* __restrict__ proto_sums) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (i >= C * (D + 1)) return;
     const int c = i / (D + 1), d = i % (D + 1);
-    if (d == D) { proto_sums[i] = (double)plan->lv_count[c]; return; }
+    if (d == D) {
+        if (lane == 0) proto_sums[i] = (double)plan->lv_count[c];
+        return;
+    }
     double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += (double)partials[((int64_t)r * C + c) * D + d];
-    proto_sums[i] = s;
+    for (int r = lane; r < rows; r += 32) s += (double)partials[((int64_t)r * C + c) * D + d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) proto_sums[i] = s;
 }
 
 // Kernel variant for a problem: the 8-dims-per-lane kernel needs 16-byte vector loads and its 8 KB * C
 // stream accumulators to fit beside the tile; otherwise the 4-dims-per-lane kernel (4 KB * C) runs.
 struct ProtoCfg {
-    bool small;       // proto_small_kernel (C <= 3, D in {16,32}: no keys can exist)
-    bool wide;        // proto8_kernel
+    int kind;         // 0 scalar fallback (proto_enqueue_kernel), 1 pipelined (proto_pipe_kernel), 2 small (proto_small_kernel)
     int nch;          // lanes per stream
+    int epl;          // feature dims per lane
     int dchunk;       // feature dims per CTA
     size_t smem;
 };
@@ -636,17 +659,17 @@ static bool proto_vec_ok(const arco_dims& d) {
 
 static ProtoCfg proto_cfg(const arco_dims& d) {
     ProtoCfg c;
-    c.small = d.classes <= 3 && (d.feat == 16 || d.feat == 32) && proto_vec_ok(d);
-    if (c.small) { c.wide = false; c.nch = 0; c.dchunk = d.feat; c.smem = 0; return c; }
-    c.wide = d.classes <= 8 && d.feat >= 32 && proto_vec_ok(d);
-    if (c.wide) {
-        c.nch = d.feat <= 64 ? 8 : 16;
-        c.dchunk = c.nch * 8;
-        const int lw = d.rep_dtype == ARCO_BF16 ? 1 : 2;
-        const int sp = 2048 / (c.nch * lw);
-        c.smem = (size_t)32768 + (size_t)8 * (32 / c.nch) * d.classes * c.nch * 32 + 2 * ARCO_TILE + 8 * 32 * 4;
-        (void)sp;
+    const bool vec = proto_vec_ok(d);
+    if (vec && d.classes <= 3 && (d.feat == 16 || d.feat == 32)) { c.kind = 2; c.nch = 0; c.epl = 0; c.dchunk = d.feat; c.smem = 0; return c; }
+    if (vec) {
+        c.kind = 1;
+        c.epl = (d.classes <= 8 && d.feat >= 32) ? 8 : 4;
+        c.nch = d.feat <= 8 * c.epl ? 8 : 16;
+        c.dchunk = c.nch * c.epl;
+        c.smem = (size_t)32768 + (size_t)(c.epl / 4) * 8 * (32 / c.nch) * d.classes * c.nch * 16 + 2 * ARCO_TILE + 8 * 32 * 4;
     } else {
+        c.kind = 0;
+        c.epl = 4;
         c.nch = d.feat <= 32 ? 8 : 16;
         c.dchunk = c.nch * 4;
         const int sp = 2048 / c.nch;
@@ -666,20 +689,21 @@ static int kernel_occupancy(K kernel, size_t smem) {
     return occ;
 }
 
+template <typename T>
+static int proto_occ(const ProtoCfg& c) {
+    if (c.kind == 1) {
+        if (c.epl == 8) return c.nch == 16 ? kernel_occupancy(proto_pipe_kernel<T, 16, 8>, c.smem) : kernel_occupancy(proto_pipe_kernel<T, 8, 8>, c.smem);
+        return c.nch == 16 ? kernel_occupancy(proto_pipe_kernel<T, 16, 4>, c.smem) : kernel_occupancy(proto_pipe_kernel<T, 8, 4>, c.smem);
+    }
+    return c.nch == 16 ? kernel_occupancy(proto_enqueue_kernel<T, 16>, c.smem) : kernel_occupancy(proto_enqueue_kernel<T, 8>, c.smem);
+}
+
 // grid geometry shared by the workspace layout and the launch: one resident wave of persistent CTAs
 static void proto_grid(const arco_dims& d, int* ndc, int* groups) {
     const ProtoCfg c = proto_cfg(d);
-    if (c.small) { *ndc = 1; *groups = sm_count() * 4; return; }
+    if (c.kind == 2) { *ndc = 1; *groups = sm_count() * 4; return; }
     *ndc = (d.feat + c.dchunk - 1) / c.dchunk;
-    const bool bf = d.rep_dtype == ARCO_BF16;
-    int occ;
-    if (c.wide) {
-        if (bf) occ = c.nch == 16 ? kernel_occupancy(proto8_kernel<__nv_bfloat16, 16>, c.smem) : kernel_occupancy(proto8_kernel<__nv_bfloat16, 8>, c.smem);
-        else occ = c.nch == 16 ? kernel_occupancy(proto8_kernel<float, 16>, c.smem) : kernel_occupancy(proto8_kernel<float, 8>, c.smem);
-    } else {
-        if (bf) occ = c.nch == 16 ? kernel_occupancy(proto_enqueue_kernel<__nv_bfloat16, 16>, c.smem) : kernel_occupancy(proto_enqueue_kernel<__nv_bfloat16, 8>, c.smem);
-        else occ = c.nch == 16 ? kernel_occupancy(proto_enqueue_kernel<float, 16>, c.smem) : kernel_occupancy(proto_enqueue_kernel<float, 8>, c.smem);
-    }
+    int occ = d.rep_dtype == ARCO_BF16 ? proto_occ<__nv_bfloat16>(c) : proto_occ<float>(c);
     // without a device (CPU-only build box) assume the shared-memory bound
     if (occ <= 0) occ = (int)((size_t)(227 * 1024) / (c.smem + 1024));
     if (occ > 8) occ = 8;
@@ -699,14 +723,19 @@ template <typename T>
 static int launch_proto(const arco_dims& d, const ProtoParams& p, int groups, cudaStream_t st) {
     const ProtoCfg c = proto_cfg(d);
     const int grid = groups * p.NDC;
-    if (c.small) {
+    if (c.kind == 2) {
 #define ARCO_SMALL(CC, DD) proto_small_kernel<T, CC, DD><<<grid, 256, 0, st>>>(p)
         if (d.feat == 16) { if (d.classes == 1) ARCO_SMALL(1, 16); else if (d.classes == 2) ARCO_SMALL(2, 16); else ARCO_SMALL(3, 16); }
         else { if (d.classes == 1) ARCO_SMALL(1, 32); else if (d.classes == 2) ARCO_SMALL(2, 32); else ARCO_SMALL(3, 32); }
 #undef ARCO_SMALL
-    } else if (c.wide) {
-        if (c.nch == 16) proto8_kernel<T, 16><<<grid, 256, c.smem, st>>>(p);
-        else proto8_kernel<T, 8><<<grid, 256, c.smem, st>>>(p);
+    } else if (c.kind == 1) {
+        if (c.epl == 8) {
+            if (c.nch == 16) proto_pipe_kernel<T, 16, 8><<<grid, 256, c.smem, st>>>(p);
+            else proto_pipe_kernel<T, 8, 8><<<grid, 256, c.smem, st>>>(p);
+        } else {
+            if (c.nch == 16) proto_pipe_kernel<T, 16, 4><<<grid, 256, c.smem, st>>>(p);
+            else proto_pipe_kernel<T, 8, 4><<<grid, 256, c.smem, st>>>(p);
+        }
     } else {
         if (c.nch == 16) proto_enqueue_kernel<T, 16><<<grid, 256, c.smem, st>>>(p);
         else proto_enqueue_kernel<T, 8><<<grid, 256, c.smem, st>>>(p);
@@ -746,7 +775,7 @@ extern "C" int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher
                                       : arco::launch_proto<float>(d, p, groups, st);
     if (rc != ARCO_OK) return rc;
     const int n = d.classes * (d.feat + 1);
-    arco::proto_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(p.partials, groups, d.classes, d.feat, p.plan, proto_sums);
+    arco::proto_finalize_kernel<<<(n + 3) / 4, 128, 0, st>>>(p.partials, groups, d.classes, d.feat, p.plan, proto_sums);
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
 }
