@@ -15,11 +15,12 @@ pointer) are device scalars updated by ``arco_scan_plan``; nothing crosses PCIe 
 The caller's lists are adopted lazily on the first call: ``memobank[c]`` is replaced by a
 :class:`BankSlot` (a ``list`` subclass) whose element 0 still answers ``.shape[0]`` and row indexing in
 logical FIFO order, and ``queue_ptrlis[c][0]`` is refreshed from the device bookkeeping whenever the
-host mirror is settled (:meth:`DeviceMemoryBank.settle`, called at the start of the next step and
-on any inspection).
+host mirror is refreshed (:meth:`DeviceMemoryBank.poll`, non-blocking, at the start of the next step;
+:meth:`DeviceMemoryBank.settle`, blocking, on any inspection).
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 from typing import List, Optional, Sequence
 
@@ -91,7 +92,8 @@ class DeviceMemoryBank:
         self.host_len = [int(x) for x in length[: self.classes]]
         self.host_ptr = [int(x) for x in ptr[: self.classes]]
         self._queue_ptrlis = queue_ptrlis
-        self._pending = None            # (event, pinned plan bytes) of the last step
+        self._pending = collections.deque()   # (event, pinned plan bytes, step id) of steps not yet mirrored
+        self._pinned_pool = []
         self.last_plan: Optional[_cabi.Plan] = None
         self.keys_by_step = {}          # step -> new_keys of that step (short history for LazyKeys)
         self.step = 0
@@ -124,35 +126,39 @@ class DeviceMemoryBank:
     # ------------------------------------------------------------------ host mirror
     def post_step(self, plan_bytes_dev: torch.Tensor, stream: torch.cuda.Stream) -> None:
         """Queue an async device->pinned copy of the step's ``arco_plan``; no host sync."""
-        pinned = torch.empty(plan_bytes_dev.numel(), dtype=torch.uint8, pin_memory=True)
+        n = plan_bytes_dev.numel()
+        pinned = self._pinned_pool.pop() if self._pinned_pool else torch.empty(n, dtype=torch.uint8, pin_memory=True)
         pinned.copy_(plan_bytes_dev, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(stream)
-        self._pending = (ev, pinned)
         self.step += 1
+        self._pending.append((ev, pinned, self.step))
+
+    def poll(self, block: bool = False) -> Optional[_cabi.Plan]:
+        """Mirror every finished step's summary on the host (bank lengths, the caller's ``queue_prtlis``,
+        ``new_keys``).  Non-blocking by default: the training loop never waits for the device here."""
+        while self._pending and (block or self._pending[0][0].query()):
+            ev, pinned, step = self._pending.popleft()
+            ev.synchronize()
+            plan = _cabi.Plan.from_buffer_copy(pinned.numpy().tobytes()[: C.sizeof(_cabi.Plan)])
+            self._pinned_pool.append(pinned)
+            self.last_plan = plan
+            self.keys_by_step[step] = [int(plan.n_key[c]) for c in range(self.classes)]
+            for old in [k for k in self.keys_by_step if k < step - 64]:
+                del self.keys_by_step[old]
+            for c in range(self.classes):
+                self.host_len[c] = int(plan.bank_len[c])
+                self.host_ptr[c] = int(plan.queue_ptr[c])
+                self._queue_ptrlis[c][0] = self.host_ptr[c]
+            if plan.status & _cabi.ST_MULTI_HOT:
+                raise ValueError("label_l/label_u are not one-hot: some pixel has more than one non-zero class entry")
+            if plan.status & _cabi.ST_LABEL_RANGE:
+                raise ValueError("integer label map contains a class id >= num_classes")
+        return self.last_plan
 
     def settle(self) -> Optional[_cabi.Plan]:
-        """Wait for the last step's summary (normally long finished) and refresh the host mirrors,
-        including the caller's ``queue_prtlis``.  Raises if the device flagged invalid labels."""
-        if self._pending is None:
-            return self.last_plan
-        ev, pinned = self._pending
-        ev.synchronize()
-        self._pending = None
-        plan = _cabi.Plan.from_buffer_copy(pinned.numpy().tobytes()[: C.sizeof(_cabi.Plan)])
-        self.last_plan = plan
-        self.keys_by_step[self.step] = [int(plan.n_key[c]) for c in range(self.classes)]
-        for old in [k for k in self.keys_by_step if k < self.step - 16]:
-            del self.keys_by_step[old]
-        for c in range(self.classes):
-            self.host_len[c] = int(plan.bank_len[c])
-            self.host_ptr[c] = int(plan.queue_ptr[c])
-            self._queue_ptrlis[c][0] = self.host_ptr[c]
-        if plan.status & _cabi.ST_MULTI_HOT:
-            raise ValueError("label_l/label_u are not one-hot: some pixel has more than one non-zero class entry")
-        if plan.status & _cabi.ST_LABEL_RANGE:
-            raise ValueError("integer label map contains a class id >= num_classes")
-        return plan
+        """Blocking :meth:`poll`: wait for every queued step (host sync) -- used by inspection only."""
+        return self.poll(block=True)
 
     def length(self, cls: int) -> int:
         self.settle()

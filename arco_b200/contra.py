@@ -28,6 +28,7 @@ DELTA_P = 0.3                  # current_class_threshold, loss_helper_3d.py:316
 LOW_RANK, HIGH_RANK = 3, 20    # loss_helper_3d.py:318
 
 _FUNC = {"smc": _cabi.FUNC_SMC, "asmc": _cabi.FUNC_ASMC}
+_GEOMETRY = {}                 # problem shape -> (arco_dims, workspace layout)
 
 
 class LazyKeys(list):
@@ -46,7 +47,7 @@ class LazyKeys(list):
             if self._ticket not in self._bank.keys_by_step:
                 self._bank.settle()
             if self._ticket not in self._bank.keys_by_step:
-                raise RuntimeError("new_keys of a step more than 16 steps old is no longer available")
+                raise RuntimeError("new_keys of a step more than 64 steps old is no longer available")
             super().extend(self._bank.keys_by_step[self._ticket])
             self._done = True
 
@@ -252,10 +253,14 @@ def compute_contra_memobank_loss(
 
     with torch.cuda.device(dev):
         bank = DeviceMemoryBank.adopt(memobank, queue_prtlis, queue_size, D, dev)
-        bank.settle()                       # last step's summary (long finished): refresh queue_prtlis, surface label errors
-        dims = _cabi.Dims(n_lab, n_unlab, Cn, D, S, int(num_queries), int(num_negatives),
-                          _cabi.BF16 if rep.dtype == torch.bfloat16 else _cabi.F32, label_kind)
-        layout = _cabi.workspace_layout(dims)
+        bank.poll()                         # mirror finished steps (non-blocking): queue_prtlis, label errors
+        key = (n_lab, n_unlab, Cn, D, S, int(num_queries), int(num_negatives), rep.dtype, label_kind, dev.index)
+        cached = _GEOMETRY.get(key)
+        if cached is None:
+            dims = _cabi.Dims(n_lab, n_unlab, Cn, D, S, int(num_queries), int(num_negatives),
+                              _cabi.BF16 if rep.dtype == torch.bfloat16 else _cabi.F32, label_kind)
+            cached = _GEOMETRY[key] = (dims, _cabi.workspace_layout(dims))
+        dims, layout = cached
         lead = 2 if label_kind == _cabi.LABEL_ONEHOT_I64 else 1
         rep_data = rep.detach().contiguous()
         state = dict(

@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads, exports every symbol include/arco_b200.h declares, and the ctypes mirrors of
+the header's structs have the C compiler's sizes.  No compute call is made (no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "arco_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"ARCO_API\s+(?:const\s+char\*|int)\s+(arco_\w+)\s*\(", src)))
+
+
+def test_header_declares_the_path():
+    names = _declared()
+    for must in ("arco_classify_count", "arco_scan_plan", "arco_proto_enqueue", "arco_sample", "arco_infonce",
+                 "arco_grad_scatter", "arco_workspace_layout", "arco_last_error_string", "arco_label_onehot"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from arco_b200 import _cabi
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} is declared in include/arco_b200.h but not exported"
+    assert set(_declared()) == set(_cabi.EXPORTS), "ctypes prototypes and header disagree"
+    lib.arco_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.arco_version()
+
+
+def test_struct_sizes_match_the_c_compiler(tmp_path):
+    from arco_b200 import _cabi
+    prog = tmp_path / "sizes.c"
+    prog.write_text('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu %%zu\\n", sizeof(arco_dims), '
+                    'sizeof(arco_ws_layout), sizeof(arco_plan), sizeof(arco_bank));return 0;}\n' % HEADER)
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", str(prog), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [ctypes.sizeof(_cabi.Dims), ctypes.sizeof(_cabi.WsLayout), ctypes.sizeof(_cabi.Plan),
+                     ctypes.sizeof(_cabi.Bank)]
+
+
+def test_layout_and_argument_errors_without_a_gpu():
+    from arco_b200 import _cabi
+    d = _cabi.Dims(4, 4, 4, 64, 65536, 256, 512, _cabi.F32, _cabi.LABEL_ONEHOT_I64)
+    L = _cabi.workspace_layout(d)
+    assert L.n_tiles == 8 * 64 and L.tiles_per_image == 64
+    assert L.total_bytes > 8 * 65536 and L.codes % 256 == 0 and L.plan == 0
+    bad = _cabi.Dims(4, 4, 40, 64, 65536, 256, 512, 0, 0)          # 40 classes > 32
+    with pytest.raises(_cabi.ArcoError, match="classes"):
+        _cabi.workspace_layout(bad)
+    bad = _cabi.Dims(4, 4, 4, 30, 65536, 256, 512, 0, 0)           # D not a multiple of 4
+    with pytest.raises(_cabi.ArcoError, match="multiple of 4"):
+        _cabi.workspace_layout(bad)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "arco_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"

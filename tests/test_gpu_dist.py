@@ -1,0 +1,82 @@
+"""GPU, needs >= 2 devices (skipped otherwise): the batch-sharded CUDA op over NCCL against the oracle's
+multi-GPU restatement (global prototypes / valid classes, rank-local anchors, negatives and banks)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import arco_b200
+    import oracle
+    from arco_b200.sharded import shard_batch
+    from arco_b200.synth import CaseSpec, exact_case, make_bank
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        spec = CaseSpec("dist", 2, 2, 4, (32, 32), 16, queries=32, negatives=8, bank_init="fill:60",
+                        caps=[80, 70, 70, 70], label_mode="absent:3", seed=31)
+        x = exact_case(spec, 0)
+        mine = shard_batch(x, spec.n_lab, rank, world)
+        bank_g, ptr_g, caps = make_bank(spec)
+        bank_c, ptr_c, _ = make_bank(spec)
+        g = {k: v.to(dev) for k, v in mine.items()}
+        rep_g = g["rep"].clone().requires_grad_(True)
+        dbg = {}
+        nk, loss = arco_b200.compute_contra_memobank_loss(
+            rep_g, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"], g["low_mask"], g["high_mask"],
+            bank_g, ptr_g, caps, g["rep_teacher"], delta_n=0.97, func="smc", num_queries=spec.queries,
+            num_negatives=spec.negatives, process_group=dist.group.WORLD, seed=5, _debug=dbg)
+        loss.backward()
+        torch.cuda.synchronize()
+        arco_b200.synchronize_bank(bank_g)
+        plan = bank_g[0].bank.last_plan
+        active = [j for j in range(spec.classes) if plan.slot_active[j]]
+        replay = []
+        for j in active:
+            replay += [dbg["idx_anchor"][j].long().cpu(), dbg["idx_neg"][j, : spec.queries * spec.negatives].long().cpu()]
+        it = iter(replay)
+        glob = dbg["proto_sums"].cpu()                        # all-reduced on the device
+
+        rep_c = mine["rep"].clone().requires_grad_(True)
+        res = oracle.contra_memobank_loss(
+            rep_c, mine["label_l"], mine["label_u"], mine["prob_l"], mine["prob_u"], mine["low_mask"], mine["high_mask"],
+            bank_c, ptr_c, caps, mine["rep_teacher"], delta_n=0.97, sampler=lambda h, s: next(it),
+            num_queries=spec.queries, num_negatives=spec.negatives, proto_sum_hook=lambda local: glob.clone())
+        res.loss.backward()
+        nv = int(plan.n_valid)
+        ok = (
+            [int(plan.valid_class[i]) for i in range(nv)] == res.valid_classes
+            and list(nk) == res.new_keys
+            and abs(float(loss) - float(res.loss)) <= 1e-5 * max(1.0, abs(float(res.loss)))
+            and float((rep_g.grad.cpu() - rep_c.grad).norm() / rep_c.grad.norm()) <= 1e-5
+        )
+        out[rank] = dict(ok=bool(ok), loss=float(loss), oracle=float(res.loss), valid=res.valid_classes)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_loss_matches_oracle():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    assert all(res[r]["ok"] for r in range(world)), res
+    assert res[0]["valid"] == res[1]["valid"]
