@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Turn gpurun_out/ artefacts (bench JSON lines, .ncu-rep captures) into the tracked summaries under profiles/.
+
+    python profiles/summarize.py r01 gpurun_out/prof_trainstep_v3.ncu-rep [more.ncu-rep ...]
+"""
+import csv
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "lts__t_sector_hit_rate.pct",
+]
+
+
+def ncu_rows(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for r in rows[2:]:
+        d = {"kernel": r[hdr.index("Kernel Name")]}
+        for m in METRICS:
+            if m in hdr:
+                d[m] = r[hdr.index(m)] + " " + units[hdr.index(m)]
+        res.append(d)
+    return res
+
+
+def main():
+    tag = sys.argv[1]
+    lines = [f"# {tag}: ncu `--set full --clock-control none` summaries (per launch, cold-ish caches, serialised)\n"]
+    traffic = {}
+    for rep in sys.argv[2:]:
+        lines.append(f"\n## {os.path.basename(rep)}\n")
+        seen = set()
+        for d in ncu_rows(rep):
+            if d["kernel"] in seen:
+                continue
+            seen.add(d["kernel"])
+            lines.append(f"\n### `{d['kernel'][:100]}`\n")
+            lines.append("| metric | value |\n|---|---|")
+            for m in METRICS:
+                if m in d:
+                    lines.append(f"| {m} | {d[m]} |")
+    with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    # bench lines
+    out = [f"# {tag}: bench.py lines brought back from the B200 box\n"]
+    for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "bench_*.json"))):
+        try:
+            j = json.load(open(path))
+        except Exception:
+            continue
+        out.append(f"\n## {os.path.basename(path)}: {j['config']['workload']} x{j['n_gpus']} -> {j['value']:.1f} {j['unit']}, "
+                   f"{j['ms_per_step']:.3f} ms/step\n")
+        out.append("| stage | ms | algorithmic MB | GB/s | frac of measured HBM peak |\n|---|---|---|---|---|")
+        for k, v in j.get("stages", {}).items():
+            if k.startswith("_"):
+                continue
+            out.append(f"| {k} | {v['ms']:.4f} | {v['alg_bytes']/1e6:.1f} | {v['gbs']:.0f} | {v['frac_hbm']:.3f} |")
+        out.append(f"\nmeasured counts: {j.get('stages', {}).get('_measured')}\n")
+        out.append("```json\n" + json.dumps({k: j[k] for k in j if k != "stages"}) + "\n```")
+    with open(os.path.join(ROOT, "profiles", f"{tag}_bench_lines.md"), "w") as f:
+        f.write("\n".join(out) + "\n")
+
+
+if __name__ == "__main__":
+    main()
