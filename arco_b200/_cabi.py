@@ -17,7 +17,7 @@ FUNC_UNIFORM, FUNC_SMC, FUNC_ASMC = 0, 1, 2
 ST_MULTI_HOT, ST_LABEL_RANGE = 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libarco_b200.so")
+LIB_PATH = os.environ.get("ARCO_B200_LIB") or os.path.join(_HERE, "lib", "libarco_b200.so")   # override: A/B builds
 
 
 class ArcoError(RuntimeError):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libarco_b200.so")
-SOURCES = ["cabi.cu", "classify.cu", "scan_plan.cu", "proto_enqueue.cu", "sampler.cu", "infonce.cu", "grad.cu"]
+SOURCES = ["cabi.cu", "classify.cu", "scan_plan.cu", "proto_enqueue.cu", "proto_tc.cu", "sampler.cu", "infonce.cu", "grad.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -35,16 +35,19 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra=None, out: str = LIB) -> str:
+    """``extra``: additional nvcc flags (e.g. ``-DARCO_TC_SUB=1``) for A/B builds written to ``out``."""
     os.makedirs(LIBDIR, exist_ok=True)
+    extra = list(extra or [])
+    tag = "" if out == LIB else "." + os.path.basename(out).replace(".so", "")
     headers = [os.path.join(CSRC, "arco_common.cuh"), os.path.join(HERE, "..", "include", "arco_b200.h")]
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        o = os.path.join(LIBDIR, src.replace(".cu", tag + ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -58,13 +61,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
                 if r.returncode != 0:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
-    if jobs or force or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    if jobs or force or _stale(out, objs):
+        cmd = [_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -71,6 +71,16 @@ class LazyKeys(list):
         return super().__repr__()
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    st = _SIDE_STREAMS.get(dev.index)
+    if st is None:
+        st = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def _flat(t: torch.Tensor, lead: int) -> torch.Tensor:
     """Contiguous view with the trailing spatial axes flattened (``lead`` leading axes kept)."""
     t = t.contiguous()
@@ -101,19 +111,26 @@ class _ContraLoss(torch.autograd.Function):
             DELTA_P, float(st["delta_n"]), LOW_RANK, HIGH_RANK, wsp, sp), "arco_classify_count")
         _cabi.check(lib.arco_scan_plan(d, b, wsp, sp), "arco_scan_plan")
         proto_sums = torch.empty((Cn, D + 1), dtype=torch.float64, device=dev)
+        idx_a = torch.empty((Cn, Q), dtype=torch.int32, device=dev)
+        idx_n = torch.empty((Cn, Q * max(N, 1)), dtype=torch.int32, device=dev)
+        plan_view = ws[layout.plan: layout.plan + C.sizeof(_cabi.Plan)]
+        group, inject = st["group"], st["inject"]
+        side = None
+        if inject is None and group is None:
+            # the sampler only needs the plan: run it on a side stream underneath the prototype pass
+            side = _side_stream(dev)
+            side.wait_stream(stream)
+            _cabi.check(lib.arco_sample(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(), idx_n.data_ptr(),
+                                        wsp, side.cuda_stream), "arco_sample")
         _cabi.check(lib.arco_proto_enqueue(d, st["rep_teacher"].data_ptr(), b, proto_sums.data_ptr(), wsp, sp),
                     "arco_proto_enqueue")
-        group = st["group"]
         if group is not None:
             # the one exchange step of the path: C*(D+1) fp64 sums + counts
             torch.distributed.all_reduce(proto_sums, group=group)
             _cabi.check(lib.arco_replan_global(d, proto_sums.data_ptr(), wsp, sp), "arco_replan_global")
-
-        idx_a = torch.empty((Cn, Q), dtype=torch.int32, device=dev)
-        idx_n = torch.empty((Cn, Q * max(N, 1)), dtype=torch.int32, device=dev)
-        plan_view = ws[layout.plan: layout.plan + C.sizeof(_cabi.Plan)]
-        inject = st["inject"]
-        if inject is None:
+        if side is not None:
+            stream.wait_stream(side)
+        elif inject is None:
             _cabi.check(lib.arco_sample(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(), idx_n.data_ptr(),
                                         wsp, sp), "arco_sample")
         else:

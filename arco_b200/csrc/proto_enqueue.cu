@@ -15,6 +15,8 @@
 //   * persistent CTAs keep one 64-dim (or 32-dim) chunk of D for their whole life, so the per-class
 //     accumulators are flushed once, to a [rows][C][D] partial buffer that a tiny fp64 kernel folds
 //     into proto_sums[C][D+1] (the buffer a multi-GPU caller all-reduces).
+#include <stdlib.h>
+
 #include "arco_common.cuh"
 
 namespace arco {
@@ -644,8 +646,13 @@ __global__ void __launch_bounds__(128) proto_finalize_kernel(const float* __rest
 
 // Kernel variant for a problem: the 8-dims-per-lane kernel needs 16-byte vector loads and its 8 KB * C
 // stream accumulators to fit beside the tile; otherwise the 4-dims-per-lane kernel (4 KB * C) runs.
+bool proto_tc_supported(const arco_dims& d);
+int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank* bank, const arco_ws_layout& L, char* ws,
+                    int rows, cudaStream_t st);
+
 struct ProtoCfg {
-    int kind;         // 0 scalar fallback (proto_enqueue_kernel), 1 pipelined (proto_pipe_kernel), 2 small (proto_small_kernel)
+    int kind;         // 0 scalar fallback (proto_enqueue_kernel), 1 pipelined (proto_pipe_kernel), 2 small (proto_small_kernel),
+                      // 3 tensor cores (proto_tc_kernel, bf16)
     int nch;          // lanes per stream
     int epl;          // feature dims per lane
     int dchunk;       // feature dims per CTA
@@ -660,6 +667,8 @@ static bool proto_vec_ok(const arco_dims& d) {
 static ProtoCfg proto_cfg(const arco_dims& d) {
     ProtoCfg c;
     const bool vec = proto_vec_ok(d);
+    const char* tc_env = getenv("ARCO_PROTO_TC");
+    if (proto_tc_supported(d) && !(tc_env && tc_env[0] == '0')) { c.kind = 3; c.nch = 0; c.epl = 0; c.dchunk = d.feat; c.smem = 0; return c; }
     if (vec && d.classes <= 3 && (d.feat == 16 || d.feat == 32)) { c.kind = 2; c.nch = 0; c.epl = 0; c.dchunk = d.feat; c.smem = 0; return c; }
     if (vec) {
         c.kind = 1;
@@ -702,6 +711,7 @@ static int proto_occ(const ProtoCfg& c) {
 static void proto_grid(const arco_dims& d, int* ndc, int* groups) {
     const ProtoCfg c = proto_cfg(d);
     if (c.kind == 2) { *ndc = 1; *groups = sm_count() * 4; return; }
+    if (c.kind == 3) { *ndc = 1; *groups = sm_count(); return; }
     *ndc = (d.feat + c.dchunk - 1) / c.dchunk;
     int occ = d.rep_dtype == ARCO_BF16 ? proto_occ<__nv_bfloat16>(c) : proto_occ<float>(c);
     // without a device (CPU-only build box) assume the shared-memory bound
@@ -771,8 +781,10 @@ extern "C" int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher
     p.NDC = ndc;
     ARCO_REQUIRE(((uintptr_t)rep_teacher & 15) == 0, "rep_teacher must be 16-byte aligned");
     p.vec_ok = arco::proto_vec_ok(d);
-    int rc = d.rep_dtype == ARCO_BF16 ? arco::launch_proto<__nv_bfloat16>(d, p, groups, st)
-                                      : arco::launch_proto<float>(d, p, groups, st);
+    int rc;
+    if (arco::proto_cfg(d).kind == 3) rc = arco::launch_proto_tc(d, rep_teacher, bank, L, ws, groups, st);
+    else rc = d.rep_dtype == ARCO_BF16 ? arco::launch_proto<__nv_bfloat16>(d, p, groups, st)
+                                       : arco::launch_proto<float>(d, p, groups, st);
     if (rc != ARCO_OK) return rc;
     const int n = d.classes * (d.feat + 1);
     arco::proto_finalize_kernel<<<(n + 3) / 4, 128, 0, st>>>(p.partials, groups, d.classes, d.feat, p.plan, proto_sums);

@@ -1,0 +1,345 @@
+// Sub-systems 2 + 3a for bf16 representations on the 5th-generation tensor cores.
+//
+//   proto_sum[c][d] = sum_px onehot[c][px] * X[d][px]          (reference: torch.mean(rep_teacher[low_valid_c]),
+//                                                                loss_helper_3d.py:380-384)
+// is a GEMM with M = feature dims, N = classes, K = pixels, and X [B, D, S] is already K-major (pixels are
+// contiguous).  So:  TMA (cp.async.bulk.tensor, SWIZZLE_128B) streams 128-row x 64-pixel bf16 boxes of X
+// straight into shared memory, a 16-class x 64-pixel one-hot tile is built from the code bytes, and one thread
+// issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) into TMEM accumulators that live for the CTA's whole
+// life.  No CUDA-core instruction touches a feature element; products are exact (one-hot x bf16) and the
+// accumulation is fp32, so results agree with the CUDA-core path to fp32 rounding.  Negative keys
+// (loss_helper_3d.py:403-411) are copied out of the same shared boxes before the stage is released.
+//
+// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 one-hot builder +
+// key enqueue; warps 0-3 run the TMEM -> partial-row epilogue.  3-stage mbarrier ring, 192 KB of loads in flight per SM.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "arco_common.cuh"
+
+namespace arco {
+
+constexpr int TC_KPX = 64;            // pixels per stage (one 128-byte swizzle row of bf16)
+constexpr int TC_ROWS = 128;          // feature rows per TMA box / per MMA (M)
+constexpr int TC_NCLS = 16;           // N of the MMA (classes, padded)
+constexpr int TC_BOX_BYTES = TC_ROWS * TC_KPX * 2;      // 16 KB
+constexpr int TC_B_BYTES = TC_NCLS * TC_KPX * 2;        // 2 KB one-hot tile
+constexpr int TC_MAX_DB = 4;                            // D <= 512
+
+struct ProtoTcParams {
+    const uint8_t* codes;
+    const uint32_t* tile_flagged;
+    const uint32_t* off_key;
+    const arco_plan* plan;
+    float* bank_rows;
+    float* partials;
+    int64_t row_off[ARCO_MAX_CLASSES];
+    int32_t cap[ARCO_MAX_CLASSES];
+    int64_t S;
+    int32_t B, C, D, tpi, NT, NDB;
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* b, uint32_t n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n));
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(s32(b)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(s32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(s32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+
+// instruction descriptor: D fp32, A/B bf16, both K-major, N = 16, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_NCLS >> 3) << 17) | ((TC_ROWS >> 4) << 24);
+
+// byte offset of (feature row r, pixel kp) inside a SWIZZLE_128B box of 128 rows x 64 bf16
+__device__ __forceinline__ uint32_t box_off(uint32_t r, uint32_t kp) {
+    return (r >> 3) * 1024 + (r & 7) * 128 + (((kp >> 3) ^ (r & 7)) << 4) + ((kp & 7) << 1);
+}
+
+// A pipeline stage is one 64-pixel step with ALL feature blocks (NDB boxes of 128 rows x 128 B) plus its own one-hot
+// tile; the 128 aux threads build the tile and copy the keys of the step.  (Measured on B200: staging 128 rows x 256
+// pixels per stage instead -- longer runs per row, fewer rows -- is 17 % slower, 0.434 vs 0.371 ms on the bf16
+// D=496 shape; spreading every stage over all D rows keeps all HBM channels busy.)
+__global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant__ CUtensorMap tmap, ProtoTcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int NDB = p.NDB;
+    const int stage_bytes = NDB * TC_BOX_BYTES + TC_B_BYTES;          // A boxes then the one-hot tile, 1024-aligned
+    constexpr int NST = 3;
+    __shared__ __align__(8) uint64_t full_bar[NST], bfull_bar[NST], empty_bar[NST], done_bar;
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_run[ARCO_MAX_CLASSES];
+    __shared__ uint32_t s_keys[TC_KPX];
+    __shared__ uint32_t s_nkeys;
+    __shared__ int32_t s_skip[ARCO_MAX_CLASSES], s_base[ARCO_MAX_CLASSES];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ngrid = gridDim.x;
+    const int64_t S = p.S;
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { bar_init(&full_bar[s], 1); bar_init(&bfull_bar[s], 1); bar_init(&empty_bar[s], 2); }
+        bar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < ARCO_MAX_CLASSES) { s_skip[tid] = p.plan->bank_skip[tid]; s_base[tid] = p.plan->bank_write_base[tid]; }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s_tmem)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    auto next_tile = [&](int t) {
+        while (t < p.NT && p.tile_flagged[t] == 0) t += ngrid;
+        return t;
+    };
+    auto steps_in_tile = [&](int t) {
+        const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
+        const int64_t left = S - s_tile;
+        return (int)min((int64_t)(ARCO_TILE / TC_KPX), (left + TC_KPX - 1) / TC_KPX);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
+                const int b = t / p.tpi;
+                const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
+                const int ns = steps_in_tile(t);
+                for (int st = 0; st < ns; ++st, ++it) {
+                    const int s = it % NST;
+                    bar_wait(&empty_bar[s], ((it / NST) & 1) ^ 1);
+                    bar_expect_tx(&full_bar[s], (uint32_t)NDB * TC_BOX_BYTES);
+                    unsigned char* dst = base + (size_t)s * stage_bytes;
+                    for (int db = 0; db < NDB; ++db)
+                        tma_load_3d(dst + db * TC_BOX_BYTES, &tmap, &full_bar[s], (int)(s_tile + st * TC_KPX), db * TC_ROWS, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
+                const int ns = steps_in_tile(t);
+                for (int st = 0; st < ns; ++st, ++it) {
+                    const int s = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
+                    bar_wait(&full_bar[s], ph);
+                    bar_wait(&bfull_bar[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = s32(base + (size_t)s * stage_bytes);
+                    const uint32_t b0 = a0 + NDB * TC_BOX_BYTES;
+                    for (int db = 0; db < NDB; ++db) {
+#pragma unroll
+                        for (int kk = 0; kk < TC_KPX / 16; ++kk)
+                            umma_bf16(tmem + db * TC_NCLS, umma_desc(a0 + db * TC_BOX_BYTES + kk * 32), umma_desc(b0 + kk * 32),
+                                      kIdesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+            }
+            umma_commit(&done_bar);
+        }
+    } else if (warp >= 4) {
+        const int at = tid - 128;
+        uint32_t it = 0;
+        for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
+            const int b = t / p.tpi;
+            const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
+            const int ns = steps_in_tile(t);
+            if (at < p.C) s_run[at] = p.off_key[(int64_t)at * (p.NT + 1) + t];
+            for (int st = 0; st < ns; ++st, ++it) {
+                const int s = it % NST;
+                const uint32_t ph = (it / NST) & 1;
+                unsigned char* stage = base + (size_t)s * stage_bytes;
+                unsigned char* btile = stage + NDB * TC_BOX_BYTES;
+                uint32_t code = 0;
+                const int64_t px = s_tile + (int64_t)st * TC_KPX + at;
+                if (at < TC_KPX && px < S) code = p.codes[(int64_t)b * S + px];
+                bar_wait(&empty_bar[s], ph ^ 1);                 // previous MMAs on this stage are done (also paces this role)
+                reinterpret_cast<uint4*>(btile)[at] = make_uint4(0u, 0u, 0u, 0u);
+                if (at == 0) s_nkeys = 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (code & CODE_LV) {
+                    const uint32_t n = code & CODE_CLS_MASK;
+                    *reinterpret_cast<unsigned short*>(btile + box_off(n, (uint32_t)at)) = 0x3F80;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (at == 0) bar_arrive(&bfull_bar[s]);
+                const bool is_key = code & CODE_KEY;
+                const uint32_t kcls = code & CODE_CLS_MASK;
+                uint32_t ord = 0;
+                if (warp == 4 || warp == 5) {
+                    const uint32_t peers = __match_any_sync(0xffffffffu, is_key ? kcls : 0xffffu);
+                    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                    if (warp == 4) {
+                        if (is_key) ord = s_run[kcls] + rank;
+                        __syncwarp();
+                        if (is_key && rank == 0) s_run[kcls] += __popc(peers);
+                    }
+                    asm volatile("bar.sync 2, 64;" ::: "memory");
+                    if (warp == 5) {
+                        if (is_key) ord = s_run[kcls] + rank;
+                        __syncwarp();
+                        if (is_key && rank == 0) s_run[kcls] += __popc(peers);
+                    }
+                }
+                if (is_key && ord >= (uint32_t)s_skip[kcls]) {
+                    const uint32_t slot = atomicAdd(&s_nkeys, 1u);
+                    s_keys[slot] = (ord << 11) | (kcls << 6) | (uint32_t)at;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const uint32_t nkeys = s_nkeys;
+                if (nkeys) {
+                    bar_wait(&full_bar[s], ph);
+                    for (uint32_t k = 0; k < nkeys; ++k) {
+                        const uint32_t e = s_keys[k];
+                        const uint32_t kp = e & 63u, kc = (e >> 6) & 31u, ko = e >> 11;
+                        const uint32_t cap = (uint32_t)p.cap[kc];
+                        const uint32_t pos = ((uint32_t)s_base[kc] + ko % cap) % cap;
+                        float* dst = p.bank_rows + (p.row_off[kc] + pos) * p.D;
+                        for (int d = at; d < p.D; d += 128)
+                            dst[d] = bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(
+                                stage + (d >> 7) * TC_BOX_BYTES + box_off((uint32_t)(d & 127), kp)));
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (at == 0) bar_arrive(&empty_bar[s]);
+            }
+        }
+    }
+
+    __syncwarp();
+    if (warp < 4) {
+        uint32_t n_it = 0;
+        for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) n_it += steps_in_tile(t);
+        if (n_it > 0) {
+            bar_wait(&done_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int db = 0; db < NDB; ++db) {
+            uint32_t v[TC_NCLS];
+#pragma unroll
+            for (int c = 0; c < TC_NCLS; ++c) v[c] = 0u;
+            if (n_it > 0) {
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + db * TC_NCLS;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            const int d = db * TC_ROWS + warp * 32 + lane;
+            if (d < p.D) {
+#pragma unroll
+                for (int c = 0; c < TC_NCLS; ++c)
+                    if (c < p.C) p.partials[((int64_t)blockIdx.x * p.C + c) * p.D + d] = __uint_as_float(v[c]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+}
+
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+bool proto_tc_supported(const arco_dims& d) {
+    return d.rep_dtype == ARCO_BF16 && d.classes <= TC_NCLS && d.feat <= TC_MAX_DB * TC_ROWS && d.space % 8 == 0 &&
+           d.feat >= 64;
+}
+
+size_t proto_tc_smem(const arco_dims& d) {
+    const int ndb = (d.feat + TC_ROWS - 1) / TC_ROWS;
+    return (size_t)3 * (ndb * TC_BOX_BYTES + TC_B_BYTES) + 1024;
+}
+
+int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank* bank, const arco_ws_layout& L, char* ws,
+                    int rows, cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    ARCO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {(cuuint64_t)d.space, (cuuint64_t)d.feat, (cuuint64_t)(d.n_lab + d.n_unlab)};
+    const cuuint64_t gstr[2] = {(cuuint64_t)d.space * 2, (cuuint64_t)d.space * d.feat * 2};
+    const cuuint32_t box[3] = {TC_KPX, TC_ROWS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(rep_teacher), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return ARCO_ERR_CUDA;
+    }
+    ProtoTcParams p;
+    p.codes = (const uint8_t*)(ws + L.codes);
+    p.tile_flagged = (const uint32_t*)(ws + L.tile_flagged);
+    p.off_key = (const uint32_t*)(ws + L.off_key);
+    p.plan = (const arco_plan*)(ws + L.plan);
+    p.bank_rows = bank->rows;
+    p.partials = (float*)(ws + L.partials);
+    for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
+    p.S = d.space; p.B = d.n_lab + d.n_unlab; p.C = d.classes; p.D = d.feat;
+    p.tpi = L.tiles_per_image; p.NT = L.n_tiles; p.NDB = (d.feat + TC_ROWS - 1) / TC_ROWS;
+    const size_t smem = proto_tc_smem(d);
+    ARCO_CUDA_CHECK(cudaFuncSetAttribute(proto_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proto_tc_kernel<<<rows, 256, smem, st>>>(map, p);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}
+
+}  // namespace arco
