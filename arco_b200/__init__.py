@@ -7,23 +7,30 @@ A trainer switches with one import line::
     from arco_b200.loss_helper_3d import *     # train_arco_2d.py:24  (4-D image tensors)
     from arco_b200.loss_helper import *        # train_arco_3d.py:22  (5-D volume tensors)
 
-Importing the package loads ``arco_b200/lib/libarco_b200.so``; there is no CPU fallback.
+The public names below are resolved on first use and load ``arco_b200/lib/libarco_b200.so`` through ctypes;
+if the library is missing or stale that raises (there is no CPU / PyTorch fallback).  Only
+``arco_b200.build`` -- the nvcc recipe that produces the library -- is importable without it.
 """
-from . import _cabi
-from ._cabi import ArcoError, version
-from .bank import BankSlot, DeviceMemoryBank, synchronize_bank
-from .contra import compute_contra_memobank_loss
-from .samplers import (
-    as_monte_carlo_sample,
-    dequeue_and_enqueue,
-    grid_as_monte_carlo_sample,
-    grid_monte_carlo_sample,
-    label_onehot,
-    monte_carlo_sample,
-)
+import importlib
 
-__all__ = [
-    "ArcoError", "BankSlot", "DeviceMemoryBank", "as_monte_carlo_sample", "compute_contra_memobank_loss",
-    "dequeue_and_enqueue", "grid_as_monte_carlo_sample", "grid_monte_carlo_sample", "label_onehot",
-    "monte_carlo_sample", "synchronize_bank", "version",
-]
+_EXPORTS = {
+    "ArcoError": "_cabi", "version": "_cabi",
+    "BankSlot": "bank", "DeviceMemoryBank": "bank", "synchronize_bank": "bank",
+    "compute_contra_memobank_loss": "contra",
+    "as_monte_carlo_sample": "samplers", "dequeue_and_enqueue": "samplers", "grid_as_monte_carlo_sample": "samplers",
+    "grid_monte_carlo_sample": "samplers", "label_onehot": "samplers", "monte_carlo_sample": "samplers",
+}
+__all__ = sorted(_EXPORTS)
+
+
+def __getattr__(name):
+    mod = _EXPORTS.get(name)
+    if mod is None:
+        raise AttributeError(f"module 'arco_b200' has no attribute {name!r}")
+    value = getattr(importlib.import_module(f"{__name__}.{mod}"), name)
+    globals()[name] = value
+    return value
+
+
+def __dir__():
+    return sorted(list(globals()) + list(_EXPORTS))

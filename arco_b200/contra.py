@@ -17,6 +17,7 @@ There is no CPU path and no PyTorch fallback: non-CUDA tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import torch
@@ -29,6 +30,7 @@ LOW_RANK, HIGH_RANK = 3, 20    # loss_helper_3d.py:318
 
 _FUNC = {"smc": _cabi.FUNC_SMC, "asmc": _cabi.FUNC_ASMC}
 _GEOMETRY = {}                 # problem shape -> (arco_dims, workspace layout)
+_PREFILL_GRAD = os.environ.get("ARCO_PREFILL_GRAD", "1") != "0"   # zero-fill grad_rep during forward (side stream)
 
 
 class LazyKeys(list):
@@ -74,10 +76,11 @@ class LazyKeys(list):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev: torch.device) -> torch.cuda.Stream:
-    st = _SIDE_STREAMS.get(dev.index)
+def _side_stream(dev: torch.device, which: int = 0) -> torch.cuda.Stream:
+    """Per-device helper streams: 0 = sampler (joins before InfoNCE), 1 = grad_rep zero fill (joins in backward)."""
+    st = _SIDE_STREAMS.get((dev.index, which))
     if st is None:
-        st = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+        st = _SIDE_STREAMS[(dev.index, which)] = torch.cuda.Stream(device=dev)
     return st
 
 
@@ -101,6 +104,15 @@ class _ContraLoss(torch.autograd.Function):
         Cn, Q, N, D = dims.classes, dims.queries, dims.negatives, dims.feat
         d = C.byref(dims)
         b = C.byref(bank.c_struct)
+        if st["prefill"]:
+            # The dense grad_rep must be zero-filled whatever the inputs are (autograd contract, P*D*e bytes of HBM
+            # writes).  Start that fill now on the side stream: it runs underneath the forward kernels, which are
+            # read-bound, and backward only has to scatter.  The buffer comes from the main stream's pool.
+            side0 = _side_stream(dev, 1)
+            buf = torch.empty(rep.shape, dtype=rep.dtype, device=dev)
+            side0.wait_stream(stream)                       # the block may still be in use by earlier main-stream work
+            _cabi.check(lib.arco_grad_zero(d, buf.data_ptr(), side0.cuda_stream), "arco_grad_zero")
+            st["grad_buf"], st["side"] = buf, side0
 
         _cabi.check(lib.arco_classify_count(
             d, st["label_l"].data_ptr() if st["label_l"] is not None else None,
@@ -163,17 +175,34 @@ class _ContraLoss(torch.autograd.Function):
         ctx.dims = dims
         ctx.rep_shape = rep.shape
         ctx.rep_dtype = rep.dtype
+        ctx.prefilled = None
+        if st["prefill"]:
+            # The dense grad_rep must be zero-filled whatever the inputs are (autograd contract, P*D*e bytes of
+            # HBM writes).  Start that fill now on the side stream: it runs underneath the forward kernels, which
+            # are not write-bound, and backward only has to scatter.
+            # join the fill here (device-side wait, no host sync): from now on the buffer is ordinary main-stream
+            # memory, so it needs no record_stream and may be dropped safely if backward never runs
+            stream.wait_stream(st["side"])
+            ctx.prefilled = [st["grad_buf"]]
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
         g_anchor, pix = ctx.saved_tensors
         dev = g_anchor.device
-        grad_rep = torch.empty(ctx.rep_shape, dtype=ctx.rep_dtype, device=dev)
         go = grad_out.detach().to(torch.float32).contiguous()
-        sp = torch.cuda.current_stream(dev).cuda_stream
-        _cabi.check(_cabi.lib.arco_grad_scatter(C.byref(ctx.dims), g_anchor.data_ptr(), pix.data_ptr(), go.data_ptr(),
-                                                grad_rep.data_ptr(), sp), "arco_grad_scatter")
+        stream = torch.cuda.current_stream(dev)
+        sp = stream.cuda_stream
+        pre = ctx.prefilled
+        if pre is not None and pre[0] is not None:
+            grad_rep = pre[0]
+            pre[0] = None                                   # a second backward (retain_graph) takes the slow path
+            _cabi.check(_cabi.lib.arco_grad_scatter_add(C.byref(ctx.dims), g_anchor.data_ptr(), pix.data_ptr(),
+                                                        go.data_ptr(), grad_rep.data_ptr(), sp), "arco_grad_scatter_add")
+        else:
+            grad_rep = torch.empty(ctx.rep_shape, dtype=ctx.rep_dtype, device=dev)
+            _cabi.check(_cabi.lib.arco_grad_scatter(C.byref(ctx.dims), g_anchor.data_ptr(), pix.data_ptr(), go.data_ptr(),
+                                                    grad_rep.data_ptr(), sp), "arco_grad_scatter")
         return grad_rep, None
 
 
@@ -289,6 +318,7 @@ def compute_contra_memobank_loss(
             delta_n=delta_n, temp=temp, func=_FUNC.get(func, _cabi.FUNC_UNIFORM),
             seed=int(seed) if seed is not None else int(torch.cuda.initial_seed()) & (2 ** 63 - 1),
             group=process_group, inject=_inject, debug=_debug,
+            prefill=bool(rep.requires_grad and torch.is_grad_enabled() and _PREFILL_GRAD),
         )
         loss = _ContraLoss.apply(rep, state)
     return LazyKeys(bank, Cn), loss

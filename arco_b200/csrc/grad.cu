@@ -42,12 +42,8 @@ __global__ void __launch_bounds__(128) grad_scatter_kernel(const float* __restri
 
 }  // namespace arco
 
-extern "C" int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
-                                 const float* grad_out, void* grad_rep, void* stream) {
-    ARCO_REQUIRE(dims && grad_anchor && anchor_pix && grad_out && grad_rep, "arco_grad_scatter: NULL argument");
-    const arco_dims& d = *dims;
+static int launch_fill(const arco_dims& d, void* grad_rep, cudaStream_t st) {
     ARCO_REQUIRE(((uintptr_t)grad_rep & 15) == 0, "grad_rep must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
     const int64_t elems = ((int64_t)d.n_lab + d.n_unlab) * d.feat * d.space;
     const int64_t bytes = elems * (d.rep_dtype == ARCO_BF16 ? 2 : 4);
     const int64_t n16 = bytes / 16;
@@ -58,6 +54,11 @@ extern "C" int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor
     if (blocks < 1) blocks = 1;
     arco::fill_zero_kernel<<<(int)blocks, 256, 0, st>>>((uint4*)grad_rep, n16, (unsigned char*)grad_rep + n16 * 16, tail);
     ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}
+
+static int launch_scatter(const arco_dims& d, const float* grad_anchor, const int32_t* anchor_pix, const float* grad_out,
+                          void* grad_rep, cudaStream_t st) {
     const int rows = d.classes * d.queries;
     if (d.rep_dtype == ARCO_BF16)
         arco::grad_scatter_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(grad_anchor, anchor_pix, grad_out,
@@ -67,4 +68,23 @@ extern "C" int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor
                                                                 d.feat, d.space);
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
+}
+
+extern "C" int arco_grad_zero(const arco_dims* dims, void* grad_rep, void* stream) {
+    ARCO_REQUIRE(dims && grad_rep, "arco_grad_zero: NULL argument");
+    return launch_fill(*dims, grad_rep, (cudaStream_t)stream);
+}
+
+extern "C" int arco_grad_scatter_add(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
+                                     const float* grad_out, void* grad_rep, void* stream) {
+    ARCO_REQUIRE(dims && grad_anchor && anchor_pix && grad_out && grad_rep, "arco_grad_scatter_add: NULL argument");
+    return launch_scatter(*dims, grad_anchor, anchor_pix, grad_out, grad_rep, (cudaStream_t)stream);
+}
+
+extern "C" int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
+                                 const float* grad_out, void* grad_rep, void* stream) {
+    ARCO_REQUIRE(dims && grad_anchor && anchor_pix && grad_out && grad_rep, "arco_grad_scatter: NULL argument");
+    int rc = launch_fill(*dims, grad_rep, (cudaStream_t)stream);
+    if (rc != ARCO_OK) return rc;
+    return launch_scatter(*dims, grad_anchor, anchor_pix, grad_out, grad_rep, (cudaStream_t)stream);
 }

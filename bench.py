@@ -377,10 +377,14 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
         except Exception:
             traffic = None
     k = "proto_enqueue"
-    roof = {"kernel": "arco::proto_enqueue_kernel (+ proto_finalize, <1% of the call)", "bound": "hbm",
+    kname = ("arco::proto_tc_kernel (tcgen05 + TMA)" if spec.dtype == "bf16" and spec.classes <= 16 and spec.feat >= 64
+             else "arco::proto_small_kernel" if spec.classes <= 3 and spec.feat in (16, 32) else "arco::proto_pipe_kernel")
+    roof = {"kernel": kname + " + proto_finalize_kernel (<2% of the call)", "bound": "hbm",
             "achieved": stages[k]["gbs"], "peak": peak, "unit": "GB/s", "frac": stages[k]["frac_hbm"],
             "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg[k], "ms_per_launch": ms[k],
-            "bytes_formula": "P_lv*D*e_t + K*D*(e_t+4) + P  (SURVEY.md section 8(d) teacher-read and key terms + 1 code byte per pixel)"}
+            "bytes_formula": "P_lv*D*e_t + K*D*(e_t+4) + P  (SURVEY.md section 8(d) teacher-read and key terms + 1 code byte per pixel)",
+            "note": "rep_teacher is channel-first, so every 32-byte sector that holds one low-valid pixel must be fetched: "
+                    "with the iid 20% masks of this workload that is ALL of P*D*e_t; 'traffic' is the ncu-measured DRAM bytes"}
     return stages, roof
 
 

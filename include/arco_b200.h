@@ -176,6 +176,12 @@ ARCO_API int arco_infonce(const arco_dims* dims, const void* rep, const arco_ban
 ARCO_API int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
                       const float* grad_out, void* grad_rep, void* stream);
 
+/* The two halves of arco_grad_scatter, so that a caller can run the (input-independent) zero fill early on
+ * a side stream, underneath the forward kernels, and only scatter in backward. */
+ARCO_API int arco_grad_zero(const arco_dims* dims, void* grad_rep, void* stream);
+ARCO_API int arco_grad_scatter_add(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
+                                   const float* grad_out, void* grad_rep, void* stream);
+
 /* Parity / inspection helpers (not on the hot path). */
 /* kind: 0 anchor candidates, 1 negative keys, 2 low-valid; writes the raster-ordered flat pixel ids of
  * class `cls` to out (capacity out_cap) and the count to *count_dev. */
