@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/arco_b200.h"
 
@@ -44,7 +45,7 @@ __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + 
 // Rows of per-class prototype partial sums: one row per proto CTA group (see proto_enqueue.cu).
 int proto_partial_rows(const arco_dims& d);
 
-inline int compute_layout(const arco_dims& d, arco_ws_layout* L) {
+inline int compute_layout_uncached(const arco_dims& d, arco_ws_layout* L) {
     const int64_t B = (int64_t)d.n_lab + d.n_unlab;
     const int64_t P = B * d.space;
     const int64_t tpi = (d.space + ARCO_TILE - 1) / ARCO_TILE;
@@ -70,6 +71,25 @@ inline int compute_layout(const arco_dims& d, arco_ws_layout* L) {
     L->tiles_per_image = (int32_t)tpi;
     L->reserved = 0;
     return 0;
+}
+
+// Every stage entry point recomputes the workspace geometry from `dims`; the prototype grid inside it asks the
+// runtime for kernel occupancy, so the result is memoised per thread (a training loop repeats one shape).
+inline int compute_layout(const arco_dims& d, arco_ws_layout* L) {
+    static thread_local arco_dims cached_dims;
+    static thread_local arco_ws_layout cached_layout;
+    static thread_local int cached_device = -1;
+    static thread_local bool valid = false;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (valid && dev == cached_device && memcmp(&d, &cached_dims, sizeof(arco_dims)) == 0) {
+        *L = cached_layout;
+        return 0;
+    }
+    memset(L, 0, sizeof(*L));
+    const int rc = compute_layout_uncached(d, L);
+    if (rc == 0) { cached_dims = d; cached_layout = *L; cached_device = dev; valid = true; }
+    return rc;
 }
 
 template <typename T>

@@ -238,8 +238,9 @@ __global__ void __launch_bounds__(256) proto_enqueue_kernel(ProtoParams p) {
                     }
                     // advance the per-warp running key ordinals by this sub-tile's keys (all warps agree)
                     __syncwarp();
-                    for (int wq = lane; wq < SP / 4; wq += 32) {
-                        const uint32_t w4 = sc_words[wq];
+                    for (int wb = 0; wb < SP / 4; wb += 32) {                // warp-uniform trip count (match.any inside)
+                        const int wq = wb + lane;
+                        const uint32_t w4 = wq < SP / 4 ? sc_words[wq] : 0u;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const uint32_t cd = (w4 >> (8 * q)) & 0xffu;
@@ -527,8 +528,9 @@ __global__ void __launch_bounds__(256, 2) proto_pipe_kernel(ProtoParams p) {
             }
             // advance the per-warp running key ordinals by this sub-tile's keys (all warps agree)
             __syncwarp();
-            for (int wq = lane; wq < SP / 4; wq += 32) {
-                const uint32_t w4 = sc_words[wq];
+            for (int wb = 0; wb < SP / 4; wb += 32) {                        // warp-uniform trip count (match.any inside)
+                const int wq = wb + lane;
+                const uint32_t w4 = wq < SP / 4 ? sc_words[wq] : 0u;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t cd = (w4 >> (8 * q)) & 0xffu;

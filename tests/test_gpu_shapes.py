@@ -1,0 +1,89 @@
+"""GPU: shape / dtype sweep of the CUDA path against the oracle's ops (run on the GPU), with the device sampler's own
+indices replayed into the oracle.  Exercises every prototype-kernel variant (tcgen05 bf16, pipelined EPL 4/8, small
+register kernel, scalar fallback), ragged tiles, empty halves of the batch and odd Q/N."""
+import pytest
+import torch
+
+import oracle
+from arco_b200.synth import CaseSpec, exact_case, make_bank
+
+pytestmark = pytest.mark.gpu
+
+SPECS = [
+    # name, n_lab, n_unlab, C, spatial, D, kwargs
+    CaseSpec("tc_bf16_ragged", 2, 2, 4, (24, 24), 496, queries=16, negatives=12, dtype="bf16", bank_init="fill:80", caps=[120] * 4),
+    CaseSpec("tc_bf16_d64_c16", 1, 2, 16, (40, 40), 64, queries=8, negatives=8, dtype="bf16", bank_init="fill:50", caps=[70] * 16),
+    CaseSpec("tc_bf16_3d", 1, 1, 5, (16, 16, 8), 128, queries=16, negatives=9, dtype="bf16", bank_init="fill:60", caps=[90] * 5, func="asmc"),
+    CaseSpec("pipe8_f32", 2, 2, 4, (48, 48), 64, queries=32, negatives=16, bank_init="fill:100", caps=[150] * 4),
+    CaseSpec("pipe8_f32_d200", 1, 1, 8, (32, 32), 200, queries=16, negatives=7, bank_init="fill:64", caps=[100] * 8),
+    CaseSpec("pipe4_f32_c19", 1, 1, 19, (32, 64), 256, queries=8, negatives=16, bank_init="fill:40", caps=[64] * 19),
+    CaseSpec("pipe4_bf16_c19", 1, 1, 19, (32, 32), 48, queries=8, negatives=5, dtype="bf16", bank_init="fill:40", caps=[64] * 19),
+    CaseSpec("small_la", 1, 1, 2, (16, 16, 12), 16, queries=16, negatives=8, bank_init="randn1", func="asmc"),
+    CaseSpec("small_c3_d32_bf16", 1, 2, 3, (32, 40), 32, queries=8, negatives=8, dtype="bf16", bank_init="fill:30", caps=[40] * 3),
+    CaseSpec("scalar_odd_s", 1, 2, 5, (9, 7, 5), 24, queries=12, negatives=3, bank_init="fill:50", caps=[64] * 5, label_mode="blocky"),
+    CaseSpec("scalar_bf16_odd_s", 1, 1, 4, (21, 13), 72, queries=12, negatives=4, dtype="bf16", bank_init="fill:50", caps=[64] * 4),
+    CaseSpec("only_unlabelled", 0, 3, 5, (32, 32), 64, queries=16, negatives=8, bank_init="fill:60", caps=[80] * 5),
+    CaseSpec("only_labelled", 3, 0, 4, (32, 32), 64, queries=16, negatives=8, bank_init="fill:60", caps=[80] * 4),
+    CaseSpec("one_negative", 2, 2, 4, (32, 32), 32, queries=7, negatives=1, bank_init="fill:60", caps=[80] * 4),
+    CaseSpec("overflow_tc", 1, 2, 5, (32, 32), 128, queries=8, negatives=8, dtype="bf16", bank_init="fill:10", caps=[16, 12, 12, 12, 12],
+             mask_frac=0.9, steps=2),
+]
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("spec", SPECS, ids=lambda s: s.name)
+@pytest.mark.parametrize("index_labels", [False, True], ids=["onehot", "indexlabels"])
+def test_shape(spec, index_labels):
+    import arco_b200
+    dev = torch.device("cuda", 0)
+    bank_g, ptr_g, caps = make_bank(spec)
+    bank_c, ptr_c, _ = make_bank(spec)
+    Q, N = spec.queries, spec.negatives
+    for step in range(spec.steps):
+        x = exact_case(spec, step)
+        g = {k: v.to(dev) for k, v in x.items()}
+        rep_g = g["rep"].clone().requires_grad_(True)
+        dbg = {}
+        ll, lu = (g["labels"][: spec.n_lab].contiguous(), g["labels"][spec.n_lab:].contiguous()) if index_labels \
+            else (g["label_l"], g["label_u"])
+        new_keys, loss = arco_b200.compute_contra_memobank_loss(
+            rep_g, ll, lu, g["prob_l"], g["prob_u"], g["low_mask"], g["high_mask"], bank_g, ptr_g, caps, g["rep_teacher"],
+            delta_n=spec.delta_n, func=spec.func, num_queries=Q, num_negatives=N, temp=spec.temp, seed=77, _debug=dbg)
+        loss.backward()
+        torch.cuda.synchronize()
+        arco_b200.synchronize_bank(bank_g)
+        plan = bank_g[0].bank.last_plan
+        active = [j for j in range(spec.classes) if plan.slot_active[j]]
+        replay = []
+        for j in active:
+            replay += [dbg["idx_anchor"][j].long().cpu(), dbg["idx_neg"][j, : Q * N].long().cpu()]
+        it = iter(replay)
+        rep_c = g["rep"].float().clone().requires_grad_(True)
+        res = oracle.contra_memobank_loss(
+            rep_c, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"], g["low_mask"], g["high_mask"], bank_c, ptr_c, caps,
+            g["rep_teacher"].float(), delta_n=spec.delta_n, sampler=lambda h, s: next(it), num_queries=Q, num_negatives=N,
+            temp=spec.temp)
+        res.loss.backward()
+        Cn = spec.classes
+        assert list(new_keys) == res.new_keys
+        assert [int(plan.lv_count[c]) for c in range(Cn)] == res.low_valid_counts
+        assert [int(plan.n_anchor[c]) for c in range(Cn)] == [len(a) for a in res.anchor_lists]
+        assert [int(plan.valid_class[i]) for i in range(int(plan.n_valid))] == res.valid_classes
+        assert [int(q) for q in ptr_g] == [int(q) for q in ptr_c]
+        for c in range(Cn):
+            assert torch.equal(bank_g[c][0].cpu(), bank_c[c][0].float()), f"bank {c} (step {step})"
+        ok = torch.tensor([n > 0 for n in res.low_valid_counts], device=dev)
+        proto_g = (dbg["proto_sums"][:, :-1] / dbg["proto_sums"][:, -1:]).float()
+        if ok.any():
+            assert _rel(proto_g[ok], res.proto[ok]) <= 2e-5
+        tol = 2e-2 if spec.dtype == "bf16" else 1e-5
+        lo = float(res.loss.detach())
+        assert abs(float(loss.detach()) - lo) <= tol * max(1.0, abs(lo))
+        if float(rep_c.grad.abs().max()) > 0:
+            assert _rel(rep_g.grad.float(), rep_c.grad) <= tol
+        else:
+            assert float(rep_g.grad.float().abs().max()) == 0.0
