@@ -31,6 +31,7 @@ LOW_RANK, HIGH_RANK = 3, 20    # loss_helper_3d.py:318
 _FUNC = {"smc": _cabi.FUNC_SMC, "asmc": _cabi.FUNC_ASMC}
 _GEOMETRY = {}                 # problem shape -> (arco_dims, workspace layout)
 _PREFILL_GRAD = os.environ.get("ARCO_PREFILL_GRAD", "1") != "0"   # zero-fill grad_rep during forward (side stream)
+_PREFILL_MIN_BYTES = 512 << 20
 
 
 class LazyKeys(list):
@@ -318,7 +319,9 @@ def compute_contra_memobank_loss(
             delta_n=delta_n, temp=temp, func=_FUNC.get(func, _cabi.FUNC_UNIFORM),
             seed=int(seed) if seed is not None else int(torch.cuda.initial_seed()) & (2 ** 63 - 1),
             group=process_group, inject=_inject, debug=_debug,
-            prefill=bool(rep.requires_grad and torch.is_grad_enabled() and _PREFILL_GRAD),
+            # only worth its three extra host calls when the step is bandwidth- rather than launch-bound
+            prefill=bool(rep.requires_grad and torch.is_grad_enabled() and _PREFILL_GRAD
+                         and rep.numel() * rep.element_size() >= _PREFILL_MIN_BYTES),
         )
         loss = _ContraLoss.apply(rep, state)
     return LazyKeys(bank, Cn), loss

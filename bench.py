@@ -59,16 +59,18 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle-reason sampler running in a thread DURING the timed region (NVML, 5 ms period;
-    falls back to one nvidia-smi query if pynvml is unavailable)."""
+    """SM clock / throttle-reason sampler: an NVML thread (1 ms period) that is started BEFORE the warm-up so that
+    it is already sampling when the timed region begins; only samples taken between mark_begin() and mark_end()
+    count.  Falls back to one nvidia-smi query if pynvml is unavailable."""
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
-        self.reasons = set()
+        self.samples = []          # (t, sm_mhz, reasons bitmask)
         self.stop_flag = False
         self.thread = None
         self.max_mhz = None
+        self.ready = False
+        self.t0 = self.t1 = None
 
     def _loop(self):
         try:
@@ -76,39 +78,48 @@ class ClockSampler:
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
             while not self.stop_flag:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.005)
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(r)))
+                self.ready = True
+                time.sleep(0.001)
         except Exception:
-            pass
+            self.ready = True
 
     def start(self):
         import threading
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
+        t = time.perf_counter()
+        while not self.ready and time.perf_counter() - t < 5.0:
+            time.sleep(0.005)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         self.stop_flag = True
         if self.thread is not None:
             self.thread.join(timeout=2)
-        if not self.samples:
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= (self.t1 or 1e30)]
+        if not inside:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
                 a, b = [float(v) for v in out.strip().split(",")[:2]]
-                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the run"}
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 0, "source": "nvidia-smi after the run (no NVML sample fell inside the timed region)"}
             except Exception:
                 return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples), "source": "NVML thread, 5 ms period, during the timed region"}
+        reasons = sorted(n for n, bit in bits.items() if any(s[2] & bit for s in inside))
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(inside), "source": "NVML thread, 1 ms period, samples inside the timed region only"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -195,6 +206,8 @@ def main_ours(args):
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
@@ -231,16 +244,16 @@ def main_ours(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    sync_all()
-
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     sync_all()
+    clocks.mark_begin()
     for i in range(args.steps):
         if flush is not None:
             flush.fill_(i & 0xff)
@@ -248,6 +261,7 @@ def main_ours(args):
         step()
         ends[i].record()
     sync_all()
+    clocks.mark_end()
     clk = clocks.stop() if rank == 0 else None
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
