@@ -82,6 +82,7 @@ def _load():
         "arco_sample": (C.c_int, [dp, i32, u64, u64, vp, vp, vp, vp]),
         "arco_sample_one": (C.c_int, [i32, i64, i64, u64, u64, vp, vp, i64, vp]),
         "arco_infonce": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
+        "arco_infonce_ema": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp]),
         "arco_grad_scatter": (C.c_int, [dp, vp, vp, vp, vp, vp]),
         "arco_grad_zero": (C.c_int, [dp, vp, vp]),
         "arco_grad_scatter_add": (C.c_int, [dp, vp, vp, vp, vp, vp]),

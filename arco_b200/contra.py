@@ -164,10 +164,24 @@ class _ContraLoss(torch.autograd.Function):
         pix = torch.empty((Cn, Q), dtype=torch.int32, device=dev)
         debug = st["debug"]
         logits = torch.zeros((Cn, Q, 1 + N), dtype=torch.float32, device=dev) if debug is not None else None
-        _cabi.check(lib.arco_infonce(
-            d, st["rep_data"].data_ptr(), b, proto_sums.data_ptr(), idx_a.data_ptr(), idx_n.data_ptr(),
-            float(st["temp"]), loss.data_ptr(), g_anchor.data_ptr(), pix.data_ptr(),
-            logits.data_ptr() if logits is not None else None, wsp, sp), "arco_infonce")
+        mom = st["momentum"]
+        if mom is None:
+            _cabi.check(lib.arco_infonce(
+                d, st["rep_data"].data_ptr(), b, proto_sums.data_ptr(), idx_a.data_ptr(), idx_n.data_ptr(),
+                float(st["temp"]), loss.data_ptr(), g_anchor.data_ptr(), pix.data_ptr(),
+                logits.data_ptr() if logits is not None else None, wsp, sp), "arco_infonce")
+        else:
+            # a11: EMA prototypes.  The "is the momentum tensor all zero" test (:489) and the <=1-valid-class early
+            # return (:421-424, which hands back the input tensor) are both resolved on the device.
+            mom_on = (mom != 0).any().to(torch.int32).reshape(1)
+            proto_out = torch.zeros_like(mom)
+            _cabi.check(lib.arco_infonce_ema(
+                d, st["rep_data"].data_ptr(), b, proto_sums.data_ptr(), idx_a.data_ptr(), idx_n.data_ptr(),
+                float(st["temp"]), loss.data_ptr(), g_anchor.data_ptr(), pix.data_ptr(),
+                logits.data_ptr() if logits is not None else None, mom.data_ptr(), mom_on.data_ptr(),
+                float(st["ema_decay"]), proto_out.data_ptr(), wsp, sp), "arco_infonce_ema")
+            n_valid = ws[layout.plan + 384: layout.plan + 388].view(torch.int32)      # arco_plan.n_valid
+            st["prototype_out"] = torch.where(n_valid <= 1, mom, proto_out)
         bank.post_step(plan_view, stream)
         if debug is not None:
             debug.update(ws=ws, layout=layout, dims=dims, proto_sums=proto_sums, logits=logits, anchor_pix=pix,
@@ -238,16 +252,14 @@ def compute_contra_memobank_loss(
     int64 one-hot maps ``[B_x, C, *S]`` the trainers pass, or -- cheaper, 8 B instead of 8*C B per pixel --
     plain integer label maps ``[B_x, *S]`` (ignore label -1 is folded into class 0 like the trainers'
     ``label_onehot``); in that case the number of classes is taken from ``prob_l``.
-    Returns ``(new_keys, loss)`` (``loss.backward()`` yields a dense ``rep.grad``).
+    Returns ``(new_keys, loss)`` (``loss.backward()`` yields a dense ``rep.grad``), or
+    ``(prototype, new_keys, loss)`` when ``momentum_prototype`` ``[C, Q, 1, D]`` is given (EMA prototypes,
+    loss_helper_3d.py:488-497,512-513; ``i_iter`` must then be >= 1 as in the reference).
 
     Keyword-only extensions: ``process_group`` (batch-sharded multi-GPU: one all-reduce of the per-class
     prototype sums), ``seed`` (Philox seed of the in-kernel sampler; defaults to torch's CUDA seed),
     ``_inject`` / ``_debug`` (parity tests).
     """
-    if momentum_prototype is not None:
-        raise NotImplementedError(
-            "momentum_prototype (EMA prototypes, loss_helper_3d.py:488-497) is not used by either ARCO trainer "
-            "and is not implemented in arco_b200")
     if not (torch.is_tensor(rep) and rep.is_cuda):
         raise RuntimeError("arco_b200.compute_contra_memobank_loss needs CUDA tensors: there is no CPU fallback")
     if rep.dim() not in (4, 5):
@@ -298,6 +310,13 @@ def compute_contra_memobank_loss(
     if len(memobank) != Cn:
         raise ValueError(f"memobank has {len(memobank)} classes, prob has {Cn}")
 
+    mom, ema_decay = None, 0.0
+    if momentum_prototype is not None:
+        if tuple(momentum_prototype.shape) != (Cn, int(num_queries), 1, D) or momentum_prototype.device != dev:
+            raise ValueError(f"momentum_prototype must be [{Cn},{int(num_queries)},1,{D}] on rep's device")
+        mom = momentum_prototype.detach().to(torch.float32).contiguous()
+        # reference: min(1 - 1/i_iter, 0.999), evaluated only when the tensor is not all zero (ZeroDivisionError at i_iter=0)
+        ema_decay = min(1.0 - 1.0 / i_iter, 0.999) if i_iter != 0 else float("nan")
     with torch.cuda.device(dev):
         bank = DeviceMemoryBank.adopt(memobank, queue_prtlis, queue_size, D, dev)
         bank.poll()                         # mirror finished steps (non-blocking): queue_prtlis, label errors
@@ -318,10 +337,12 @@ def compute_contra_memobank_loss(
             rep_teacher=rep_teacher.detach().contiguous(), rep_data=rep_data,
             delta_n=delta_n, temp=temp, func=_FUNC.get(func, _cabi.FUNC_UNIFORM),
             seed=int(seed) if seed is not None else int(torch.cuda.initial_seed()) & (2 ** 63 - 1),
-            group=process_group, inject=_inject, debug=_debug,
+            group=process_group, inject=_inject, debug=_debug, momentum=mom, ema_decay=ema_decay,
             # only worth its three extra host calls when the step is bandwidth- rather than launch-bound
             prefill=bool(rep.requires_grad and torch.is_grad_enabled() and _PREFILL_GRAD
                          and rep.numel() * rep.element_size() >= _PREFILL_MIN_BYTES),
         )
         loss = _ContraLoss.apply(rep, state)
+    if mom is not None:
+        return state["prototype_out"].to(momentum_prototype.dtype), LazyKeys(bank, Cn), loss
     return LazyKeys(bank, Cn), loss

@@ -31,6 +31,11 @@ struct InfoParams {
     int32_t* anchor_pix;
     float* logits;
     float* loss_parts;
+    // optional EMA prototypes (a11, loss_helper_3d.py:488-497)
+    const float* momentum;       // [C][Q][D] or NULL
+    const int32_t* momentum_on;  // device flag: momentum tensor has a non-zero entry (:489)
+    float* proto_out;            // [C][Q][D] positive_feat written per (bank class, query) (:497), or NULL
+    float ema_decay;
     int64_t row_off[ARCO_MAX_CLASSES];
     int32_t cap[ARCO_MAX_CLASSES];
     int64_t S;
@@ -164,7 +169,13 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
                 v = bf16_bits_to_float(reinterpret_cast<const unsigned short*>(p.rep)[((int64_t)ab * D + d) * p.S + as]);
             else
                 v = reinterpret_cast<const float*>(p.rep)[((int64_t)ab * D + d) * p.S + as];
-            const float k = (float)(p.proto_sums[(int64_t)j * (D + 1) + d] / cntj);   // class mean (:380-384)
+            float k = (float)(p.proto_sums[(int64_t)j * (D + 1) + d] / cntj);   // class mean (:380-384)
+            if (p.momentum) {
+                // positive = (1-a)*proto + a*momentum_prototype[valid_classes[i]][q]  (:490-495); prototype[...] = positive (:497)
+                const int64_t mo = ((int64_t)bank_cls * p.Q + q) * D + d;
+                if (*p.momentum_on) k = (1.f - p.ema_decay) * k + p.ema_decay * p.momentum[mo];
+                if (p.proto_out) p.proto_out[mo] = k;
+            }
             a_hat[d] = v;
             k0hat[d] = k;
             n2a += v * v;
@@ -359,9 +370,10 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
 
 }  // namespace arco
 
-extern "C" int arco_infonce(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
-                            const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
-                            float* grad_anchor, int32_t* anchor_pix, float* logits, void* workspace, void* stream) {
+static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
+                        const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
+                        float* grad_anchor, int32_t* anchor_pix, float* logits, const float* momentum,
+                        const int32_t* momentum_on, float ema_decay, float* proto_out, void* workspace, void* stream) {
     ARCO_REQUIRE(dims && rep && bank && proto_sums && idx_anchor && idx_neg && loss && grad_anchor && anchor_pix &&
                      workspace, "arco_infonce: NULL argument");
     const arco_dims& d = *dims;
@@ -378,6 +390,8 @@ extern "C" int arco_infonce(const arco_dims* dims, const void* rep, const arco_b
     p.plan = (arco_plan*)(ws + L.plan);
     p.loss = loss; p.g_anchor = grad_anchor; p.anchor_pix = anchor_pix; p.logits = logits;
     p.loss_parts = (float*)(ws + L.loss_parts);
+    p.momentum = momentum; p.momentum_on = momentum_on; p.proto_out = proto_out; p.ema_decay = ema_decay;
+    ARCO_REQUIRE(momentum == nullptr || momentum_on != nullptr, "momentum needs the device flag momentum_on");
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
     p.S = d.space; p.C = d.classes; p.D = d.feat; p.Q = d.queries; p.N = d.negatives;
     p.tpi = L.tiles_per_image; p.NT = L.n_tiles; p.rep_dtype = d.rep_dtype; p.temp = temp;
@@ -403,4 +417,21 @@ extern "C" int arco_infonce(const arco_dims* dims, const void* rep, const arco_b
     }
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
+}
+
+extern "C" int arco_infonce(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
+                            const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
+                            float* grad_anchor, int32_t* anchor_pix, float* logits, void* workspace, void* stream) {
+    return infonce_impl(dims, rep, bank, proto_sums, idx_anchor, idx_neg, temp, loss, grad_anchor, anchor_pix, logits,
+                        nullptr, nullptr, 0.f, nullptr, workspace, stream);
+}
+
+extern "C" int arco_infonce_ema(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
+                                const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
+                                float* grad_anchor, int32_t* anchor_pix, float* logits, const float* momentum,
+                                const int32_t* momentum_on, float ema_decay, float* proto_out, void* workspace,
+                                void* stream) {
+    ARCO_REQUIRE(momentum && momentum_on && proto_out, "arco_infonce_ema: NULL momentum argument");
+    return infonce_impl(dims, rep, bank, proto_sums, idx_anchor, idx_neg, temp, loss, grad_anchor, anchor_pix, logits,
+                        momentum, momentum_on, ema_decay, proto_out, workspace, stream);
 }

@@ -43,6 +43,8 @@ class CaseSpec:
     steps: int = 1
     dtype: str = "f32"                        # f32 | bf16 (representation tensors)
     seed: int = 1337
+    momentum: str = ""                        # "" (none) | "zeros" | "rand": momentum_prototype [C,Q,1,D] (a11)
+    i_iter: int = 0
 
     @property
     def batch(self) -> int:
@@ -144,6 +146,10 @@ def exact_case(spec: CaseSpec, step: int = 0) -> dict:
         low_mask=torch.from_numpy(low.astype(np.float32)).unsqueeze(1),
         high_mask=torch.from_numpy(high.astype(np.float32)).unsqueeze(1),
     )
+    if spec.momentum:
+        shape = (C, spec.queries, 1, D)
+        mom = np.zeros(shape, np.float32) if spec.momentum == "zeros" else _exact_normal_like(rs, shape)
+        out["momentum_prototype"] = torch.from_numpy(mom)
     return out
 
 

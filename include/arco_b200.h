@@ -171,6 +171,15 @@ ARCO_API int arco_infonce(const arco_dims* dims, const void* rep, const arco_ban
                  float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits,
                  void* workspace, void* stream);
 
+/* (a11) same with the optional EMA prototypes (momentum_prototype, loss_helper_3d.py:488-497): positive =
+ * (1-ema_decay)*class_mean + ema_decay*momentum[bank_class][q] when *momentum_on != 0; the positive actually used is
+ * written to proto_out[bank_class][q][:] (the reference's returned `prototype`).  momentum, proto_out: f32 [C,Q,D]. */
+ARCO_API int arco_infonce_ema(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
+                              const int32_t* idx_anchor, const int32_t* idx_neg, float temp,
+                              float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits,
+                              const float* momentum, const int32_t* momentum_on, float ema_decay, float* proto_out,
+                              void* workspace, void* stream);
+
 /* (a10) backward: grad_rep[B,D,S] = 0, then += grad_out * grad_anchor at the anchor pixels
  * (duplicates accumulate, trap 8).  grad_out: device f32 scalar. */
 ARCO_API int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,

@@ -43,6 +43,12 @@ CASES = [
     # blocky labels, unequal labelled / unlabelled split, image size not a multiple of 4
     CaseSpec("blocky_odd", 1, 3, 6, (15, 13), 20, queries=24, negatives=5, func="asmc",
              bank_init="fill:60", caps=[80] * 6, label_mode="blocky", seed=23),
+    # optional EMA prototypes (a11, loss_helper_3d.py:488-497): non-zero momentum with class 1 absent, and the all-zero
+    # momentum tensor that leaves the prototypes untouched; 3-tuple return
+    CaseSpec("momentum", 2, 2, 4, (16, 16), 8, func="smc", bank_init="fill:30", caps=[50, 30, 30, 30],
+             label_mode="absent:1", momentum="rand", i_iter=7, seed=37),
+    CaseSpec("momentum_zero", 2, 2, 4, (16, 16), 8, func="asmc", bank_init="fill:30", caps=[50, 30, 30, 30],
+             momentum="zeros", i_iter=3, seed=41),
     # bf16 representation tensors (config 2); compared at bf16 tolerance
     CaseSpec("bf16_rep", 2, 2, 4, (16, 16), 16, func="smc", bank_init="fill:25",
              caps=[40, 40, 40, 40], dtype="bf16", seed=29),

@@ -64,10 +64,12 @@ def run_case(spec):
             else:
                 mod.torch.randint = recording(originals[2])
             try:
-                new_keys, loss = mod.compute_contra_memobank_loss(
+                ret = mod.compute_contra_memobank_loss(
                     rep, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"],
-                    memobank, ptrs, caps, x["rep_teacher"], delta_n=spec.delta_n, func=spec.func,
+                    memobank, ptrs, caps, x["rep_teacher"], momentum_prototype=x.get("momentum_prototype"),
+                    i_iter=spec.i_iter, delta_n=spec.delta_n, func=spec.func,
                     num_queries=spec.queries, num_negatives=spec.negatives, temp=spec.temp)
+                new_keys, loss = ret[-2], ret[-1]
             finally:
                 mod.grid_monte_carlo_sample, mod.grid_as_monte_carlo_sample = originals[0], originals[1]
                 mod.torch.randint = originals[2]
@@ -75,6 +77,8 @@ def run_case(spec):
             p = f"s{step}_"
             out[p + "new_keys"] = np.asarray(new_keys, np.int64)
             out[p + "loss"] = loss.detach().float().numpy()
+            if len(ret) == 3:
+                out[p + "prototype"] = ret[0].detach().float().numpy()
             out[p + "grad"] = rep.grad.float().numpy()
             out[p + "ptr"] = np.asarray([int(q) for q in ptrs], np.int64)
             out[p + "bank_len"] = np.asarray([m[0].shape[0] for m in memobank], np.int64)

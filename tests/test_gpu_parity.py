@@ -55,7 +55,8 @@ def _run_case(spec, use_index_labels=False):
         replay_c = Replay(gold, step)
         ores = oracle.contra_memobank_loss(
             rep_c, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"],
-            bank_cpu, ptr_cpu, caps, x["rep_teacher"].float(), delta_n=spec.delta_n, sampler=replay_c,
+            bank_cpu, ptr_cpu, caps, x["rep_teacher"].float(), momentum_prototype=x.get("momentum_prototype"),
+            i_iter=spec.i_iter, delta_n=spec.delta_n, sampler=replay_c,
             num_queries=spec.queries, num_negatives=spec.negatives, temp=spec.temp)
         ores.loss.backward()
         # ---------------- CUDA path ----------------
@@ -68,11 +69,14 @@ def _run_case(spec, use_index_labels=False):
             ll, lu = lab[: spec.n_lab].contiguous(), lab[spec.n_lab:].contiguous()
         else:
             ll, lu = xg["label_l"], xg["label_u"]
-        new_keys, loss = arco_b200.compute_contra_memobank_loss(
+        ret = arco_b200.compute_contra_memobank_loss(
             rep_g, ll, lu, xg["prob_l"], xg["prob_u"], xg["low_mask"], xg["high_mask"],
-            bank_gpu, ptr_gpu, caps, xg["rep_teacher"], delta_n=spec.delta_n, func=spec.func,
+            bank_gpu, ptr_gpu, caps, xg["rep_teacher"], momentum_prototype=xg.get("momentum_prototype"),
+            i_iter=spec.i_iter, delta_n=spec.delta_n, func=spec.func,
             num_queries=spec.queries, num_negatives=spec.negatives, temp=spec.temp,
             _inject={"anchor": anchors, "neg": negs}, _debug=dbg)
+        new_keys, loss = ret[-2], ret[-1]
+        assert len(ret) == (3 if spec.momentum else 2)
         loss.backward()
         torch.cuda.synchronize()
 
@@ -105,6 +109,10 @@ def _run_case(spec, use_index_labels=False):
             proto_g = (dbg["proto_sums"][:, :-1] / dbg["proto_sums"][:, -1:]).float().cpu()
             ok = torch.tensor([c > 0 for c in ores.low_valid_counts])
             assert rel_err(proto_g[ok], ores.proto[ok]) <= tol
+        if spec.momentum:                      # a11: the returned `prototype` tensor [C,Q,1,D]
+            assert ret[0].shape == (spec.classes, spec.queries, 1, spec.feat)
+            assert rel_err(ret[0].cpu(), torch.from_numpy(gold[p + "prototype"])) <= tol
+            assert rel_err(ret[0].cpu(), ores.prototype) <= tol
         gl, ol = float(gold[p + "loss"]), float(ores.loss.detach())
         assert abs(float(loss.detach()) - gl) <= tol * max(1.0, abs(gl)), f"loss {float(loss)} vs reference {gl}"
         assert abs(float(loss.detach()) - ol) <= tol * max(1.0, abs(ol)), f"loss {float(loss)} vs oracle {ol}"

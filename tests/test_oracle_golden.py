@@ -22,7 +22,8 @@ def test_loss_matches_reference(spec):
         replay = Replay(gold, step)
         res = oracle.contra_memobank_loss(
             rep, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"],
-            memobank, ptrs, caps, x["rep_teacher"], delta_n=spec.delta_n, sampler=replay,
+            memobank, ptrs, caps, x["rep_teacher"], momentum_prototype=x.get("momentum_prototype"), i_iter=spec.i_iter,
+            delta_n=spec.delta_n, sampler=replay,
             num_queries=spec.queries, num_negatives=spec.negatives, temp=spec.temp)
         res.loss.backward()
         p = f"s{step}_"
@@ -38,6 +39,8 @@ def test_loss_matches_reference(spec):
         g = torch.from_numpy(gold[p + "grad"])
         assert torch.equal(rep.grad.float() != 0, g != 0) or spec.dtype == "bf16"
         assert rel_err(rep.grad.float(), g) <= tol
+        if spec.momentum:
+            assert rel_err(res.prototype, torch.from_numpy(gold[p + "prototype"])) <= 1e-6
 
 
 @pytest.mark.parametrize("func,high,shape,seed", SAMPLER_CASES)
