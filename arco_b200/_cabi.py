@@ -62,6 +62,16 @@ class Bank(C.Structure):
     ]
 
 
+class StepIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "rep", "rep_teacher", "label_l", "label_u", "prob_l", "prob_u", "low_mask", "high_mask", "proto_sums",
+        "idx_anchor", "idx_neg", "loss", "grad_anchor", "anchor_pix", "logits", "grad_prefill", "momentum",
+        "momentum_on", "proto_out")] + [
+        ("seed", C.c_uint64), ("step", C.c_uint64),
+        ("delta_p", C.c_float), ("delta_n", C.c_float), ("temp", C.c_float), ("ema_decay", C.c_float),
+        ("low_rank", C.c_int32), ("high_rank", C.c_int32), ("func", C.c_int32), ("reserved", C.c_int32)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -86,6 +96,7 @@ def _load():
         "arco_grad_scatter": (C.c_int, [dp, vp, vp, vp, vp, vp]),
         "arco_grad_zero": (C.c_int, [dp, vp, vp]),
         "arco_grad_scatter_add": (C.c_int, [dp, vp, vp, vp, vp, vp]),
+        "arco_forward": (C.c_int, [dp, C.POINTER(StepIO), bp, vp, vp]),
         "arco_export_list": (C.c_int, [dp, i32, i32, vp, i64, vp, vp, vp]),
         "arco_bank_read": (C.c_int, [bp, i32, i32, vp, vp]),
     }

@@ -92,10 +92,9 @@ class DeviceMemoryBank:
         self.host_len = [int(x) for x in length[: self.classes]]
         self.host_ptr = [int(x) for x in ptr[: self.classes]]
         self._queue_ptrlis = queue_ptrlis
-        self._pending = collections.deque()   # (event, pinned plan bytes, step id) of steps not yet mirrored
-        self._pinned_pool = []
+        self._plan_view = None          # device view of the last step's arco_plan
+        self._dirty = False
         self.last_plan: Optional[_cabi.Plan] = None
-        self.keys_by_step = {}          # step -> new_keys of that step (short history for LazyKeys)
         self.step = 0
         self.c_struct = _cabi.Bank()
         self.c_struct.rows = self.rows.data_ptr()
@@ -124,41 +123,40 @@ class DeviceMemoryBank:
         return DeviceMemoryBank(memobank, queue_ptrlis, queue_size, feat, device)
 
     # ------------------------------------------------------------------ host mirror
-    def post_step(self, plan_bytes_dev: torch.Tensor, stream: torch.cuda.Stream) -> None:
-        """Queue an async device->pinned copy of the step's ``arco_plan``; no host sync."""
-        n = plan_bytes_dev.numel()
-        pinned = self._pinned_pool.pop() if self._pinned_pool else torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        pinned.copy_(plan_bytes_dev, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(stream)
+    def post_step(self, plan_view: torch.Tensor) -> None:
+        """Remember the step's device-resident ``arco_plan`` (a view into its workspace); nothing is copied."""
+        self._plan_view = plan_view
+        self._dirty = True
         self.step += 1
-        self._pending.append((ev, pinned, self.step))
 
     def poll(self, block: bool = False) -> Optional[_cabi.Plan]:
-        """Mirror every finished step's summary on the host (bank lengths, the caller's ``queue_prtlis``,
-        ``new_keys``).  Non-blocking by default: the training loop never waits for the device here."""
-        while self._pending and (block or self._pending[0][0].query()):
-            ev, pinned, step = self._pending.popleft()
-            ev.synchronize()
-            plan = _cabi.Plan.from_buffer_copy(pinned.numpy().tobytes()[: C.sizeof(_cabi.Plan)])
-            self._pinned_pool.append(pinned)
-            self.last_plan = plan
-            self.keys_by_step[step] = [int(plan.n_key[c]) for c in range(self.classes)]
-            for old in [k for k in self.keys_by_step if k < step - 64]:
-                del self.keys_by_step[old]
-            for c in range(self.classes):
-                self.host_len[c] = int(plan.bank_len[c])
-                self.host_ptr[c] = int(plan.queue_ptr[c])
-                self._queue_ptrlis[c][0] = self.host_ptr[c]
-            if plan.status & _cabi.ST_MULTI_HOT:
-                raise ValueError("label_l/label_u are not one-hot: some pixel has more than one non-zero class entry")
-            if plan.status & _cabi.ST_LABEL_RANGE:
-                raise ValueError("integer label map contains a class id >= num_classes")
-        return self.last_plan
+        """Kept for API symmetry: the host mirrors are refreshed on demand by :meth:`settle`."""
+        return self.settle() if block else self.last_plan
+
+    @staticmethod
+    def check_status(status: int) -> None:
+        if status & _cabi.ST_MULTI_HOT:
+            raise ValueError("label_l/label_u are not one-hot: some pixel has more than one non-zero class entry")
+        if status & _cabi.ST_LABEL_RANGE:
+            raise ValueError("integer label map contains a class id >= num_classes")
 
     def settle(self) -> Optional[_cabi.Plan]:
-        """Blocking :meth:`poll`: wait for every queued step (host sync) -- used by inspection only."""
-        return self.poll(block=True)
+        """Read the device bookkeeping (host sync) and refresh the host mirrors, including the caller's
+        ``queue_prtlis``.  Raises if the device flagged invalid labels.  Used by inspection only: the training step
+        itself never calls it."""
+        if not self._dirty:
+            return self.last_plan
+        self._dirty = False
+        lens = self.len.cpu().tolist()
+        ptrs = self.ptr.cpu().tolist()
+        for c in range(self.classes):
+            self.host_len[c] = int(lens[c])
+            self.host_ptr[c] = int(ptrs[c])
+            self._queue_ptrlis[c][0] = self.host_ptr[c]
+        if self._plan_view is not None:
+            self.last_plan = _cabi.Plan.from_buffer_copy(self._plan_view.cpu().numpy().tobytes())
+            self.check_status(self.last_plan.status)
+        return self.last_plan
 
     def length(self, cls: int) -> int:
         self.settle()
@@ -185,6 +183,7 @@ class DeviceMemoryBank:
         self.head[cls] = 0
         self.len[cls] = n
         self.host_len[cls] = n
+        self._dirty = True
 
 
 def synchronize_bank(memobank: list) -> None:

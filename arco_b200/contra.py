@@ -35,23 +35,22 @@ _PREFILL_MIN_BYTES = 512 << 20
 
 
 class LazyKeys(list):
-    """``new_keys`` (reference: list of ints, loss_helper_3d.py:404-411) resolved on first access so the
-    step itself never waits for the device."""
+    """``new_keys`` (reference: list of ints, loss_helper_3d.py:404-411) resolved on first access -- a device->host read of
+    the step's own ``arco_plan`` -- so the step itself never waits for the device."""
 
-    def __init__(self, bank: DeviceMemoryBank, classes: int):
+    def __init__(self, bank: DeviceMemoryBank, classes: int, plan_view: torch.Tensor):
         super().__init__()
         self._bank = bank
         self._classes = classes
-        self._ticket = bank.step
+        self._plan_view = plan_view
         self._done = False
 
     def _resolve(self):
         if not self._done:
-            if self._ticket not in self._bank.keys_by_step:
-                self._bank.settle()
-            if self._ticket not in self._bank.keys_by_step:
-                raise RuntimeError("new_keys of a step more than 64 steps old is no longer available")
-            super().extend(self._bank.keys_by_step[self._ticket])
+            plan = _cabi.Plan.from_buffer_copy(self._plan_view.cpu().numpy().tobytes())
+            self._plan_view = None
+            self._bank.check_status(plan.status)
+            super().extend(int(plan.n_key[c]) for c in range(self._classes))
             self._done = True
 
     def __getitem__(self, i):
@@ -100,6 +99,8 @@ class _ContraLoss(torch.autograd.Function):
         sp = stream.cuda_stream
         lib = _cabi.lib
         layout = st["layout"]
+        if st["inject"] is None and st["group"] is None and st["debug"] is None:
+            return _ContraLoss._forward_fused(ctx, rep, st, dims, bank, layout, dev, sp)
         ws = torch.empty(layout.total_bytes, dtype=torch.uint8, device=dev)
         wsp = ws.data_ptr()
         Cn, Q, N, D = dims.classes, dims.queries, dims.negatives, dims.feat
@@ -182,7 +183,9 @@ class _ContraLoss(torch.autograd.Function):
                 float(st["ema_decay"]), proto_out.data_ptr(), wsp, sp), "arco_infonce_ema")
             n_valid = ws[layout.plan + 384: layout.plan + 388].view(torch.int32)      # arco_plan.n_valid
             st["prototype_out"] = torch.where(n_valid <= 1, mom, proto_out)
-        bank.post_step(plan_view, stream)
+        bank.post_step(plan_view)
+        st["plan_view"] = plan_view
+        ctx.fused = None
         if debug is not None:
             debug.update(ws=ws, layout=layout, dims=dims, proto_sums=proto_sums, logits=logits, anchor_pix=pix,
                          grad_anchor=g_anchor, idx_anchor=idx_a, idx_neg=idx_n)
@@ -202,9 +205,66 @@ class _ContraLoss(torch.autograd.Function):
         return loss.reshape(())
 
     @staticmethod
+    def _forward_fused(ctx, rep, st, dims, bank, layout, dev, sp):
+        """Production path: one allocation, one FFI call (arco_forward), no tensor views besides the loss."""
+        Cn, Q, N, D = dims.classes, dims.queries, dims.negatives, dims.feat
+        al = lambda n: (n + 255) & ~255
+        o_proto = al(layout.total_bytes)
+        o_ia = o_proto + al(Cn * (D + 1) * 8)
+        o_in = o_ia + al(Cn * Q * 4)
+        o_loss = o_in + al(Cn * Q * max(N, 1) * 4)
+        o_pix = o_loss + 256
+        o_ga = o_pix + al(Cn * Q * 4)
+        o_mom = o_ga + al(Cn * Q * D * 4)
+        mom = st["momentum"]
+        total = o_mom + (al(Cn * Q * D * 4) + 256 if mom is not None else 0)
+        buf = torch.empty(total, dtype=torch.uint8, device=dev)
+        base = buf.data_ptr()
+        io = _cabi.StepIO()
+        io.rep, io.rep_teacher = st["rep_data"].data_ptr(), st["rep_teacher"].data_ptr()
+        io.label_l = st["label_l"].data_ptr() if st["label_l"] is not None else None
+        io.label_u = st["label_u"].data_ptr() if st["label_u"] is not None else None
+        io.prob_l = st["prob_l"].data_ptr() if st["prob_l"] is not None else None
+        io.prob_u = st["prob_u"].data_ptr() if st["prob_u"] is not None else None
+        io.low_mask, io.high_mask = st["low_mask"].data_ptr(), st["high_mask"].data_ptr()
+        io.proto_sums, io.idx_anchor, io.idx_neg = base + o_proto, base + o_ia, base + o_in
+        io.loss, io.anchor_pix, io.grad_anchor = base + o_loss, base + o_pix, base + o_ga
+        io.logits = None
+        grad_buf = None
+        if st["prefill"]:
+            grad_buf = torch.empty(rep.shape, dtype=rep.dtype, device=dev)
+            io.grad_prefill = grad_buf.data_ptr()
+        if mom is not None:
+            mom_on = (mom != 0).any().to(torch.int32).reshape(1)
+            proto_out = buf[o_mom: o_mom + Cn * Q * D * 4].view(torch.float32).view(mom.shape)
+            proto_out.zero_()
+            io.momentum, io.momentum_on, io.proto_out, io.ema_decay = mom.data_ptr(), mom_on.data_ptr(), proto_out.data_ptr(), float(st["ema_decay"])
+        io.seed, io.step = st["seed"], bank.step
+        io.delta_p, io.delta_n, io.temp = DELTA_P, float(st["delta_n"]), float(st["temp"])
+        io.low_rank, io.high_rank, io.func = LOW_RANK, HIGH_RANK, st["func"]
+        _cabi.check(_cabi.lib.arco_forward(C.byref(dims), C.byref(io), C.byref(bank.c_struct), base, sp), "arco_forward")
+        plan_view = buf[layout.plan: layout.plan + C.sizeof(_cabi.Plan)]
+        bank.post_step(plan_view)
+        st["plan_view"] = plan_view
+        if mom is not None:
+            n_valid = buf[layout.plan + 384: layout.plan + 388].view(torch.int32)      # arco_plan.n_valid
+            st["prototype_out"] = torch.where(n_valid <= 1, mom, proto_out)
+        ctx.fused = (buf, base + o_ga, base + o_pix)
+        ctx.dims = dims
+        ctx.rep_shape = rep.shape
+        ctx.rep_dtype = rep.dtype
+        ctx.prefilled = [grad_buf] if grad_buf is not None else None
+        return buf[o_loss: o_loss + 4].view(torch.float32).reshape(())
+
+    @staticmethod
     def backward(ctx, grad_out):
-        g_anchor, pix = ctx.saved_tensors
-        dev = g_anchor.device
+        if getattr(ctx, "fused", None) is not None:
+            buf, ga_ptr, pix_ptr = ctx.fused
+            dev = buf.device
+        else:
+            g_anchor, pix = ctx.saved_tensors
+            dev = g_anchor.device
+            ga_ptr, pix_ptr = g_anchor.data_ptr(), pix.data_ptr()
         go = grad_out.detach().to(torch.float32).contiguous()
         stream = torch.cuda.current_stream(dev)
         sp = stream.cuda_stream
@@ -212,11 +272,11 @@ class _ContraLoss(torch.autograd.Function):
         if pre is not None and pre[0] is not None:
             grad_rep = pre[0]
             pre[0] = None                                   # a second backward (retain_graph) takes the slow path
-            _cabi.check(_cabi.lib.arco_grad_scatter_add(C.byref(ctx.dims), g_anchor.data_ptr(), pix.data_ptr(),
+            _cabi.check(_cabi.lib.arco_grad_scatter_add(C.byref(ctx.dims), ga_ptr, pix_ptr,
                                                         go.data_ptr(), grad_rep.data_ptr(), sp), "arco_grad_scatter_add")
         else:
             grad_rep = torch.empty(ctx.rep_shape, dtype=ctx.rep_dtype, device=dev)
-            _cabi.check(_cabi.lib.arco_grad_scatter(C.byref(ctx.dims), g_anchor.data_ptr(), pix.data_ptr(), go.data_ptr(),
+            _cabi.check(_cabi.lib.arco_grad_scatter(C.byref(ctx.dims), ga_ptr, pix_ptr, go.data_ptr(),
                                                     grad_rep.data_ptr(), sp), "arco_grad_scatter")
         return grad_rep, None
 
@@ -327,13 +387,12 @@ def compute_contra_memobank_loss(
                               _cabi.BF16 if rep.dtype == torch.bfloat16 else _cabi.F32, label_kind)
             cached = _GEOMETRY[key] = (dims, _cabi.workspace_layout(dims))
         dims, layout = cached
-        lead = 2 if label_kind == _cabi.LABEL_ONEHOT_I64 else 1
         rep_data = rep.detach().contiguous()
         state = dict(
             dims=dims, layout=layout, bank=bank,
-            label_l=_flat(label_l, lead) if n_lab else None, label_u=_flat(label_u, lead) if n_unlab else None,
-            prob_l=_flat(prob_l, 2) if n_lab else None, prob_u=_flat(prob_u, 2) if n_unlab else None,
-            low_mask=_flat(low_mask, 2), high_mask=_flat(high_mask, 2),
+            label_l=label_l.contiguous() if n_lab else None, label_u=label_u.contiguous() if n_unlab else None,
+            prob_l=prob_l.contiguous() if n_lab else None, prob_u=prob_u.contiguous() if n_unlab else None,
+            low_mask=low_mask.contiguous(), high_mask=high_mask.contiguous(),
             rep_teacher=rep_teacher.detach().contiguous(), rep_data=rep_data,
             delta_n=delta_n, temp=temp, func=_FUNC.get(func, _cabi.FUNC_UNIFORM),
             seed=int(seed) if seed is not None else int(torch.cuda.initial_seed()) & (2 ** 63 - 1),
@@ -343,6 +402,7 @@ def compute_contra_memobank_loss(
                          and rep.numel() * rep.element_size() >= _PREFILL_MIN_BYTES),
         )
         loss = _ContraLoss.apply(rep, state)
+    keys = LazyKeys(bank, Cn, state["plan_view"])
     if mom is not None:
-        return state["prototype_out"].to(momentum_prototype.dtype), LazyKeys(bank, Cn), loss
-    return LazyKeys(bank, Cn), loss
+        return state["prototype_out"].to(momentum_prototype.dtype), keys, loss
+    return keys, loss

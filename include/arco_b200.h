@@ -191,6 +191,37 @@ ARCO_API int arco_grad_zero(const arco_dims* dims, void* grad_rep, void* stream)
 ARCO_API int arco_grad_scatter_add(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
                                    const float* grad_out, void* grad_rep, void* stream);
 
+/* Every device pointer of one single-GPU forward step, for arco_forward. */
+typedef struct arco_step_io {
+    const void*    rep;            /* [B,D,S] student representation                                   */
+    const void*    rep_teacher;    /* [B,D,S]                                                          */
+    const int64_t* label_l;        /* per dims->label_kind                                             */
+    const int64_t* label_u;
+    const float*   prob_l;         /* [B_l,C,S]                                                        */
+    const float*   prob_u;         /* [B_u,C,S]                                                        */
+    const float*   low_mask;       /* [B,S]                                                            */
+    const float*   high_mask;      /* [B,S]                                                            */
+    double*        proto_sums;     /* out [C,D+1]                                                      */
+    int32_t*       idx_anchor;     /* out [C,Q]                                                        */
+    int32_t*       idx_neg;        /* out [C,Q*N]                                                      */
+    float*         loss;           /* out [1]                                                          */
+    float*         grad_anchor;    /* out [C,Q,D]                                                      */
+    int32_t*       anchor_pix;     /* out [C,Q]                                                        */
+    float*         logits;         /* out [C,Q,1+N] or NULL                                            */
+    void*          grad_prefill;   /* NULL, or the grad_rep buffer to zero-fill on a side stream       */
+    const float*   momentum;       /* NULL, or [C,Q,D] (a11)                                           */
+    const int32_t* momentum_on;
+    float*         proto_out;
+    uint64_t       seed, step;     /* Philox seed / per-step stream id of the sampler                  */
+    float          delta_p, delta_n, temp, ema_decay;
+    int32_t        low_rank, high_rank, func, reserved;
+} arco_step_io;
+
+/* The whole single-GPU forward in one call (same kernels and order as the stage entry points; the sampler and the
+ * optional grad_rep zero fill run on library-owned side streams and are joined with events, no host sync). */
+ARCO_API int arco_forward(const arco_dims* dims, const arco_step_io* io, const arco_bank* bank, void* workspace,
+                          void* stream);
+
 /* Parity / inspection helpers (not on the hot path). */
 /* kind: 0 anchor candidates, 1 negative keys, 2 low-valid; writes the raster-ordered flat pixel ids of
  * class `cls` to out (capacity out_cap) and the count to *count_dev. */

@@ -37,13 +37,13 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_the_c_compiler(tmp_path):
     from arco_b200 import _cabi
     prog = tmp_path / "sizes.c"
-    prog.write_text('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu %%zu\\n", sizeof(arco_dims), '
-                    'sizeof(arco_ws_layout), sizeof(arco_plan), sizeof(arco_bank));return 0;}\n' % HEADER)
+    prog.write_text('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu %%zu %%zu\\n", sizeof(arco_dims), '
+                    'sizeof(arco_ws_layout), sizeof(arco_plan), sizeof(arco_bank), sizeof(arco_step_io));return 0;}\n' % HEADER)
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", str(prog), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     assert sizes == [ctypes.sizeof(_cabi.Dims), ctypes.sizeof(_cabi.WsLayout), ctypes.sizeof(_cabi.Plan),
-                     ctypes.sizeof(_cabi.Bank)]
+                     ctypes.sizeof(_cabi.Bank), ctypes.sizeof(_cabi.StepIO)]
 
 
 def test_layout_and_argument_errors_without_a_gpu():
