@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--aten-gpu", action="store_true",
+                    help="also time the oracle port's torch/ATen ops ON THE GPU (the reference's own op mix, CPU banks "
+                         "uploaded per class like loss_helper_3d.py:466) as a like-for-like GPU baseline")
     return ap.parse_args()
 
 
@@ -285,6 +288,10 @@ def main_ours(args):
             e2e["_total_ms"] = float(tt.item())
         e2e["value"] = world * P * e2e["steps"] / (e2e.pop("_total_ms") * 1e-3) / 1e6
 
+    aten = None
+    if rank == 0 and world == 1 and args.aten_gpu:
+        aten = run_aten_gpu(torch, spec, x, dev, args.func)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = run_cpu(args.workload, 5, 1, args.func)
@@ -304,7 +311,7 @@ def main_ours(args):
                 "l2": l2_note, "timing": "CUDA events per step on the launching stream, max over ranks",
             },
             "clocks": clk, "gpu_launches": args.steps * (KERNELS_PER_STEP + (1 if world > 1 else 0)),
-            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "stages": stages,
+            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "aten_gpu_baseline": aten, "stages": stages,
         }
         print(json.dumps(line))
     if world > 1:
@@ -400,6 +407,31 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
             "note": "rep_teacher is channel-first, so every 32-byte sector that holds one low-valid pixel must be fetched: "
                     "with the iid 20% masks of this workload that is ALL of P*D*e_t; 'traffic' is the ncu-measured DRAM bytes"}
     return stages, roof
+
+
+def run_aten_gpu(torch, spec, x, dev, func, steps=3):
+    """The oracle port (same ATen op mix as the reference) with CUDA tensors: what running the reference's PyTorch loss on
+    this B200 costs, including its per-class CPU->GPU bank upload and CPU samplers.  Reported, not optimised."""
+    import oracle
+    from arco_b200.synth import bench_bank
+    memobank, ptrs, caps = bench_bank(spec, seed=4321)
+    sampler = {"smc": oracle.grid_strata_sample, "asmc": oracle.grid_antithetic_sample}.get(func)
+    rep = x["rep"].detach().clone().requires_grad_(True)
+    times = []
+    for i in range(steps + 1):
+        rep.grad = None
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        res = oracle.contra_memobank_loss(
+            rep, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"], memobank, ptrs, caps,
+            x["rep_teacher"], delta_n=0.97, sampler=sampler, num_queries=spec.queries, num_negatives=spec.negatives, temp=0.5)
+        res.loss.backward()
+        torch.cuda.synchronize(dev)
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return {"value": spec.pixels / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "what": "oracle port (torch/ATen ops of the reference) on the same B200, full workload, wall clock with sync"}
 
 
 def run_e2e(torch, arco_b200, spec, x, memobank, ptrs, caps, dev, kw, world, steps, sync_all):
