@@ -9,8 +9,13 @@ The reference trainers own three Python lists (``/root/reference/code/train_arco
 
 and ``dequeue_and_enqueue`` (``loss_helper_3d.py:12-32``) copies every step's keys to the CPU,
 concatenates, and keeps the newest ``queue_size`` rows; the loss then uploads the whole bank again
-(``:466``).  Here the rows live in HBM as one ``[sum(cap), D]`` fp32 ring per class; (head, length,
+(``:466``).  Here the rows live in HBM as one ``[sum(cap), D]`` ring per class; (head, length,
 pointer) are device scalars updated by ``arco_scan_plan``; nothing crosses PCIe in the step.
+
+Row storage is fp32, or bf16 when the trainer runs the representation head in bf16 AND every adopted row is exactly
+representable in bf16 (keys are teacher rows, so with a bf16 ``rep_teacher`` the narrow ring holds bit-identical
+values at half the gather traffic).  Assigning a row that is not bf16-exact, or a later fp32 call, widens the ring
+back to fp32 -- values never change.  ``ARCO_BANK_BF16=0`` forces fp32 storage.
 
 The caller's lists are adopted lazily on the first call: ``memobank[c]`` is replaced by a
 :class:`BankSlot` (a ``list`` subclass) whose element 0 still answers ``.shape[0]`` and row indexing in
@@ -22,6 +27,7 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -57,8 +63,14 @@ class BankSlot(list):
         return f"BankSlot(class={self.cls}, rows={self.bank.length(self.cls)}, cap={self.bank.caps[self.cls]})"
 
 
+def _bf16_exact(t: torch.Tensor) -> bool:
+    t = t.to(torch.float32)
+    return bool((t.to(torch.bfloat16).to(torch.float32) == t).all())
+
+
 class DeviceMemoryBank:
-    def __init__(self, memobank: list, queue_ptrlis: list, queue_size: Sequence[int], feat: int, device):
+    def __init__(self, memobank: list, queue_ptrlis: list, queue_size: Sequence[int], feat: int, device,
+                 prefer_bf16: bool = False):
         self.device = torch.device(device)
         self.feat = int(feat)
         self.classes = len(memobank)
@@ -72,7 +84,10 @@ class DeviceMemoryBank:
         self.row_off = [0]
         for cap in self.caps:
             self.row_off.append(self.row_off[-1] + cap)
-        self.rows = torch.zeros((self.row_off[-1], self.feat), dtype=torch.float32, device=self.device)
+        narrow = (prefer_bf16 and self.feat % 8 == 0 and os.environ.get("ARCO_BANK_BF16", "1") != "0"
+                  and all(_bf16_exact(m[0]) for m in memobank))
+        self.rows = torch.zeros((self.row_off[-1], self.feat), dtype=torch.bfloat16 if narrow else torch.float32,
+                                device=self.device)
         head = torch.zeros(_cabi.MAX_CLASSES, dtype=torch.int32)
         length = torch.zeros(_cabi.MAX_CLASSES, dtype=torch.int32)
         ptr = torch.zeros(_cabi.MAX_CLASSES, dtype=torch.int64)
@@ -83,7 +98,7 @@ class DeviceMemoryBank:
             init = init[-self.caps[c]:] if init.shape[0] > self.caps[c] else init
             n = init.shape[0]
             if n:
-                self.rows[self.row_off[c]: self.row_off[c] + n] = init.to(self.device, torch.float32)
+                self.rows[self.row_off[c]: self.row_off[c] + n] = init.to(self.device, self.rows.dtype)
             length[c] = n
             ptr[c] = int(queue_ptrlis[c].reshape(-1)[0])
         self.head = head.to(self.device)
@@ -98,6 +113,7 @@ class DeviceMemoryBank:
         self.step = 0
         self.c_struct = _cabi.Bank()
         self.c_struct.rows = self.rows.data_ptr()
+        self.c_struct.row_dtype = _cabi.BF16 if narrow else _cabi.F32
         self.c_struct.head = self.head.data_ptr()
         self.c_struct.len = self.len.data_ptr()
         self.c_struct.queue_ptr = self.ptr.data_ptr()
@@ -110,7 +126,8 @@ class DeviceMemoryBank:
 
     # ------------------------------------------------------------------ adoption
     @staticmethod
-    def adopt(memobank: list, queue_ptrlis: list, queue_size: Sequence[int], feat: int, device) -> "DeviceMemoryBank":
+    def adopt(memobank: list, queue_ptrlis: list, queue_size: Sequence[int], feat: int, device,
+              rep_dtype: torch.dtype = torch.float32) -> "DeviceMemoryBank":
         first = memobank[0] if len(memobank) else None
         if isinstance(first, BankSlot):
             bank = first.bank
@@ -119,8 +136,22 @@ class DeviceMemoryBank:
             if [int(q) for q in queue_size] != bank.caps:
                 raise ValueError("queue_size changed after the memory bank was adopted")
             bank._queue_ptrlis = queue_ptrlis
+            if rep_dtype != torch.bfloat16:
+                bank.widen()                     # fp32 keys are not bf16-exact in general
             return bank
-        return DeviceMemoryBank(memobank, queue_ptrlis, queue_size, feat, device)
+        return DeviceMemoryBank(memobank, queue_ptrlis, queue_size, feat, device, rep_dtype == torch.bfloat16)
+
+    @property
+    def row_dtype(self) -> torch.dtype:
+        return self.rows.dtype
+
+    def widen(self) -> None:
+        """Switch a bf16 ring to fp32 storage (exact); no-op for an fp32 ring."""
+        if self.rows.dtype == torch.float32:
+            return
+        self.rows = self.rows.to(torch.float32)
+        self.c_struct.rows = self.rows.data_ptr()
+        self.c_struct.row_dtype = _cabi.F32
 
     # ------------------------------------------------------------------ host mirror
     def post_step(self, plan_view: torch.Tensor) -> None:
@@ -179,7 +210,9 @@ class DeviceMemoryBank:
             raise ValueError(f"bank rows must be [n, {self.feat}]")
         value = value[-self.caps[cls]:] if value.shape[0] > self.caps[cls] else value
         n = value.shape[0]
-        self.rows[self.row_off[cls]: self.row_off[cls] + n] = value.to(self.device, torch.float32)
+        if self.rows.dtype == torch.bfloat16 and not _bf16_exact(value):
+            self.widen()
+        self.rows[self.row_off[cls]: self.row_off[cls] + n] = value.to(self.device, self.rows.dtype)
         self.head[cls] = 0
         self.len[cls] = n
         self.host_len[cls] = n

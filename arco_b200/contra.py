@@ -378,7 +378,7 @@ def compute_contra_memobank_loss(
         # reference: min(1 - 1/i_iter, 0.999), evaluated only when the tensor is not all zero (ZeroDivisionError at i_iter=0)
         ema_decay = min(1.0 - 1.0 / i_iter, 0.999) if i_iter != 0 else float("nan")
     with torch.cuda.device(dev):
-        bank = DeviceMemoryBank.adopt(memobank, queue_prtlis, queue_size, D, dev)
+        bank = DeviceMemoryBank.adopt(memobank, queue_prtlis, queue_size, D, dev, rep.dtype)
         bank.poll()                         # mirror finished steps (non-blocking): queue_prtlis, label errors
         key = (n_lab, n_unlab, Cn, D, S, int(num_queries), int(num_negatives), rep.dtype, label_kind, dev.index)
         cached = _GEOMETRY.get(key)

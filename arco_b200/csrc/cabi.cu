@@ -69,14 +69,18 @@ __global__ void __launch_bounds__(1024) export_list_kernel(const uint8_t* __rest
     }
 }
 
-__global__ void bank_read_kernel(const float* __restrict__ rows, const int32_t* __restrict__ head,
+__global__ void bank_read_kernel(const void* __restrict__ rows, int bf16, const int32_t* __restrict__ head,
                                  const int32_t* __restrict__ len, int cls, int cap, int64_t row_off, int D,
                                  float* __restrict__ out) {
     const int n = len[cls], h = head[cls];
     for (int r = blockIdx.x; r < n; r += gridDim.x) {
         int phys = h + r;
         if (phys >= cap) phys -= cap;
-        for (int d = threadIdx.x; d < D; d += blockDim.x) out[(int64_t)r * D + d] = rows[(row_off + phys) * D + d];
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const int64_t at = (row_off + phys) * D + d;
+            out[(int64_t)r * D + d] = bf16 ? bf16_bits_to_float(reinterpret_cast<const unsigned short*>(rows)[at])
+                                           : reinterpret_cast<const float*>(rows)[at];
+        }
     }
 }
 
@@ -114,7 +118,7 @@ extern "C" int arco_export_list(const arco_dims* dims, int32_t kind, int32_t cls
 
 extern "C" int arco_bank_read(const arco_bank* bank, int32_t cls, int32_t feat, float* out, void* stream) {
     ARCO_REQUIRE(bank && out && cls >= 0 && cls < ARCO_MAX_CLASSES && feat > 0, "arco_bank_read: bad argument");
-    arco::bank_read_kernel<<<256, 128, 0, (cudaStream_t)stream>>>(bank->rows, bank->head, bank->len, cls, bank->cap[cls],
+    arco::bank_read_kernel<<<256, 128, 0, (cudaStream_t)stream>>>(bank->rows, bank->row_dtype == ARCO_BF16, bank->head, bank->len, cls, bank->cap[cls],
                                                                 bank->row_off[cls], feat, out);
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;

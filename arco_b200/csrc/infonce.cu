@@ -19,7 +19,7 @@ namespace arco {
 
 struct InfoParams {
     const void* rep;
-    const float* bank_rows;
+    const void* bank_rows;       // fp32 or bf16 rows (arco_bank.row_dtype)
     const double* proto_sums;
     const int32_t* idx_a;
     const int32_t* idx_n;
@@ -40,7 +40,7 @@ struct InfoParams {
     int32_t cap[ARCO_MAX_CLASSES];
     int64_t S;
     int32_t C, D, Q, N, tpi, NT;
-    int32_t KC, RS;          // keys per staged chunk, padded row stride (floats)
+    int32_t KC, RS16;        // keys per staged chunk, padded row stride in 16-byte chunks
     int32_t rep_dtype;
     float temp;
 };
@@ -85,14 +85,29 @@ __device__ __forceinline__ float warp_max(float v) {
 
 constexpr float kEps = 1e-8f;   // torch.cosine_similarity eps (ATen default), applied per norm
 
-template <int MAXIT>
+// 16-byte chunk of a bank row -> CHD floats (4 fp32, or 8 bf16 widened)
+template <bool BF16BANK>
+__device__ __forceinline__ void unpack_chunk(const uint4& u, float* v) {
+    if (BF16BANK) {
+        v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+        v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+        v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+        v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+    } else {
+        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    }
+}
+
+// MAXIT: 16-byte chunks per lane in pass 2 (ceil(chunks per row / 32)); BF16BANK: the ring stores bf16 rows
+template <int MAXIT, bool BF16BANK>
 __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int D = p.D, CPL = D / 4;
+    constexpr int CHD = BF16BANK ? 8 : 4;                         // feature dims per 16-byte chunk of a bank row
+    const int D = p.D, CPL = D / CHD;
     float* a_hat = reinterpret_cast<float*>(smem_raw);            // [D]
     float* k0hat = a_hat + D;                                     // [D]
     float* gbuf = k0hat + D;                                      // [4][D]
-    float* stage = gbuf + 4 * D;                                  // [4][KC*RS]  one stage per warp
+    uint4* stage = reinterpret_cast<uint4*>(gbuf + 4 * D);        // [4][KC*RS16]  one stage per warp
     __shared__ __align__(8) uint64_t bars[4];
     __shared__ float s_red[4][2];
     __shared__ float s_stats[4][3];
@@ -111,7 +126,8 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         const int blen = pl->bank_len[bank_cls];
         const int bhead = pl->bank_head[bank_cls];
         const int cap = p.cap[bank_cls];
-        const float* bank = p.bank_rows + p.row_off[bank_cls] * D;
+        const uint32_t row_bytes = (uint32_t)D * (BF16BANK ? 2u : 4u);
+        const unsigned char* bank = reinterpret_cast<const unsigned char*>(p.bank_rows) + p.row_off[bank_cls] * (int64_t)row_bytes;
         const float inv_scale = pl->inv_scale;
 
         if (tid < 4) mbar_init(&bars[tid], 1);
@@ -204,14 +220,13 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         const float z0 = cos0 * inv_temp;
 
         // ---- this warp's share of the negatives ----
-        const int KC = p.KC, RS = p.RS;
+        const int KC = p.KC, RS16 = p.RS16;
         const int npw = (p.N + 3) / 4;
         const int n_begin = min(p.N, warp * npw), n_end = min(p.N, n_begin + npw);
         const int cnt = n_end - n_begin;
         const int nchunks = (cnt + KC - 1) / KC;
         const int32_t* my_idx = p.idx_n + ((int64_t)j * p.Q + q) * p.N + n_begin;
-        float* wstage = stage + (size_t)warp * KC * RS;
-        const uint32_t row_bytes = (uint32_t)D * 4u;
+        uint4* wstage = stage + (size_t)warp * KC * RS16;
 
         // Occupancy instead of double buffering: a warp owns ONE stage (<= 9 KB); with ~5 CTAs (20 warps) per
         // SM the other warps' gathers and math hide this warp's wait.
@@ -224,7 +239,7 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
                 r = min(max(r, 0), blen - 1);
                 int phys = bhead + r;
                 if (phys >= cap) phys -= cap;
-                bulk_g2s(wstage + (size_t)lane * RS, bank + (int64_t)phys * D, row_bytes, &bars[warp]);
+                bulk_g2s(wstage + (size_t)lane * RS16, bank + (int64_t)phys * row_bytes, row_bytes, &bars[warp]);
             }
         };
 
@@ -234,28 +249,33 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         const int KP = 32 / cplp, kpar = lane / cplp, chl = lane % cplp;
 
         float m_run = -INFINITY, S_run = 0.f, S2_run = 0.f;
-        float4 G[MAXIT];
+        float G[MAXIT][CHD];
 #pragma unroll
-        for (int it = 0; it < MAXIT; ++it) G[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* a4 = reinterpret_cast<const float4*>(a_hat);
+        for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+            for (int e = 0; e < CHD; ++e) G[it][e] = 0.f;
 
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             issue(chunk);
             mbar_wait(&bars[warp], (uint32_t)(chunk & 1));
             const int nv = min(KC, cnt - chunk * KC);
-            const float* rows = wstage;
+            const uint4* rows = wstage;
             // pass 1: lane (key kq, segment seg) -> dot and squared norm
             float dot = 0.f, n2 = 0.f;
             if (kq < nv) {
-                const float4* r4 = reinterpret_cast<const float4*>(rows + (size_t)kq * RS);
-                float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f), n4 = d4;   // 8 independent FMA chains
+                const uint4* r16 = rows + (size_t)kq * RS16;
+                float dacc[CHD], nacc[CHD];                                   // CHD independent FMA chains each
+#pragma unroll
+                for (int e = 0; e < CHD; ++e) { dacc[e] = 0.f; nacc[e] = 0.f; }
                 for (int ch = seg; ch < CPL; ch += DSEG) {
-                    const float4 kv = r4[ch], av = a4[ch];
-                    d4.x += kv.x * av.x; d4.y += kv.y * av.y; d4.z += kv.z * av.z; d4.w += kv.w * av.w;
-                    n4.x += kv.x * kv.x; n4.y += kv.y * kv.y; n4.z += kv.z * kv.z; n4.w += kv.w * kv.w;
+                    float kv[CHD];
+                    unpack_chunk<BF16BANK>(r16[ch], kv);
+                    const float* av = a_hat + ch * CHD;
+#pragma unroll
+                    for (int e = 0; e < CHD; ++e) { dacc[e] += kv[e] * av[e]; nacc[e] += kv[e] * kv[e]; }
                 }
-                dot = (d4.x + d4.y) + (d4.z + d4.w);
-                n2 = (n4.x + n4.y) + (n4.z + n4.w);
+#pragma unroll
+                for (int e = 0; e < CHD; ++e) { dot += dacc[e]; n2 += nacc[e]; }
             }
             for (int o = KC; o < 32; o <<= 1) {
                 dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -277,18 +297,22 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
             const float coef = e * inv_nk;
             // pass 2: G += sum_k coef_k * key_k, lanes tile the row in 16-byte chunks
 #pragma unroll
-            for (int it = 0; it < MAXIT; ++it) { G[it].x *= rescale; G[it].y *= rescale; G[it].z *= rescale; G[it].w *= rescale; }
+            for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+                for (int e2 = 0; e2 < CHD; ++e2) G[it][e2] *= rescale;
             for (int kk0 = 0; kk0 < nv; kk0 += KP) {
                 const int kk = kk0 + kpar;
                 const float ck = __shfl_sync(0xffffffffu, coef, kk < KC ? kk : 0);
                 if (kk < nv) {
-                    const float4* r4 = reinterpret_cast<const float4*>(rows + (size_t)kk * RS);
+                    const uint4* r16 = rows + (size_t)kk * RS16;
 #pragma unroll
                     for (int it = 0; it < MAXIT; ++it) {
                         const int ch = chl + 32 * it;
                         if (ch < CPL) {
-                            const float4 kv = r4[ch];
-                            G[it].x += ck * kv.x; G[it].y += ck * kv.y; G[it].z += ck * kv.z; G[it].w += ck * kv.w;
+                            float kv[CHD];
+                            unpack_chunk<BF16BANK>(r16[ch], kv);
+#pragma unroll
+                            for (int e2 = 0; e2 < CHD; ++e2) G[it][e2] += ck * kv[e2];
                         }
                     }
                 }
@@ -297,18 +321,18 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         }
         for (int o = cplp; o < 32; o <<= 1) {
 #pragma unroll
-            for (int it = 0; it < MAXIT; ++it) {
-                G[it].x += __shfl_xor_sync(0xffffffffu, G[it].x, o);
-                G[it].y += __shfl_xor_sync(0xffffffffu, G[it].y, o);
-                G[it].z += __shfl_xor_sync(0xffffffffu, G[it].z, o);
-                G[it].w += __shfl_xor_sync(0xffffffffu, G[it].w, o);
-            }
+            for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+                for (int e2 = 0; e2 < CHD; ++e2) G[it][e2] += __shfl_xor_sync(0xffffffffu, G[it][e2], o);
         }
         if (kpar == 0) {
 #pragma unroll
             for (int it = 0; it < MAXIT; ++it) {
                 const int ch = chl + 32 * it;
-                if (ch < CPL) reinterpret_cast<float4*>(gbuf + (size_t)warp * D)[ch] = G[it];
+                if (ch < CPL) {
+#pragma unroll
+                    for (int e2 = 0; e2 < CHD; ++e2) gbuf[(size_t)warp * D + ch * CHD + e2] = G[it][e2];
+                }
             }
         }
         if (lane == 0) { s_stats[warp][0] = m_run; s_stats[warp][1] = S_run; s_stats[warp][2] = S2_run; }
@@ -396,25 +420,32 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     p.S = d.space; p.C = d.classes; p.D = d.feat; p.Q = d.queries; p.N = d.negatives;
     p.tpi = L.tiles_per_image; p.NT = L.n_tiles; p.rep_dtype = d.rep_dtype; p.temp = temp;
     // stage geometry: KC keys per chunk (<= 9 KB per stage), row stride padded for conflict-free 16-B reads
-    const int cpl = d.feat / 4;
+    const bool bf16bank = bank->row_dtype == ARCO_BF16;
+    ARCO_REQUIRE(!bf16bank || d.feat % 8 == 0, "a bf16 bank needs D to be a multiple of 8");
+    const int cpl = d.feat / (bf16bank ? 8 : 4);
+    static const int64_t stage_budget = [] {
+        const char* e = getenv("ARCO_INFONCE_STAGE");               // tuning knob: bytes of staged rows per warp
+        return e && atoi(e) > 0 ? (int64_t)atoi(e) : (int64_t)9216;
+    }();
     int kc = 32;
-    while (kc > 4 && (int64_t)kc * (cpl + 2) * 16 > 9216) kc >>= 1;
-    int rs4 = cpl;
-    if (kc >= 8) { while ((rs4 & 1) == 0) ++rs4; } else { while ((rs4 & 3) != 2) ++rs4; }
-    p.KC = kc; p.RS = rs4 * 4;
-    const size_t smem = (size_t)6 * d.feat * 4 + (size_t)4 * kc * p.RS * 4;
+    while (kc > 4 && (int64_t)kc * (cpl + 2) * 16 > stage_budget) kc >>= 1;
+    int rs16 = cpl;
+    if (kc >= 8) { while ((rs16 & 1) == 0) ++rs16; } else { while ((rs16 & 3) != 2) ++rs16; }
+    p.KC = kc; p.RS16 = rs16;
+    const size_t smem = (size_t)6 * d.feat * 4 + (size_t)4 * kc * rs16 * 16;
     const int grid = d.classes * d.queries;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d.feat <= 128) {
-        ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        arco::infonce_kernel<1><<<grid, 128, smem, st>>>(p);
-    } else if (d.feat <= 256) {
-        ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        arco::infonce_kernel<2><<<grid, 128, smem, st>>>(p);
+#define ARCO_INFONCE(MI, BF)                                                                                               \
+    do {                                                                                                                   \
+        ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_kernel<MI, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        arco::infonce_kernel<MI, BF><<<grid, 128, smem, st>>>(p);                                                           \
+    } while (0)
+    if (bf16bank) {
+        if (cpl <= 32) ARCO_INFONCE(1, true); else ARCO_INFONCE(2, true);
     } else {
-        ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        arco::infonce_kernel<4><<<grid, 128, smem, st>>>(p);
+        if (cpl <= 32) ARCO_INFONCE(1, false); else if (cpl <= 64) ARCO_INFONCE(2, false); else ARCO_INFONCE(4, false);
     }
+#undef ARCO_INFONCE
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
 }

@@ -27,14 +27,21 @@ struct ProtoParams {
     const uint32_t* tile_flagged;
     const uint32_t* off_key;
     const arco_plan* plan;
-    float* bank_rows;
+    void* bank_rows;
     float* partials;
     int64_t row_off[ARCO_MAX_CLASSES];
     int32_t cap[ARCO_MAX_CLASSES];
     int64_t S;
     int32_t B, C, D, tpi, NT, NDC;
     int32_t vec_ok;        // 16-byte loads along S are legal
+    int32_t bank_bf16;     // ring rows are bf16 (only with a bf16 rep_teacher: the narrowing is exact)
 };
+
+// four floats that came from bf16 values -> their four bf16 bit patterns (exact: the low halves are zero)
+__device__ __forceinline__ uint2 narrow4(const float4& v) {
+    return make_uint2(__byte_perm(__float_as_uint(v.x), __float_as_uint(v.y), 0x7632u),
+                      __byte_perm(__float_as_uint(v.z), __float_as_uint(v.w), 0x7632u));
+}
 
 template <typename T> struct Elem;
 template <> struct Elem<float> { static constexpr int PER16 = 4; };
@@ -232,7 +239,12 @@ __global__ void __launch_bounds__(256) proto_enqueue_kernel(ProtoParams p) {
                             if (ord >= s_skip[cls]) {
                                 const int64_t pos = ((int64_t)s_base[cls] + ord) % p.cap[cls];
                                 const float4 v = tile[target * NCH + ((ci + (target >> ROT)) & (NCH - 1))];
-                                reinterpret_cast<float4*>(p.bank_rows + (p.row_off[cls] + pos) * D + d0)[ci] = v;
+                                if (p.bank_bf16)
+                                    reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(p.bank_rows) +
+                                                             (p.row_off[cls] + pos) * D + d0)[ci] = narrow4(v);
+                                else
+                                    reinterpret_cast<float4*>(reinterpret_cast<float*>(p.bank_rows) +
+                                                              (p.row_off[cls] + pos) * D + d0)[ci] = v;
                             }
                         }
                     }
@@ -520,9 +532,16 @@ __global__ void __launch_bounds__(256, 2) proto_pipe_kernel(ProtoParams p) {
                         const uint32_t pos = ((uint32_t)s_base[cls] + ord % cap) % cap;
                         float4 lo, hi;
                         widen(cell_of(target), lo, hi);
-                        float4* dst = reinterpret_cast<float4*>(p.bank_rows + (p.row_off[cls] + pos) * D + d0 + EPL * ci);
-                        dst[0] = lo;
-                        if (EPL == 8 && rows_on > 4) dst[1] = hi;
+                        const int64_t at = (p.row_off[cls] + pos) * D + d0 + EPL * ci;
+                        if (p.bank_bf16) {
+                            uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(p.bank_rows) + at);
+                            dst[0] = narrow4(lo);
+                            if (EPL == 8 && rows_on > 4) dst[1] = narrow4(hi);
+                        } else {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.bank_rows) + at);
+                            dst[0] = lo;
+                            if (EPL == 8 && rows_on > 4) dst[1] = hi;
+                        }
                     }
                 }
             }
@@ -774,6 +793,9 @@ extern "C" int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher
     p.off_key = (const uint32_t*)(ws + L.off_key);
     p.plan = (const arco_plan*)(ws + L.plan);
     p.bank_rows = bank->rows;
+    p.bank_bf16 = bank->row_dtype == ARCO_BF16;
+    ARCO_REQUIRE(!p.bank_bf16 || (d.rep_dtype == ARCO_BF16 && d.feat % 8 == 0),
+                 "a bf16 bank needs a bf16 rep_teacher and D a multiple of 8");
     p.partials = (float*)(ws + L.partials);
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
     p.S = d.space; p.B = d.n_lab + d.n_unlab; p.C = d.classes; p.D = d.feat;

@@ -31,7 +31,8 @@ struct ProtoTcParams {
     const uint32_t* tile_flagged;
     const uint32_t* off_key;
     const arco_plan* plan;
-    float* bank_rows;
+    void* bank_rows;
+    int32_t bank_bf16;
     float* partials;
     int64_t row_off[ARCO_MAX_CLASSES];
     int32_t cap[ARCO_MAX_CLASSES];
@@ -236,10 +237,13 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
                         const uint32_t kp = e & 63u, kc = (e >> 6) & 31u, ko = e >> 11;
                         const uint32_t cap = (uint32_t)p.cap[kc];
                         const uint32_t pos = ((uint32_t)s_base[kc] + ko % cap) % cap;
-                        float* dst = p.bank_rows + (p.row_off[kc] + pos) * p.D;
-                        for (int d = at; d < p.D; d += 128)
-                            dst[d] = bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(
-                                stage + (d >> 7) * TC_BOX_BYTES + box_off((uint32_t)(d & 127), kp)));
+                        const int64_t row = (p.row_off[kc] + pos) * p.D;
+                        for (int d = at; d < p.D; d += 128) {
+                            const unsigned short bits = *reinterpret_cast<const unsigned short*>(
+                                stage + (d >> 7) * TC_BOX_BYTES + box_off((uint32_t)(d & 127), kp));
+                            if (p.bank_bf16) reinterpret_cast<unsigned short*>(p.bank_rows)[row + d] = bits;
+                            else reinterpret_cast<float*>(p.bank_rows)[row + d] = bf16_bits_to_float(bits);
+                        }
                     }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -331,6 +335,7 @@ int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank
     p.off_key = (const uint32_t*)(ws + L.off_key);
     p.plan = (const arco_plan*)(ws + L.plan);
     p.bank_rows = bank->rows;
+    p.bank_bf16 = bank->row_dtype == ARCO_BF16;
     p.partials = (float*)(ws + L.partials);
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
     p.S = d.space; p.B = d.n_lab + d.n_unlab; p.C = d.classes; p.D = d.feat;

@@ -229,10 +229,14 @@ def bench_inputs(name: str, device, seed: int = 1337, blocky: bool = False, n_la
 
 
 def bench_bank(spec: CaseSpec, seed: int = 1337):
-    """Banks pre-filled to capacity with N(0,1) rows (CPU lists, the trainers' layout)."""
+    """Banks pre-filled to capacity with N(0,1) rows (CPU lists, the trainers' layout).  With a bf16 representation
+    head every row a real run ever enqueues is a bf16 teacher row, so the steady-state bank is bf16-exact: the rows
+    are rounded to bf16 values (still handed over as fp32 tensors, as the trainers hold them)."""
     g = torch.Generator()
     g.manual_seed(seed)
     caps = spec.queue_sizes()
     memobank = [[torch.randn(caps[c], spec.feat, generator=g)] for c in range(spec.classes)]
+    if spec.dtype == "bf16":
+        memobank = [[m[0].to(torch.bfloat16).to(torch.float32)] for m in memobank]
     ptrs = [torch.zeros(1, dtype=torch.long) for _ in range(spec.classes)]
     return memobank, ptrs, caps

@@ -306,7 +306,7 @@ def main_ours(args):
                 "workload": args.workload, "batch_per_gpu": spec.batch, "labelled_per_gpu": spec.n_lab,
                 "classes": spec.classes, "spatial": list(spec.spatial), "feat": spec.feat, "rep_storage": spec.dtype,
                 "queries": spec.queries, "negatives": spec.negatives, "func": args.func,
-                "labels": "blocky16" if args.blocky else "iid", "banks": "pre-filled to capacity (50000/30000 rows)",
+                "labels": "blocky16" if args.blocky else "iid", "banks": "pre-filled to capacity (50000/30000 rows)" + (", bf16-exact rows in a bf16 ring" if spec.dtype == "bf16" else ", fp32 ring"),
                 "pixels_per_gpu": P, "parallelism": f"batch-shard x{world}, 1 all-reduce of C*(D+1) fp64" if world > 1 else "single GPU",
                 "l2": l2_note, "timing": "CUDA events per step on the launching stream, max over ranks",
             },
@@ -374,15 +374,16 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
     plan = _cabi.Plan.from_buffer_copy(ws[L.plan: L.plan + C.sizeof(_cabi.Plan)].cpu().numpy().tobytes())
     P = spec.pixels
     e_t = 2 if spec.dtype == "bf16" else 4
+    e_bank = 2 if bank.row_dtype == torch.bfloat16 else 4
     P_lv = sum(int(plan.lv_count[c]) for c in range(Cn))
     K = sum(min(int(plan.n_key[c]), caps[c]) for c in range(Cn))
     Cv = sum(1 for j in range(Cn) if plan.slot_active[j])
     alg = {
         "classify_count": P * (8 * Cn + 4 * Cn + 8) + P,
         "scan_plan": 2 * Cn * L.n_tiles * 8,
-        "proto_enqueue": P_lv * D * e_t + K * D * (e_t + 4) + P,
+        "proto_enqueue": P_lv * D * e_t + K * D * (e_t + e_bank) + P,
         "sample": Cv * (Q + Q * N) * 4,
-        "infonce": Cv * Q * D * e_t + Cv * Q * N * D * 4 + Cv * Q * D * 4,
+        "infonce": Cv * Q * D * e_t + Cv * Q * N * D * e_bank + Cv * Q * D * 4,
         "grad_scatter": P * D * e_t + Cv * Q * D * (4 + 2 * e_t),
     }
     peak, peak_src = peaks()
@@ -403,7 +404,7 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
     roof = {"kernel": kname + " + proto_finalize_kernel (<2% of the call)", "bound": "hbm",
             "achieved": stages[k]["gbs"], "peak": peak, "unit": "GB/s", "frac": stages[k]["frac_hbm"],
             "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg[k], "ms_per_launch": ms[k],
-            "bytes_formula": "P_lv*D*e_t + K*D*(e_t+4) + P  (SURVEY.md section 8(d) teacher-read and key terms + 1 code byte per pixel)",
+            "bytes_formula": "P_lv*D*e_t + K*D*(e_t+e_bank) + P  (SURVEY.md section 8(d) teacher-read and key terms + 1 code byte per pixel)",
             "note": "rep_teacher is channel-first, so every 32-byte sector that holds one low-valid pixel must be fetched: "
                     "with the iid 20% masks of this workload that is ALL of P*D*e_t; 'traffic' is the ncu-measured DRAM bytes"}
     return stages, roof

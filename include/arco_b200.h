@@ -107,12 +107,15 @@ typedef struct arco_plan {
 /* Device-resident ring-buffer memory bank (replaces the CPU list memobank[c] = [tensor[n,D]],
  * train_arco_2d.py:147-154).  Row r of class c lives at rows[(row_off[c] + (head[c]+r) % cap[c]) * D]. */
 typedef struct arco_bank {
-    float*   rows;                            /* [sum(cap), D] f32                    */
+    void*    rows;                            /* [sum(cap), D] f32, or bf16 when row_dtype == ARCO_BF16 (bf16 rep only:
+                                                 every enqueued key is then exactly representable)                   */
     int32_t* head;                            /* [C] device, updated by arco_scan_plan */
     int32_t* len;                             /* [C] device                            */
     int64_t* queue_ptr;                       /* [C] device                            */
     int32_t  cap[ARCO_MAX_CLASSES];           /* queue_size[c]                         */
     int64_t  row_off[ARCO_MAX_CLASSES];
+    int32_t  row_dtype;                       /* ARCO_F32 | ARCO_BF16                  */
+    int32_t  reserved;
 } arco_bank;
 
 ARCO_API const char* arco_version(void);

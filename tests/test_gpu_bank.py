@@ -75,3 +75,66 @@ def test_mismatched_bank_is_rejected():
     bad[2] = [torch.zeros(3, 7)]                                                 # wrong feature size
     with pytest.raises(ValueError, match="must be"):
         _step(spec, bad, ptr2, caps2)
+
+
+@pytest.mark.parametrize("feat,spatial", [(16, (16, 16)), (72, (32, 32)), (264, (32, 32))])
+def test_bf16_ring_is_value_identical_to_fp32_ring(feat, spatial, monkeypatch):
+    """A bf16 representation head with a bf16-exact bank is stored as a bf16 ring: the integer artefacts and the bank
+    rows (after eviction) are bit-identical to the fp32 ring fed the same sampler seed; loss and gradient agree to
+    fp32 summation-order noise (the 16-byte chunks hold 8 dims instead of 4, so the dot products associate
+    differently)."""
+    import arco_b200
+    spec = CaseSpec("bankbf", 2, 2, 5, spatial, feat, bank_init="fill:30", caps=[40, 36, 36, 36, 36], mask_frac=0.9,
+                    dtype="bf16", queries=32, negatives=24, seed=31)
+    dev = torch.device("cuda", 0)
+
+    def run(narrow):
+        monkeypatch.setenv("ARCO_BANK_BF16", "1" if narrow else "0")
+        bank, ptr, caps = make_bank(spec)
+        for b in bank:
+            b[0] = b[0].to(torch.bfloat16).to(torch.float32)
+        outs = []
+        for step in range(3):                                                    # third step wraps the rings
+            x = {k: v.to(dev) for k, v in exact_case(spec, step).items()}
+            rep = x["rep"].clone().requires_grad_(True)
+            nk, loss = arco_b200.compute_contra_memobank_loss(
+                rep, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"], bank, ptr,
+                caps, x["rep_teacher"], delta_n=spec.delta_n, func=spec.func, num_queries=spec.queries,
+                num_negatives=spec.negatives, seed=1234 + step)
+            loss.backward()
+            outs.append((list(nk), loss.detach().clone(), rep.grad.clone()))
+        assert bank[0].bank.row_dtype == (torch.bfloat16 if narrow else torch.float32)
+        return outs, [bank[c][0].clone() for c in range(spec.classes)], bank
+
+    a, rows_a, bank_a = run(True)
+    b, rows_b, _ = run(False)
+    for (nk_a, loss_a, g_a), (nk_b, loss_b, g_b) in zip(a, b):
+        assert nk_a == nk_b
+        assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * max(1.0, abs(float(loss_b)))
+        # grad_rep is bf16 and duplicate anchors (sampling with replacement) accumulate through bf16 atomics whose
+        # order is not fixed: allow a few bf16 ulps of the largest entry, like two runs of the same configuration
+        gmax = max(float(g_b.float().abs().max()), 1e-30)
+        assert torch.allclose(g_a.float(), g_b.float(), rtol=2.0 ** -6, atol=2.0 ** -7 * gmax)
+    assert sum(a[-1][0]) > 0
+    for ra, rb in zip(rows_a, rows_b):
+        assert ra.dtype == torch.float32 and torch.equal(ra, rb)
+    # assigning a row that bf16 cannot hold widens the ring; the other classes keep their values
+    odd = torch.full((2, feat), 1.0 + 2.0 ** -12)
+    bank_a[1][0] = odd
+    assert bank_a[0].bank.row_dtype == torch.float32
+    assert torch.equal(bank_a[1][0].cpu(), odd) and torch.equal(bank_a[2][0], rows_a[2])
+
+
+def test_bf16_ring_needs_exact_rows_and_bf16_rep():
+    import arco_b200
+    spec = CaseSpec("bankbf2", 2, 2, 4, (16, 16), 16, bank_init="fill:9", caps=[12, 12, 12, 12], dtype="bf16", seed=33)
+    bank, ptr, caps = make_bank(spec)
+    bank[3][0] = torch.full((1, 16), 1.0 + 2.0 ** -12)                           # not a bf16 value
+    _step(spec, bank, ptr, caps)
+    assert bank[0].bank.row_dtype == torch.float32
+    spec32 = CaseSpec("bankbf3", 2, 2, 4, (16, 16), 16, bank_init="fill:9", caps=[12, 12, 12, 12], seed=33)
+    bank, ptr, caps = make_bank(spec32)
+    for b in bank:
+        b[0] = b[0].to(torch.bfloat16).to(torch.float32)
+    _step(spec32, bank, ptr, caps)
+    assert bank[0].bank.row_dtype == torch.float32                               # fp32 keys are not bf16-exact
