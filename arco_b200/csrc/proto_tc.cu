@@ -93,7 +93,8 @@ __device__ __forceinline__ uint32_t box_off(uint32_t r, uint32_t kp) {
 }
 
 // A pipeline stage is one 64-pixel step with ALL feature blocks (NDB boxes of 128 rows x 128 B) plus its own one-hot
-// tile; the 128 aux threads build the tile and copy the keys of the step.  (Measured on B200: staging 128 rows x 256
+// tile; two builder warps (one thread per pixel) write the tile and the step's key list, two copier warps enqueue the
+// key rows from the staged boxes, so the builders run up to NST stages ahead of the loads.  (Measured on B200: staging 128 rows x 256
 // pixels per stage instead -- longer runs per row, fewer rows -- is 17 % slower, 0.434 vs 0.371 ms on the bf16
 // D=496 shape; spreading every stage over all D rows keeps all HBM channels busy.)
 __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant__ CUtensorMap tmap, ProtoTcParams p) {
@@ -102,11 +103,12 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
     const int NDB = p.NDB;
     const int stage_bytes = NDB * TC_BOX_BYTES + TC_B_BYTES;          // A boxes then the one-hot tile, 1024-aligned
     constexpr int NST = 3;
-    __shared__ __align__(8) uint64_t full_bar[NST], bfull_bar[NST], empty_bar[NST], done_bar;
+    __shared__ __align__(8) uint64_t full_bar[NST], bfull_bar[NST], kfull_bar[NST], empty_bar[NST], done_bar;
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t s_run[ARCO_MAX_CLASSES];
-    __shared__ uint32_t s_keys[TC_KPX];
-    __shared__ uint32_t s_nkeys;
+    __shared__ uint32_t s_keys[NST][TC_KPX];
+    __shared__ uint32_t s_nkeys[NST];
+    __shared__ __align__(16) uint8_t s_codes[ARCO_TILE];
     __shared__ int32_t s_skip[ARCO_MAX_CLASSES], s_base[ARCO_MAX_CLASSES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
     const int64_t S = p.S;
 
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { bar_init(&full_bar[s], 1); bar_init(&bfull_bar[s], 1); bar_init(&empty_bar[s], 2); }
+        for (int s = 0; s < NST; ++s) { bar_init(&full_bar[s], 1); bar_init(&bfull_bar[s], 1); bar_init(&kfull_bar[s], 1); bar_init(&empty_bar[s], 2); }
         bar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -179,66 +181,100 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
             }
             umma_commit(&done_bar);
         }
-    } else if (warp >= 4) {
+    } else if (warp == 4 || warp == 5) {
+        // ---- builders: one thread per pixel of the step; one-hot tile for the MMA, key list for the copiers ----
         const int at = tid - 128;
         uint32_t it = 0;
-        for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
-            const int b = t / p.tpi;
-            const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
+        int t = next_tile(blockIdx.x);
+        uint4 pre = make_uint4(0u, 0u, 0u, 0u);                  // this thread's 16 codes of the tile, fetched one tile ahead
+        auto fetch = [&](int tt) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (tt < p.NT) {
+                const int64_t s0 = (int64_t)(tt % p.tpi) * ARCO_TILE + 16 * at;
+                const uint8_t* src = p.codes + (int64_t)(tt / p.tpi) * S + s0;
+                if (s0 + 16 <= S && ((S & 15) == 0)) v = *reinterpret_cast<const uint4*>(src);
+                else {
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+                    for (int i = 0; i < 16; ++i)
+                        if (s0 + i < S) w[i >> 2] |= (uint32_t)src[i] << (8 * (i & 3));
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            return v;
+        };
+        pre = fetch(t);
+        for (; t < p.NT;) {
             const int ns = steps_in_tile(t);
+            asm volatile("bar.sync 1, 64;" ::: "memory");        // every builder is done with the previous tile's codes
+            reinterpret_cast<uint4*>(s_codes)[at] = pre;
             if (at < p.C) s_run[at] = p.off_key[(int64_t)at * (p.NT + 1) + t];
+            const int t_next = next_tile(t + ngrid);
+            pre = fetch(t_next);
+            asm volatile("bar.sync 1, 64;" ::: "memory");
             for (int st = 0; st < ns; ++st, ++it) {
                 const int s = it % NST;
                 const uint32_t ph = (it / NST) & 1;
-                unsigned char* stage = base + (size_t)s * stage_bytes;
-                unsigned char* btile = stage + NDB * TC_BOX_BYTES;
-                uint32_t code = 0;
-                const int64_t px = s_tile + (int64_t)st * TC_KPX + at;
-                if (at < TC_KPX && px < S) code = p.codes[(int64_t)b * S + px];
-                bar_wait(&empty_bar[s], ph ^ 1);                 // previous MMAs on this stage are done (also paces this role)
+                unsigned char* btile = base + (size_t)s * stage_bytes + NDB * TC_BOX_BYTES;
+                const uint32_t code = s_codes[st * TC_KPX + at];
+                bar_wait(&empty_bar[s], ph ^ 1);                 // MMAs and key copies of the stage's previous use are done
                 reinterpret_cast<uint4*>(btile)[at] = make_uint4(0u, 0u, 0u, 0u);
-                if (at == 0) s_nkeys = 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                reinterpret_cast<uint4*>(btile)[at + 64] = make_uint4(0u, 0u, 0u, 0u);
+                if (at == 0) s_nkeys[s] = 0;
+                asm volatile("bar.sync 1, 64;" ::: "memory");
                 if (code & CODE_LV) {
                     const uint32_t n = code & CODE_CLS_MASK;
                     *reinterpret_cast<unsigned short*>(btile + box_off(n, (uint32_t)at)) = 0x3F80;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 64;" ::: "memory");
                 if (at == 0) bar_arrive(&bfull_bar[s]);
+                // FIFO ordinal of every key pixel of the step (warp 4 owns pixels 0-31, warp 5 the next 32)
                 const bool is_key = code & CODE_KEY;
                 const uint32_t kcls = code & CODE_CLS_MASK;
                 uint32_t ord = 0;
-                if (warp == 4 || warp == 5) {
-                    const uint32_t peers = __match_any_sync(0xffffffffu, is_key ? kcls : 0xffffu);
-                    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-                    if (warp == 4) {
-                        if (is_key) ord = s_run[kcls] + rank;
-                        __syncwarp();
-                        if (is_key && rank == 0) s_run[kcls] += __popc(peers);
-                    }
-                    asm volatile("bar.sync 2, 64;" ::: "memory");
-                    if (warp == 5) {
-                        if (is_key) ord = s_run[kcls] + rank;
-                        __syncwarp();
-                        if (is_key && rank == 0) s_run[kcls] += __popc(peers);
-                    }
+                const uint32_t peers = __match_any_sync(0xffffffffu, is_key ? kcls : 0xffffu);
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                if (warp == 4) {
+                    if (is_key) ord = s_run[kcls] + rank;
+                    __syncwarp();
+                    if (is_key && rank == 0) s_run[kcls] += __popc(peers);
+                }
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+                if (warp == 5) {
+                    if (is_key) ord = s_run[kcls] + rank;
+                    __syncwarp();
+                    if (is_key && rank == 0) s_run[kcls] += __popc(peers);
                 }
                 if (is_key && ord >= (uint32_t)s_skip[kcls]) {
-                    const uint32_t slot = atomicAdd(&s_nkeys, 1u);
-                    s_keys[slot] = (ord << 11) | (kcls << 6) | (uint32_t)at;
+                    const uint32_t slot = atomicAdd(&s_nkeys[s], 1u);
+                    s_keys[s][slot] = (ord << 11) | (kcls << 6) | (uint32_t)at;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const uint32_t nkeys = s_nkeys;
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+                if (at == 0) bar_arrive(&kfull_bar[s]);
+            }
+            t = t_next;
+        }
+    } else if (warp >= 6) {
+        // ---- copiers: enqueue the step's key rows from the staged boxes into the ring ----
+        const int ct = tid - 192;
+        uint32_t it = 0;
+        for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
+            const int ns = steps_in_tile(t);
+            for (int st = 0; st < ns; ++st, ++it) {
+                const int s = it % NST;
+                const uint32_t ph = (it / NST) & 1;
+                const unsigned char* stage = base + (size_t)s * stage_bytes;
+                bar_wait(&kfull_bar[s], ph);
+                const uint32_t nkeys = s_nkeys[s];
                 if (nkeys) {
                     bar_wait(&full_bar[s], ph);
                     for (uint32_t k = 0; k < nkeys; ++k) {
-                        const uint32_t e = s_keys[k];
+                        const uint32_t e = s_keys[s][k];
                         const uint32_t kp = e & 63u, kc = (e >> 6) & 31u, ko = e >> 11;
                         const uint32_t cap = (uint32_t)p.cap[kc];
                         const uint32_t pos = ((uint32_t)s_base[kc] + ko % cap) % cap;
                         const int64_t row = (p.row_off[kc] + pos) * p.D;
-                        for (int d = at; d < p.D; d += 128) {
+                        for (int d = ct; d < p.D; d += 64) {
                             const unsigned short bits = *reinterpret_cast<const unsigned short*>(
                                 stage + (d >> 7) * TC_BOX_BYTES + box_off((uint32_t)(d & 127), kp));
                             if (p.bank_bf16) reinterpret_cast<unsigned short*>(p.bank_rows)[row + d] = bits;
@@ -246,8 +282,8 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (at == 0) bar_arrive(&empty_bar[s]);
+                asm volatile("bar.sync 2, 64;" ::: "memory");
+                if (ct == 0) bar_arrive(&empty_bar[s]);
             }
         }
     }
