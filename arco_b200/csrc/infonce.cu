@@ -98,6 +98,158 @@ __device__ __forceinline__ void unpack_chunk(const uint4& u, float* v) {
     }
 }
 
+struct AnchorInfo { int pix; float na, cos0; };
+
+// Anchor rank-select, anchor and prototype rows -> a_hat / k0hat (unit vectors in shared memory), |a| and cos(a, k0).
+// Called by all 128 threads of the CTA.
+__device__ __forceinline__ AnchorInfo info_prologue(const InfoParams& p, int j, int q, int bank_cls, float* a_hat,
+                                                    float* k0hat, float (*s_red)[2], int* s_pix) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = p.D;
+    const arco_plan* pl = p.plan;
+    // ---- anchor rank-select: idx-th anchor candidate of class j (... anchors by POSITION j) ----
+    if (warp == 0) {
+        const uint32_t n_anchor = pl->n_anchor[j];
+        uint32_t idx = (uint32_t)p.idx_a[(int64_t)j * p.Q + q];
+        if (idx >= n_anchor) idx = n_anchor - 1;
+        const uint32_t* off = p.off_anchor + (int64_t)j * (p.NT + 1);
+        // largest tile lo with off[lo] <= idx: 32 probes per round instead of a dependent load per halving
+        int lo = 0, hi = p.NT;
+        while (hi - lo > 1) {
+            const int step = (hi - lo + 31) >> 5;
+            const int pos = lo + lane * step;
+            const bool le = pos < hi && off[pos] <= idx;
+            const int k = __popc(__ballot_sync(0xffffffffu, le));         // >= 1: off[lo] <= idx holds throughout
+            lo += (k - 1) * step;
+            hi = min(hi, lo + step);
+        }
+        const uint32_t r = idx - off[lo];
+        const int b = lo / p.tpi;
+        const int64_t s0 = (int64_t)(lo % p.tpi) * ARCO_TILE;
+        const int64_t n = min((int64_t)ARCO_TILE, p.S - s0);
+        const uint8_t* cp = p.codes + (int64_t)b * p.S + s0;
+        const uint32_t want = CODE_ANCHOR | (uint32_t)j;
+        uint32_t mask = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const int i = lane * 32 + k;
+            const uint32_t cd = i < n ? cp[i] : 0u;
+            mask |= (uint32_t)((cd & (CODE_ANCHOR | CODE_CLS_MASK)) == want) << k;
+        }
+        const uint32_t cnt = __popc(mask);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t excl = incl - cnt;
+        if (r >= excl && r < incl) {
+            uint32_t m = mask;
+            for (uint32_t i = 0; i < r - excl; ++i) m &= m - 1;
+            *s_pix = (int)((int64_t)b * p.S + s0 + lane * 32 + (__ffs(m) - 1));
+        }
+    }
+    __syncthreads();
+    const int pix = *s_pix;
+    const int ab = (int)(pix / p.S);
+    const int64_t as = pix - (int64_t)ab * p.S;
+
+    // ---- anchor row (D strided loads, one 32-B sector each) and prototype row ----
+    float n2a = 0.f, n2k = 0.f;
+    const double cntj = p.proto_sums[(int64_t)j * (D + 1) + D];
+    for (int d = tid; d < D; d += 128) {
+        float v;
+        if (p.rep_dtype == ARCO_BF16)
+            v = bf16_bits_to_float(reinterpret_cast<const unsigned short*>(p.rep)[((int64_t)ab * D + d) * p.S + as]);
+        else
+            v = reinterpret_cast<const float*>(p.rep)[((int64_t)ab * D + d) * p.S + as];
+        float k = (float)(p.proto_sums[(int64_t)j * (D + 1) + d] / cntj);   // class mean (:380-384)
+        if (p.momentum) {
+            // positive = (1-a)*proto + a*momentum_prototype[valid_classes[i]][q]  (:490-495); prototype[...] = positive (:497)
+            const int64_t mo = ((int64_t)bank_cls * p.Q + q) * D + d;
+            if (*p.momentum_on) k = (1.f - p.ema_decay) * k + p.ema_decay * p.momentum[mo];
+            if (p.proto_out) p.proto_out[mo] = k;
+        }
+        a_hat[d] = v;
+        k0hat[d] = k;
+        n2a += v * v;
+        n2k += k * k;
+    }
+    n2a = warp_sum(n2a);
+    n2k = warp_sum(n2k);
+    if (lane == 0) { s_red[warp][0] = n2a; s_red[warp][1] = n2k; }
+    __syncthreads();
+    const float na = sqrtf(s_red[0][0] + s_red[1][0] + s_red[2][0] + s_red[3][0]);
+    const float nk0 = sqrtf(s_red[0][1] + s_red[1][1] + s_red[2][1] + s_red[3][1]);
+    const float inv_na = 1.f / fmaxf(na, kEps), inv_nk0 = 1.f / fmaxf(nk0, kEps);
+    float c0 = 0.f;
+    for (int d = tid; d < D; d += 128) {
+        const float a = a_hat[d] * inv_na, k = k0hat[d] * inv_nk0;
+        a_hat[d] = a;
+        k0hat[d] = k;
+        c0 += a * k;
+    }
+    c0 = warp_sum(c0);
+    __syncthreads();                       // everyone is done reading s_red
+    if (lane == 0) s_red[warp][0] = c0;
+    __syncthreads();
+    AnchorInfo out;
+    out.pix = pix;
+    out.na = na;
+    out.cos0 = s_red[0][0] + s_red[1][0] + s_red[2][0] + s_red[3][0];
+    return out;
+}
+
+// d loss / d anchor and the per-query loss from the merged softmax statistics.  gsum(d) = sum_k e_k k_hat_k[d] over the
+// negatives, S_all / S2_all include the positive key's e0 and e0*cos0, m_all is the offset the exponentials were taken at.
+template <typename GSum>
+__device__ __forceinline__ void info_epilogue(const InfoParams& p, int bid, int j, int q, const AnchorInfo& ai, float inv_scale,
+                                              float e0, float m_all, float S_all, float S2_all, const float* a_hat,
+                                              const float* k0hat, GSum gsum) {
+    const int tid = threadIdx.x, D = p.D;
+    const float inv_temp = 1.f / p.temp;
+    const float z0 = ai.cos0 * inv_temp;
+    const float inv_S = 1.f / S_all;
+    const float sdot = (S2_all * inv_S - ai.cos0) * inv_temp;
+    for (int d = tid; d < D; d += 128) {
+        const float g = gsum(d) + e0 * k0hat[d];
+        const float gw = (g * inv_S - k0hat[d]) * inv_temp;
+        const float grad = (ai.na > kEps) ? (gw - sdot * a_hat[d]) / ai.na : gw / kEps;
+        p.g_anchor[(int64_t)bid * D + d] = grad * inv_scale;
+    }
+    if (tid == 0) {
+        p.loss_parts[bid] = (__logf(S_all) + m_all - z0) * inv_scale;
+        p.anchor_pix[bid] = ai.pix;
+        if (p.logits) p.logits[((int64_t)j * p.Q + q) * (1 + p.N)] = ai.cos0;
+    }
+}
+
+// last CTA folds the per-query losses in a fixed order (deterministic); called by all 128 threads
+__device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
+    __shared__ bool s_last;
+    __shared__ float s_fold[128];
+    const int tid = threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&p.plan->loss_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile float* lp = p.loss_parts;
+    const int total = gridDim.x;
+    float acc = 0.f;
+    const int per = (total + 127) / 128;
+    for (int i = tid * per; i < min(total, (tid + 1) * per); ++i) acc += lp[i];
+    s_fold[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 128; ++i) s += s_fold[i];
+        p.loss[0] = s;
+    }
+}
+
 // MAXIT: 16-byte chunks per lane in pass 2 (ceil(chunks per row / 32)); BF16BANK: the ring stores bf16 rows
 template <int MAXIT, bool BF16BANK>
 __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
@@ -112,7 +264,6 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
     __shared__ float s_red[4][2];
     __shared__ float s_stats[4][3];
     __shared__ int s_pix;
-    __shared__ bool s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bid = blockIdx.x;
@@ -133,89 +284,9 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         if (tid < 4) mbar_init(&bars[tid], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
-        // ---- anchor rank-select: idx-th anchor candidate of class j (... anchors by POSITION j) ----
-        if (warp == 0) {
-            const uint32_t n_anchor = pl->n_anchor[j];
-            uint32_t idx = (uint32_t)p.idx_a[(int64_t)j * p.Q + q];
-            if (idx >= n_anchor) idx = n_anchor - 1;
-            const uint32_t* off = p.off_anchor + (int64_t)j * (p.NT + 1);
-            int lo = 0, hi = p.NT;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (off[mid] <= idx) lo = mid; else hi = mid;
-            }
-            const uint32_t r = idx - off[lo];
-            const int b = lo / p.tpi;
-            const int64_t s0 = (int64_t)(lo % p.tpi) * ARCO_TILE;
-            const int64_t n = min((int64_t)ARCO_TILE, p.S - s0);
-            const uint8_t* cp = p.codes + (int64_t)b * p.S + s0;
-            const uint32_t want = CODE_ANCHOR | (uint32_t)j;
-            uint32_t mask = 0;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                const int i = lane * 32 + k;
-                const uint32_t cd = i < n ? cp[i] : 0u;
-                mask |= (uint32_t)((cd & (CODE_ANCHOR | CODE_CLS_MASK)) == want) << k;
-            }
-            const uint32_t cnt = __popc(mask);
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
-            }
-            const uint32_t excl = incl - cnt;
-            if (r >= excl && r < incl) {
-                uint32_t m = mask;
-                for (uint32_t i = 0; i < r - excl; ++i) m &= m - 1;
-                s_pix = (int)((int64_t)b * p.S + s0 + lane * 32 + (__ffs(m) - 1));
-            }
-        }
-        __syncthreads();
-        const int pix = s_pix;
-        const int ab = (int)(pix / p.S);
-        const int64_t as = pix - (int64_t)ab * p.S;
-
-        // ---- anchor row (D strided loads, one 32-B sector each) and prototype row ----
-        float n2a = 0.f, n2k = 0.f;
-        const double cntj = p.proto_sums[(int64_t)j * (D + 1) + D];
-        for (int d = tid; d < D; d += 128) {
-            float v;
-            if (p.rep_dtype == ARCO_BF16)
-                v = bf16_bits_to_float(reinterpret_cast<const unsigned short*>(p.rep)[((int64_t)ab * D + d) * p.S + as]);
-            else
-                v = reinterpret_cast<const float*>(p.rep)[((int64_t)ab * D + d) * p.S + as];
-            float k = (float)(p.proto_sums[(int64_t)j * (D + 1) + d] / cntj);   // class mean (:380-384)
-            if (p.momentum) {
-                // positive = (1-a)*proto + a*momentum_prototype[valid_classes[i]][q]  (:490-495); prototype[...] = positive (:497)
-                const int64_t mo = ((int64_t)bank_cls * p.Q + q) * D + d;
-                if (*p.momentum_on) k = (1.f - p.ema_decay) * k + p.ema_decay * p.momentum[mo];
-                if (p.proto_out) p.proto_out[mo] = k;
-            }
-            a_hat[d] = v;
-            k0hat[d] = k;
-            n2a += v * v;
-            n2k += k * k;
-        }
-        n2a = warp_sum(n2a);
-        n2k = warp_sum(n2k);
-        if (lane == 0) { s_red[warp][0] = n2a; s_red[warp][1] = n2k; }
-        __syncthreads();
-        const float na = sqrtf(s_red[0][0] + s_red[1][0] + s_red[2][0] + s_red[3][0]);
-        const float nk0 = sqrtf(s_red[0][1] + s_red[1][1] + s_red[2][1] + s_red[3][1]);
-        const float inv_na = 1.f / fmaxf(na, kEps), inv_nk0 = 1.f / fmaxf(nk0, kEps);
-        float c0 = 0.f;
-        for (int d = tid; d < D; d += 128) {
-            const float a = a_hat[d] * inv_na, k = k0hat[d] * inv_nk0;
-            a_hat[d] = a;
-            k0hat[d] = k;
-            c0 += a * k;
-        }
-        c0 = warp_sum(c0);
-        __syncthreads();                       // everyone is done reading s_red
-        if (lane == 0) s_red[warp][0] = c0;
-        __syncthreads();
-        const float cos0 = s_red[0][0] + s_red[1][0] + s_red[2][0] + s_red[3][0];
+        const AnchorInfo ai = info_prologue(p, j, q, bank_cls, a_hat, k0hat, s_red, &s_pix);
+        const int pix = ai.pix;
+        const float na = ai.na, cos0 = ai.cos0;
         const float inv_temp = 1.f / p.temp;
         const float z0 = cos0 * inv_temp;
 
@@ -351,45 +422,250 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
             S_all += s_stats[w][1] * f[w];
             S2_all += s_stats[w][2] * f[w];
         }
-        const float inv_S = 1.f / S_all;
-        const float sdot = (S2_all * inv_S - cos0) * inv_temp;
-        for (int d = tid; d < D; d += 128) {
-            const float g = gbuf[d] * f[0] + gbuf[D + d] * f[1] + gbuf[2 * D + d] * f[2] + gbuf[3 * D + d] * f[3] +
-                            e0 * k0hat[d];
-            const float gw = (g * inv_S - k0hat[d]) * inv_temp;
-            const float grad = (na > kEps) ? (gw - sdot * a_hat[d]) / na : gw / kEps;
-            p.g_anchor[(int64_t)bid * D + d] = grad * inv_scale;
-        }
-        if (tid == 0) {
-            p.loss_parts[bid] = (__logf(S_all) + m_all - z0) * inv_scale;
-            p.anchor_pix[bid] = pix;
-            if (p.logits) p.logits[((int64_t)j * p.Q + q) * (1 + p.N)] = cos0;
-        }
+        info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, S_all, S2_all, a_hat, k0hat, [&](int d) {
+            return gbuf[d] * f[0] + gbuf[D + d] * f[1] + gbuf[2 * D + d] * f[2] + gbuf[3 * D + d] * f[3];
+        });
     } else if (tid == 0) {
         p.loss_parts[bid] = 0.f;
         p.anchor_pix[bid] = -1;
     }
 
-    // ---- last CTA folds the per-query losses in a fixed order (deterministic) ----
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&pl->loss_done, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const volatile float* lp = p.loss_parts;
-    const int total = gridDim.x;
-    float acc = 0.f;
-    const int per = (total + 127) / 128;
-    for (int i = tid * per; i < min(total, (tid + 1) * per); ++i) acc += lp[i];
-    __shared__ float s_fold[128];
-    s_fold[tid] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        float s = 0.f;
-        for (int i = 0; i < 128; ++i) s += s_fold[i];
-        p.loss[0] = s;
+    info_fold_loss(p);
+}
+
+
+// ======================================================================================================================
+// bf16 ring: the same InfoNCE on the legacy tensor-core path (mma.sync m16n8k16, bf16 x bf16 -> fp32).
+//
+// The gathered rows cannot be a tcgen05 operand (a UMMA descriptor wants 8-row core matrices at a fixed stride, the
+// gather delivers one row per bank position), ldmatrix takes one address per row.  Per query the work is a
+// matrix-VECTOR product, so the vector operand is widened to use the 8/16-wide MMA dimension exactly:
+//   pass 1  C[16 x 8 keys] += A[16 x 16 dims] . B[16 dims x 8 keys]     A rows 0-7 = the same 8 keys (diagonal of the
+//           top block = |k|^2), rows 8-10 = a_hat split into three bf16 terms (hi + mid + lo carry all 24 mantissa bits;
+//           the products are exact and the accumulation is fp32, so the dot equals the FFMA path's up to summation order)
+//   pass 2  G[16 dims x 8] += K^T[16 dims x 16 keys] . W[16 keys x 8]  W columns 0-2 = the softmax weights e_k/|k| split
+//           the same way; the three useful columns are added at the end.
+// cos <= 1, so the exponentials are taken at the fixed offset 1/temp: no running maximum, no rescaling of G.
+// The CTA works on 16-key chunks staged by TMA bulk copies in NSTG shared buffers; each warp owns a quarter of the
+// feature dimension in BOTH passes (partial dots are added through shared memory), which keeps 32 accumulator registers
+// per thread instead of D/4.
+// ======================================================================================================================
+constexpr int MMA_KEYS = 16;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// term `part` (0 hi, 1 mid, 2 lo) of the three-way bf16 split of x, as bf16 bits
+__device__ __forceinline__ uint32_t bf16_term(float x, int part) {
+    const float hi = __bfloat162float(__float2bfloat16_rn(x));
+    if (part == 0) return __float_as_uint(hi) >> 16;
+    const float r1 = x - hi;
+    const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+    if (part == 1) return __float_as_uint(mid) >> 16;
+    return __float_as_uint(__bfloat162float(__float2bfloat16_rn(r1 - mid))) >> 16;
+}
+
+template <int NSTG>
+__global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(InfoParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int D = p.D;
+    const int KS = (D + 15) >> 4;                                 // 16-dim steps (pass 1 k-steps == pass 2 m-tiles)
+    const int RS16 = p.RS16;                                      // odd, and RS16*8 >= KS*16: the pad stays zero
+    float* a_hat = reinterpret_cast<float*>(smem_raw);            // [D]
+    float* k0hat = a_hat + D;                                     // [D]
+    uint2* asf = reinterpret_cast<uint2*>(k0hat + D);             // [KS][12]  A-fragment rows 8-10 (a_hat terms)
+    float* s_part = reinterpret_cast<float*>(asf + KS * 12);      // [2][4][16][2]  per-warp partial (dot, |k|^2)
+    uint4* stage = reinterpret_cast<uint4*>(s_part + 2 * 4 * MMA_KEYS * 2);   // [NSTG][16 * RS16]; G after the loop
+    __shared__ __align__(8) uint64_t bars[NSTG];
+    __shared__ float s_red[4][2];
+    __shared__ int s_pix;
+    __shared__ uint32_t s_done;                                   // warps finished with the current chunk's stage
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int bid = blockIdx.x;
+    const int j = bid / p.Q, q = bid % p.Q;
+    arco_plan* pl = p.plan;
+    const bool active = pl->slot_active[j] != 0;
+
+    if (active) {
+        const int bank_cls = pl->valid_class[j];
+        const int blen = pl->bank_len[bank_cls];
+        const int bhead = pl->bank_head[bank_cls];
+        const int cap = p.cap[bank_cls];
+        const uint32_t row_bytes = (uint32_t)D * 2u;
+        const unsigned char* bank = reinterpret_cast<const unsigned char*>(p.bank_rows) + p.row_off[bank_cls] * (int64_t)row_bytes;
+        const float inv_scale = pl->inv_scale;
+        const int stage_u4 = MMA_KEYS * RS16;
+
+        if (tid < NSTG) mbar_init(&bars[tid], 1);
+        if (tid == 0) s_done = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // zero the stages once: row pads and the unused rows of a short last chunk must read as finite values
+        for (int i = tid; i < NSTG * stage_u4; i += 128) stage[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+
+        const int nch = (p.N + MMA_KEYS - 1) / MMA_KEYS;
+        const int32_t* my_idx = p.idx_n + ((int64_t)j * p.Q + q) * p.N;
+        auto load_idx = [&](int chunk) {                          // ring row of key `lane` of the chunk (lanes 0-15)
+            const int n = chunk * MMA_KEYS + lane;
+            return (lane < MMA_KEYS && n < p.N) ? my_idx[n] : -1;
+        };
+        auto issue = [&](int chunk, int r) {                      // one whole warp
+            const int s = chunk % NSTG;
+            const int nv = min(MMA_KEYS, p.N - chunk * MMA_KEYS);
+            if (lane == 0) mbar_expect_tx(&bars[s], (uint32_t)nv * row_bytes);
+            __syncwarp();
+            if (lane < nv) {
+                r = min(max(r, 0), blen - 1);
+                int phys = bhead + r;
+                if (phys >= cap) phys -= cap;
+                bulk_g2s(stage + (size_t)s * stage_u4 + (size_t)lane * RS16, bank + (int64_t)phys * row_bytes, row_bytes, &bars[s]);
+            }
+        };
+        // the first gathers do not depend on the anchor: they fly while the prologue chases its pointers
+        if (warp == 0)
+            for (int c = 0; c < NSTG && c < nch; ++c) issue(c, load_idx(c));
+        int r_next = load_idx(NSTG);                              // every warp: any of them may issue the next chunk
+
+        const AnchorInfo ai = info_prologue(p, j, q, bank_cls, a_hat, k0hat, s_red, &s_pix);
+        const float inv_temp = 1.f / p.temp;
+        const float z0 = ai.cos0 * inv_temp;
+        // A-fragment rows 8..10 of every k-step: lane (g < 3, t) holds terms g of a_hat[16ks + 2t, +1] and [.. + 8, + 9]
+        for (int i = tid; i < KS * 12; i += 128) {
+            const int ks = i / 12, gg = (i % 12) >> 2, tt = i & 3;
+            const int d0 = 16 * ks + 2 * tt;
+            auto av = [&](int d) { return d < D ? a_hat[d] : 0.f; };
+            asf[i] = make_uint2(bf16_term(av(d0), gg) | (bf16_term(av(d0 + 1), gg) << 16),
+                                bf16_term(av(d0 + 8), gg) | (bf16_term(av(d0 + 9), gg) << 16));
+        }
+        __syncthreads();
+
+        const int ks_begin = (KS * warp) >> 2;                    // this warp's slice of D, both passes
+        const int nks = ((KS * (warp + 1)) >> 2) - ks_begin;      // <= 8
+        // ldmatrix lane address inside a stage: matrix i = lane >> 3 -> keys (i >> 1) * 8 + (lane & 7), dims + (i & 1) * 8
+        const uint32_t lm_base = smem_u32(stage) +
+                                 (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * RS16 + ((lane >> 3) & 1) + 2 * ks_begin) * 16u;
+        const uint2* af_ptr = asf + ks_begin * 12 + (g < 3 ? g * 4 + t : 0);
+        float acc[8][4];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+        float S_lane = 0.f, S2_lane = 0.f;
+        const int key = lane & 15;
+
+        for (int c = 0; c < nch; ++c) {
+            const int s = c % NSTG;
+            mbar_wait(&bars[s], (uint32_t)((c / NSTG) & 1));
+            const uint32_t sbase = lm_base + (uint32_t)(s * stage_u4) * 16u;
+            // ---- pass 1: partial dots / squared norms of the 16 keys over this warp's dims ----
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                if (m < nks) {
+                    uint32_t r[4];
+                    ldsm_x4(r, sbase + (uint32_t)m * 32u);
+                    uint2 af = af_ptr[m * 12];
+                    if (g >= 3) af = make_uint2(0u, 0u);
+                    mma_bf16_16816(c0, r[0], af.x, r[1], af.y, r[0], r[1]);
+                    mma_bf16_16816(c1, r[2], af.x, r[3], af.y, r[2], r[3]);
+                }
+            }
+            // rows 8..10 (c[2], c[3]) summed over g; the diagonal of rows 0..7 sits in lane 4n + n/2
+#pragma unroll
+            for (int o = 4; o <= 8; o <<= 1) {
+                c0[2] += __shfl_xor_sync(0xffffffffu, c0[2], o); c0[3] += __shfl_xor_sync(0xffffffffu, c0[3], o);
+                c1[2] += __shfl_xor_sync(0xffffffffu, c1[2], o); c1[3] += __shfl_xor_sync(0xffffffffu, c1[3], o);
+            }
+            float* part = s_part + ((c & 1) * 4 + warp) * (MMA_KEYS * 2);
+            if (g == 0) {                                         // lane t: dots of keys 2t, 2t+1 (tile 0) and 8+2t, 9+2t (tile 1)
+                part[4 * t] = c0[2]; part[4 * t + 2] = c0[3];
+                part[16 + 4 * t] = c1[2]; part[16 + 4 * t + 2] = c1[3];
+            }
+            if (t == (g >> 1)) {                                  // |k|^2 of key g (tile 0) and key 8+g (tile 1)
+                part[g * 2 + 1] = (g & 1) ? c0[1] : c0[0];
+                part[(8 + g) * 2 + 1] = (g & 1) ? c1[1] : c1[0];
+            }
+            __syncthreads();
+            // ---- softmax weights of the 16 keys (every warp computes all of them; lanes 16-31 mirror 0-15) ----
+            const float2* pr = reinterpret_cast<const float2*>(s_part + (c & 1) * 4 * (MMA_KEYS * 2)) + key;
+            const float2 p0 = pr[0], p1 = pr[MMA_KEYS], p2 = pr[2 * MMA_KEYS], p3 = pr[3 * MMA_KEYS];
+            const float dot = (p0.x + p1.x) + (p2.x + p3.x);
+            const float n2 = (p0.y + p1.y) + (p2.y + p3.y);
+            const bool valid = c * MMA_KEYS + key < p.N;
+            const float inv_nk = 1.f / fmaxf(sqrtf(n2), kEps);
+            const float cosv = dot * inv_nk;
+            const float e = valid ? __expf((cosv - 1.f) * inv_temp) : 0.f;
+            const float coef = e * inv_nk;
+            if (warp == 0 && lane < MMA_KEYS) {
+                S_lane += e;
+                S2_lane += e * cosv;
+                if (p.logits && valid) p.logits[((int64_t)j * p.Q + q) * (1 + p.N) + 1 + c * MMA_KEYS + key] = cosv;
+            }
+            // B fragment of pass 2: column g (< 3) = term g of the weights of keys (2t, 2t+1) and (2t+8, 2t+9)
+            const float w0 = __shfl_sync(0xffffffffu, coef, 2 * t), w1 = __shfl_sync(0xffffffffu, coef, 2 * t + 1);
+            const float w2 = __shfl_sync(0xffffffffu, coef, 2 * t + 8), w3 = __shfl_sync(0xffffffffu, coef, 2 * t + 9);
+            uint32_t b0 = 0u, b1 = 0u;
+            if (g < 3) {
+                b0 = bf16_term(w0, g) | (bf16_term(w1, g) << 16);
+                b1 = bf16_term(w2, g) | (bf16_term(w3, g) << 16);
+            }
+            // ---- pass 2: G[dims of this warp] += K^T . W ----
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                if (m < nks) {
+                    uint32_t r[4];
+                    ldsm_x4_trans(r, sbase + (uint32_t)m * 32u);
+                    mma_bf16_16816(acc[m], r[0], r[1], r[2], r[3], b0, b1);
+                }
+            }
+            // ---- the last warp to leave the stage refills it with chunk c + NSTG (nobody waits for anybody) ----
+            __syncwarp();
+            uint32_t prev = 0;
+            if (lane == 0) { __threadfence_block(); prev = atomicAdd(&s_done, 1u); }
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev == 3u) {
+                if (lane == 0) s_done = 0;
+                if (c + NSTG < nch) issue(c + NSTG, r_next);
+            }
+            r_next = load_idx(c + NSTG + 1);
+        }
+        __syncthreads();                                          // every warp is done with the stages: reuse as G
+        float* gbuf = reinterpret_cast<float*>(stage);
+        // columns 0..2 of every accumulator tile -> G
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int mt = ks_begin + m;
+            float lo = acc[m][0] + acc[m][1], hi = acc[m][2] + acc[m][3];
+            lo += __shfl_xor_sync(0xffffffffu, lo, 1); lo += __shfl_xor_sync(0xffffffffu, lo, 2);
+            hi += __shfl_xor_sync(0xffffffffu, hi, 1); hi += __shfl_xor_sync(0xffffffffu, hi, 2);
+            if (m < nks && t == 0) { gbuf[16 * mt + g] = lo; gbuf[16 * mt + 8 + g] = hi; }
+        }
+        if (warp == 0) {
+            const float S = warp_sum(S_lane), S2 = warp_sum(S2_lane);
+            if (lane == 0) { s_red[0][0] = S; s_red[0][1] = S2; }
+        }
+        __syncthreads();
+        const float m_all = inv_temp;                             // offset of every exponential: z <= 1/temp
+        const float e0 = __expf(z0 - m_all);
+        info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, e0 + s_red[0][0], e0 * ai.cos0 + s_red[0][1], a_hat, k0hat,
+                      [&](int d) { return gbuf[d]; });
+    } else if (tid == 0) {
+        p.loss_parts[bid] = 0.f;
+        p.anchor_pix[bid] = -1;
     }
+    info_fold_loss(p);
 }
 
 }  // namespace arco
@@ -440,7 +716,25 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
         ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_kernel<MI, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         arco::infonce_kernel<MI, BF><<<grid, 128, smem, st>>>(p);                                                           \
     } while (0)
-    if (bf16bank) {
+    static const int mma_env = [] { const char* e = getenv("ARCO_INFONCE_MMA"); return e ? atoi(e) : 1; }();   // 0 = off, else stages (1 | 2)
+    if (bf16bank && mma_env > 0 && temp >= 0.03f) {
+        // tensor-core path (fixed softmax offset 1/temp needs exp(-2/temp) to stay a normal float)
+        const int nstg = mma_env >= 2 ? 2 : 1;
+        const int ks = (d.feat + 15) / 16;
+        int r16 = 2 * ks;                                               // >= 16*ks dims
+        if ((r16 & 1) == 0) ++r16;                                      // odd stride: ldmatrix rows hit distinct banks
+        p.RS16 = r16; p.KC = arco::MMA_KEYS;
+        size_t stage_bytes = (size_t)nstg * arco::MMA_KEYS * r16 * 16;
+        if (stage_bytes < (size_t)ks * 64) stage_bytes = (size_t)ks * 64;   // G[16*ks] lives there after the loop
+        const size_t sm = (size_t)2 * d.feat * 4 + (size_t)ks * 12 * 8 + 2 * 4 * arco::MMA_KEYS * 2 * 4 + stage_bytes;
+        if (nstg == 1) {
+            ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            arco::infonce_mma_kernel<1><<<grid, 128, sm, st>>>(p);
+        } else {
+            ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            arco::infonce_mma_kernel<2><<<grid, 128, sm, st>>>(p);
+        }
+    } else if (bf16bank) {
         if (cpl <= 32) ARCO_INFONCE(1, true); else ARCO_INFONCE(2, true);
     } else {
         if (cpl <= 32) ARCO_INFONCE(1, false); else if (cpl <= 64) ARCO_INFONCE(2, false); else ARCO_INFONCE(4, false);

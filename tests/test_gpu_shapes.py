@@ -42,6 +42,12 @@ def test_shape(spec, index_labels):
     dev = torch.device("cuda", 0)
     bank_g, ptr_g, caps = make_bank(spec)
     bank_c, ptr_c, _ = make_bank(spec)
+    if spec.dtype == "bf16":
+        # a bf16 run only ever enqueues bf16 teacher rows: bf16-exact banks are stored as a bf16 ring and take the
+        # tensor-core InfoNCE path (the fp32 ring under a bf16 head is covered by the golden bf16_rep case)
+        for bank in (bank_g, bank_c):
+            for m in bank:
+                m[0] = m[0].to(torch.bfloat16).to(torch.float32)
     Q, N = spec.queries, spec.negatives
     for step in range(spec.steps):
         x = exact_case(spec, step)
@@ -82,7 +88,9 @@ def test_shape(spec, index_labels):
             assert _rel(proto_g[ok], res.proto[ok]) <= 2e-5
         tol = 2e-2 if spec.dtype == "bf16" else 1e-5
         lo = float(res.loss.detach())
-        assert abs(float(loss.detach()) - lo) <= tol * max(1.0, abs(lo))
+        assert abs(float(loss.detach()) - lo) <= min(tol, 1e-4) * max(1.0, abs(lo))     # the loss itself is fp32 either way
+        if spec.dtype == "bf16" and spec.feat % 8 == 0:
+            assert bank_g[0].bank.row_dtype == torch.bfloat16
         if float(rep_c.grad.abs().max()) > 0:
             assert _rel(rep_g.grad.float(), rep_c.grad) <= tol
         else:
