@@ -92,6 +92,18 @@ __device__ __forceinline__ uint32_t box_off(uint32_t r, uint32_t kp) {
     return (r >> 3) * 1024 + (r & 7) * 128 + (((kp >> 3) ^ (r & 7)) << 4) + ((kp & 7) << 1);
 }
 
+#ifdef ARCO_TC_TRACE
+// debug build only: per-role clock64 stamps of CTA 0's first 256 steps (read back with arco_debug_tc_trace)
+__device__ long long g_tc_trace[8][256];
+__device__ unsigned long long g_tc_cta[4][160];        // globaltimer ns per CTA: entry, first full, last commit seen, exit
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TC_CTA(k) do { if (blockIdx.x < 160) g_tc_cta[k][blockIdx.x] = gtime(); } while (0)
+#define TC_STAMP(role, it) do { if (blockIdx.x == 0 && (it) < 256) g_tc_trace[role][it] = clock64(); } while (0)
+#else
+#define TC_STAMP(role, it) do { } while (0)
+#define TC_CTA(k) do { } while (0)
+#endif
+
 // A pipeline stage is one 64-pixel step with ALL feature blocks (NDB boxes of 128 rows x 128 B) plus its own one-hot
 // tile; two builder warps (one thread per pixel) write the tile and the step's key list, two copier warps enqueue the
 // key rows from the staged boxes, so the builders run up to NST stages ahead of the loads.  (Measured on B200: staging 128 rows x 256
@@ -113,6 +125,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ngrid = gridDim.x;
+    if (tid == 0) TC_CTA(0);
     const int64_t S = p.S;
 
     if (tid == 0) {
@@ -150,6 +163,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
                 for (int st = 0; st < ns; ++st, ++it) {
                     const int s = it % NST;
                     bar_wait(&empty_bar[s], ((it / NST) & 1) ^ 1);
+                    TC_STAMP(0, it);
                     bar_expect_tx(&full_bar[s], (uint32_t)NDB * TC_BOX_BYTES);
                     unsigned char* dst = base + (size_t)s * stage_bytes;
                     for (int db = 0; db < NDB; ++db)
@@ -166,7 +180,10 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
                     const int s = it % NST;
                     const uint32_t ph = (it / NST) & 1;
                     bar_wait(&full_bar[s], ph);
+                    TC_STAMP(1, it);
+                    if (it == 0) TC_CTA(1);
                     bar_wait(&bfull_bar[s], ph);
+                    TC_STAMP(2, it);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a0 = s32(base + (size_t)s * stage_bytes);
                     const uint32_t b0 = a0 + NDB * TC_BOX_BYTES;
@@ -177,6 +194,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
                                       kIdesc, (it > 0 || kk > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);
+                    TC_STAMP(3, it);
                 }
             }
             umma_commit(&done_bar);
@@ -217,6 +235,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
                 unsigned char* btile = base + (size_t)s * stage_bytes + NDB * TC_BOX_BYTES;
                 const uint32_t code = s_codes[st * TC_KPX + at];
                 bar_wait(&empty_bar[s], ph ^ 1);                 // MMAs and key copies of the stage's previous use are done
+                if (at == 0) TC_STAMP(4, it);
                 reinterpret_cast<uint4*>(btile)[at] = make_uint4(0u, 0u, 0u, 0u);
                 reinterpret_cast<uint4*>(btile)[at + 64] = make_uint4(0u, 0u, 0u, 0u);
                 if (at == 0) s_nkeys[s] = 0;
@@ -245,45 +264,57 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
                     __syncwarp();
                     if (is_key && rank == 0) s_run[kcls] += __popc(peers);
                 }
-                if (is_key && ord >= (uint32_t)s_skip[kcls]) {
+                if (is_key && ord >= (uint32_t)s_skip[kcls]) {                // not evicted within this very call
+                    const uint32_t cap = (uint32_t)p.cap[kcls];
+                    const uint32_t pos = ((uint32_t)s_base[kcls] + ord % cap) % cap;
                     const uint32_t slot = atomicAdd(&s_nkeys[s], 1u);
-                    s_keys[s][slot] = (ord << 11) | (kcls << 6) | (uint32_t)at;
+                    s_keys[s][slot] = (((uint32_t)p.row_off[kcls] + pos) << 6) | (uint32_t)at;   // ring row | pixel
                 }
                 asm volatile("bar.sync 1, 64;" ::: "memory");
-                if (at == 0) bar_arrive(&kfull_bar[s]);
+                if (at == 0) { bar_arrive(&kfull_bar[s]); TC_STAMP(5, it); }
             }
             t = t_next;
         }
-    } else if (warp >= 6) {
-        // ---- copiers: enqueue the step's key rows from the staged boxes into the ring ----
-        const int ct = tid - 192;
+    } else if (warp == 2 || warp == 3 || warp >= 6) {
+        // ---- copiers (4 warps; warps 2-3 go on to the epilogue): enqueue the step's key rows from the staged boxes.
+        // Thread ct owns feature rows ct, ct+128, ...: inside a box that is a fixed (row, swizzle phase), so a key costs
+        // one address, NDB shared loads at +box stride and NDB coalesced 2-byte stores per thread.
+        const int ct = (warp < 4 ? (warp - 2) * 32 : 64 + (warp - 6) * 32) + lane;
+        const uint32_t t_off = (uint32_t)(ct >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
         uint32_t it = 0;
         for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
             const int ns = steps_in_tile(t);
             for (int st = 0; st < ns; ++st, ++it) {
                 const int s = it % NST;
                 const uint32_t ph = (it / NST) & 1;
-                const unsigned char* stage = base + (size_t)s * stage_bytes;
+                const uint32_t stage_a = s32(base + (size_t)s * stage_bytes) + t_off;
                 bar_wait(&kfull_bar[s], ph);
+                if (ct == 0) TC_STAMP(6, it);
                 const uint32_t nkeys = s_nkeys[s];
                 if (nkeys) {
                     bar_wait(&full_bar[s], ph);
                     for (uint32_t k = 0; k < nkeys; ++k) {
                         const uint32_t e = s_keys[s][k];
-                        const uint32_t kp = e & 63u, kc = (e >> 6) & 31u, ko = e >> 11;
-                        const uint32_t cap = (uint32_t)p.cap[kc];
-                        const uint32_t pos = ((uint32_t)s_base[kc] + ko % cap) % cap;
-                        const int64_t row = (p.row_off[kc] + pos) * p.D;
-                        for (int d = ct; d < p.D; d += 64) {
-                            const unsigned short bits = *reinterpret_cast<const unsigned short*>(
-                                stage + (d >> 7) * TC_BOX_BYTES + box_off((uint32_t)(d & 127), kp));
-                            if (p.bank_bf16) reinterpret_cast<unsigned short*>(p.bank_rows)[row + d] = bits;
-                            else reinterpret_cast<float*>(p.bank_rows)[row + d] = bf16_bits_to_float(bits);
+                        const uint32_t kp = e & 63u;
+                        const int64_t row = (int64_t)(e >> 6) * p.D;
+                        const uint32_t src = stage_a + ((((kp >> 3) ^ (uint32_t)(ct & 7))) << 4) + ((kp & 7u) << 1);
+                        unsigned short v[TC_MAX_DB];
+#pragma unroll
+                        for (int i = 0; i < TC_MAX_DB; ++i)
+                            if (ct + i * TC_ROWS < p.D)
+                                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v[i]) : "r"(src + (uint32_t)i * TC_BOX_BYTES));
+#pragma unroll
+                        for (int i = 0; i < TC_MAX_DB; ++i) {
+                            const int d = ct + i * TC_ROWS;
+                            if (d < p.D) {
+                                if (p.bank_bf16) reinterpret_cast<unsigned short*>(p.bank_rows)[row + d] = v[i];
+                                else reinterpret_cast<float*>(p.bank_rows)[row + d] = bf16_bits_to_float(v[i]);
+                            }
                         }
                     }
                 }
-                asm volatile("bar.sync 2, 64;" ::: "memory");
-                if (ct == 0) bar_arrive(&empty_bar[s]);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (ct == 0) { bar_arrive(&empty_bar[s]); TC_STAMP(7, it); }
             }
         }
     }
@@ -294,6 +325,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
         for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) n_it += steps_in_tile(t);
         if (n_it > 0) {
             bar_wait(&done_bar, 0);
+            if (tid == 0) TC_CTA(2);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         for (int db = 0; db < NDB; ++db) {
@@ -320,6 +352,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+    if (tid == 0) TC_CTA(3);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -353,6 +386,8 @@ int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank
                     int rows, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
     ARCO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    for (int c = 0; c < d.classes; ++c)
+        ARCO_REQUIRE(bank->row_off[c] + bank->cap[c] < (1ll << 26), "memory bank too large for the packed key list (2^26 rows)");
     CUtensorMap map;
     const cuuint64_t gdim[3] = {(cuuint64_t)d.space, (cuuint64_t)d.feat, (cuuint64_t)(d.n_lab + d.n_unlab)};
     const cuuint64_t gstr[2] = {(cuuint64_t)d.space * 2, (cuuint64_t)d.space * d.feat * 2};
@@ -384,3 +419,11 @@ int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank
 }
 
 }  // namespace arco
+
+#ifdef ARCO_TC_TRACE
+extern "C" __attribute__((visibility("default"))) int arco_debug_tc_trace(long long* out) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, arco::g_tc_trace, sizeof(long long) * 8 * 256);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out + 8 * 256, arco::g_tc_cta, sizeof(long long) * 4 * 160);
+    return (int)e;
+}
+#endif
