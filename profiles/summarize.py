@@ -52,8 +52,25 @@ def main():
             for m in METRICS:
                 if m in d:
                     lines.append(f"| {m} | {d[m]} |")
+            # DRAM bytes of the prototype kernel per launch -> profiles/traffic.json (bench.py's roofline.traffic)
+            base = os.path.basename(rep)
+            wl = ("acdc2d_trainstep" if "trainstep" in base else "cityscapes" if "city" in base else
+                  "la3d" if "la3d" in base else "acdc2d_loss" if "acdc" in base else None)
+            if wl and "proto_" in d["kernel"] and "finalize" not in d["kernel"]:
+                def num(m):
+                    v, u = d.get(m, "0 byte").split()[:2]
+                    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+                traffic.setdefault(wl, {})["proto_enqueue"] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+                traffic[wl]["source"] = f"{base}: {d['kernel'][:60]} dram__bytes_read.sum + dram__bytes_write.sum"
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w") as f:
         f.write("\n".join(lines) + "\n")
+    if traffic:
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        old = json.load(open(tp)) if os.path.exists(tp) else {}
+        old.update(traffic)
+        with open(tp, "w") as f:
+            json.dump(old, f, indent=1, sort_keys=True)
+            f.write("\n")
     # bench lines
     out = [f"# {tag}: bench.py lines brought back from the B200 box\n"]
     for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "bench_*.json"))):
