@@ -99,6 +99,8 @@ def _load():
         "arco_forward": (C.c_int, [dp, C.POINTER(StepIO), bp, vp, vp]),
         "arco_export_list": (C.c_int, [dp, i32, i32, vp, i64, vp, vp, vp]),
         "arco_bank_read": (C.c_int, [bp, i32, i32, vp, vp]),
+        "arco_similarity_dense_scratch": (C.c_int64, [i32, i32, i32, bp, vp]),
+        "arco_similarity_dense": (C.c_int, [i32, i32, i32, i32, vp, vp, bp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)      # AttributeError here == header/library mismatch

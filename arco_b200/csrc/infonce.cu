@@ -717,9 +717,11 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
         arco::infonce_kernel<MI, BF><<<grid, 128, smem, st>>>(p);                                                           \
     } while (0)
     static const int mma_env = [] { const char* e = getenv("ARCO_INFONCE_MMA"); return e ? atoi(e) : 1; }();   // 0 = off, else stages (1 | 2)
-    if (bf16bank && mma_env > 0 && temp >= 0.03f) {
+    // Measured (profiles/r01_config5_sweep.md): the mma.sync kernel's per-chunk cost is flat in D, so it wins for long rows
+    // (D = 496: 0.142 vs 0.190 ms) and loses to the FFMA kernel on the same bf16 ring at D <= 256 (0.114 vs 0.090 ms).
+    if (bf16bank && mma_env > 0 && temp >= 0.03f && (d.feat >= 320 || mma_env >= 8)) {
         // tensor-core path (fixed softmax offset 1/temp needs exp(-2/temp) to stay a normal float)
-        const int nstg = mma_env >= 2 ? 2 : 1;
+        const int nstg = (mma_env & 7) >= 2 ? 2 : 1;
         const int ks = (d.feat + 15) / 16;
         int r16 = 2 * ks;                                               // >= 16*ks dims
         if ((r16 & 1) == 0) ++r16;                                      // odd stride: ldmatrix rows hit distinct banks

@@ -228,13 +228,20 @@ def bench_inputs(name: str, device, seed: int = 1337, blocky: bool = False, n_la
     return spec, tensors
 
 
-def bench_bank(spec: CaseSpec, seed: int = 1337):
-    """Banks pre-filled to capacity with N(0,1) rows (CPU lists, the trainers' layout).  With a bf16 representation
+def bench_bank(spec: CaseSpec, seed: int = 1337, cold: bool = False):
+    """``cold``: the trainers' own initial bank (one zero row per class in 2-D, train_arco_2d.py:147-154; one N(0,1) row
+    in 3-D, train_arco_3d.py:144-151) -- the reference-faithful state of SURVEY.md trap 3.  Otherwise:
+    banks pre-filled to capacity with N(0,1) rows (CPU lists, the trainers' layout).  With a bf16 representation
     head every row a real run ever enqueues is a bf16 teacher row, so the steady-state bank is bf16-exact: the rows
     are rounded to bf16 values (still handed over as fp32 tensors, as the trainers hold them)."""
     g = torch.Generator()
     g.manual_seed(seed)
     caps = spec.queue_sizes()
+    if cold:
+        three_d = len(spec.spatial) == 3
+        memobank = [[torch.randn(1, spec.feat, generator=g) if three_d else torch.zeros(1, spec.feat)]
+                    for _ in range(spec.classes)]
+        return memobank, [torch.zeros(1, dtype=torch.long) for _ in range(spec.classes)], caps
     memobank = [[torch.randn(caps[c], spec.feat, generator=g)] for c in range(spec.classes)]
     if spec.dtype == "bf16":
         memobank = [[m[0].to(torch.bfloat16).to(torch.float32)] for m in memobank]

@@ -34,6 +34,9 @@ UNIT = "Mpixels/s"
 KERNELS_PER_STEP = 9        # classify, scan_plan, proto_enqueue, proto_finalize, sample_scan, sample_emit, infonce, fill_zero, grad_scatter
 
 
+COLD_BANK = False
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -44,6 +47,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--func", default="smc")
     ap.add_argument("--blocky", action="store_true", help="labels constant on 16-pixel tiles instead of iid")
+    ap.add_argument("--bank", default="full", choices=["full", "cold"],
+                    help="full: banks pre-filled to capacity; cold: the trainers' initial one-row banks (reference-faithful "
+                         "start, SURVEY.md section 8(d) config 3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
@@ -145,7 +151,7 @@ def run_cpu(workload, steps, warmup, func):
     torch.set_num_threads(cores)
     cfg = cpu_sample_spec(workload)
     spec, x = bench_inputs(workload, torch.device("cpu"), seed=1337, n_lab=cfg["n_lab"], n_unlab=cfg["n_unlab"])
-    memobank, ptrs, caps = bench_bank(spec)
+    memobank, ptrs, caps = bench_bank(spec, cold=COLD_BANK)
     sampler = {"smc": oracle.grid_strata_sample, "asmc": oracle.grid_antithetic_sample}.get(func)
     rep = x["rep"].float().requires_grad_(True)           # CPU bf16 kernels are not what the reference ran on
     teacher = x["rep_teacher"].float()
@@ -219,7 +225,7 @@ def main_ours(args):
     from arco_b200.synth import bench_bank, bench_inputs
 
     spec, x = bench_inputs(args.workload, dev, seed=1337 + rank, blocky=args.blocky)
-    memobank, ptrs, caps = bench_bank(spec, seed=1337 + rank)
+    memobank, ptrs, caps = bench_bank(spec, seed=1337 + rank, cold=COLD_BANK)
     rep = x["rep"].requires_grad_(True)
     P = spec.pixels
     kw = dict(delta_n=0.97, func=args.func, num_queries=spec.queries, num_negatives=spec.negatives, temp=0.5,
@@ -306,7 +312,7 @@ def main_ours(args):
                 "workload": args.workload, "batch_per_gpu": spec.batch, "labelled_per_gpu": spec.n_lab,
                 "classes": spec.classes, "spatial": list(spec.spatial), "feat": spec.feat, "rep_storage": spec.dtype,
                 "queries": spec.queries, "negatives": spec.negatives, "func": args.func,
-                "labels": "blocky16" if args.blocky else "iid", "banks": "pre-filled to capacity (50000/30000 rows)" + (", bf16-exact rows in a bf16 ring" if spec.dtype == "bf16" else ", fp32 ring"),
+                "labels": "blocky16" if args.blocky else "iid", "banks": ("cold: the trainers' initial one-row banks" if COLD_BANK else "pre-filled to capacity (50000/30000 rows)") + (", bf16-exact rows in a bf16 ring" if spec.dtype == "bf16" else ", fp32 ring"),
                 "pixels_per_gpu": P, "parallelism": f"batch-shard x{world}, 1 all-reduce of C*(D+1) fp64" if world > 1 else "single GPU",
                 "l2": l2_note, "timing": "CUDA events per step on the launching stream, max over ranks",
             },
@@ -415,7 +421,7 @@ def run_aten_gpu(torch, spec, x, dev, func, steps=3):
     this B200 costs, including its per-class CPU->GPU bank upload and CPU samplers.  Reported, not optimised."""
     import oracle
     from arco_b200.synth import bench_bank
-    memobank, ptrs, caps = bench_bank(spec, seed=4321)
+    memobank, ptrs, caps = bench_bank(spec, seed=4321, cold=COLD_BANK)
     sampler = {"smc": oracle.grid_strata_sample, "asmc": oracle.grid_antithetic_sample}.get(func)
     rep = x["rep"].detach().clone().requires_grad_(True)
     times = []
@@ -470,6 +476,7 @@ def run_e2e(torch, arco_b200, spec, x, memobank, ptrs, caps, dev, kw, world, ste
 
 if __name__ == "__main__":
     a = parse()
+    COLD_BANK = a.bank == "cold"
     if a.impl == "reference":
         main_reference(a)
     else:

@@ -233,6 +233,22 @@ ARCO_API int arco_export_list(const arco_dims* dims, int32_t kind, int32_t cls, 
 /* Copy class `cls` of the ring to `out` in logical FIFO order ([cap, D], rows >= len untouched). */
 ARCO_API int arco_bank_read(const arco_bank* bank, int32_t cls, int32_t feat, float* out, void* stream);
 
+
+/* ---- config 5: dense tensor-core similarity, forward only ----------------------------------
+   Replaces, for the crossover study, the paired gather of loss_helper_3d.py:466-486 (negative_feat = bank[idx]; cosine of
+   every query against its own N rows) by  S = A_hat [Q, D] x Ring^T [D, cap]  on tcgen05 (anchor rows split into three bf16
+   terms, ring rows bf16: exact products, fp32 accumulation) and a scalar gather  logits[q][n] = S[q][row(idx[q][n])] / |k_row|.
+   anchors   f32 device [n_slots][Q][D]  raw (un-normalised) anchor rows
+   slot_class int32 HOST [n_slots]       ring class each slot is contrasted against (valid_classes[i], trap 1)
+   idx_neg   int32 device [n_slots][Q][N] logical ring rows (as arco_sample writes them)
+   logits    f32 device [n_slots][Q][N]  cosines (not divided by temp)
+   scratch   device, arco_similarity_dense_scratch() bytes.  Needs a bf16 ring, D % 8 == 0, Q % 128 == 0.          */
+ARCO_API int64_t arco_similarity_dense_scratch(int32_t feat, int32_t queries, int32_t n_slots, const arco_bank* bank,
+                                               const int32_t* slot_class);
+ARCO_API int arco_similarity_dense(int32_t feat, int32_t queries, int32_t negatives, int32_t n_slots,
+                                   const int32_t* slot_class, const float* anchors, const arco_bank* bank,
+                                   const int32_t* idx_neg, float* logits, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "arco_b200.h")
 
 def _declared():
     src = open(HEADER).read()
-    return sorted(set(re.findall(r"ARCO_API\s+(?:const\s+char\*|int)\s+(arco_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"ARCO_API\s+(?:const\s+char\*|int64_t|int)\s+(arco_\w+)\s*\(", src)))
 
 
 def test_header_declares_the_path():
