@@ -17,6 +17,8 @@ _EXPORTS = {
     "ArcoError": "_cabi", "version": "_cabi",
     "BankSlot": "bank", "DeviceMemoryBank": "bank", "synchronize_bank": "bank",
     "compute_contra_memobank_loss": "contra",
+    "prepare_contrast_inputs": "prepare", "softmax_entropy": "prepare", "entropy_masks": "prepare",
+    "dense_similarity": "similarity",
     "as_monte_carlo_sample": "samplers", "dequeue_and_enqueue": "samplers", "grid_as_monte_carlo_sample": "samplers",
     "grid_monte_carlo_sample": "samplers", "label_onehot": "samplers", "monte_carlo_sample": "samplers",
 }

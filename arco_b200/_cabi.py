@@ -99,6 +99,10 @@ def _load():
         "arco_forward": (C.c_int, [dp, C.POINTER(StepIO), bp, vp, vp]),
         "arco_export_list": (C.c_int, [dp, i32, i32, vp, i64, vp, vp, vp]),
         "arco_bank_read": (C.c_int, [bp, i32, i32, vp, vp]),
+        "arco_softmax_rows": (C.c_int, [vp, i64, i32, i64, vp, vp, vp]),
+        "arco_entropy_masks_scratch": (C.c_int64, []),
+        "arco_entropy_masks": (C.c_int, [vp, vp, vp, i64, i64, f32, f32, vp, vp, vp, vp, vp]),
+        "arco_prepare_contrast": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i64, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "arco_similarity_dense_scratch": (C.c_int64, [i32, i32, i32, bp, vp]),
         "arco_similarity_dense": (C.c_int, [i32, i32, i32, i32, vp, vp, bp, vp, vp, vp, vp]),
     }

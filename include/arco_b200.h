@@ -249,6 +249,29 @@ ARCO_API int arco_similarity_dense(int32_t feat, int32_t queries, int32_t negati
                                    const int32_t* slot_class, const float* anchors, const arco_bank* bank,
                                    const int32_t* idx_neg, float* logits, void* scratch, void* stream);
 
+/* ---- mask / threshold preparation upstream of the loss -------------------------------
+   Replaces train_arco_2d.py:345-393 (train_arco_3d.py:315-353): teacher softmax, student entropy, the two np.percentile
+   thresholds (a GPU -> CPU -> GPU round trip each in the reference) and the low / high entropy masks.                  */
+/* softmax over the class axis of logits [batch, classes, space] (f32); prob (same shape) and/or
+   entropy[batch, space] = -sum_c p*log(p + 1e-10) may be NULL.  (:353-359)                                             */
+ARCO_API int arco_softmax_rows(const float* logits, int64_t batch, int32_t classes, int64_t space, float* prob,
+                               float* entropy, void* stream);
+ARCO_API int64_t arco_entropy_masks_scratch(void);
+/* entropy f32 [n_unlab_px] (student, unlabelled images), label_l / label_u int64 label maps (ignore = negative).
+   q_low / q_high = float32(percent) / float32(100) exactly as numpy 2.x forms them for float32 data.
+   low_mask / high_mask f32 [n_lab_px + n_unlab_px] (labelled part: label >= 0; unlabelled part: entropy <= / >= the
+   numpy-"linear" percentile of the valid entropies, times label >= 0)  (:360-392); thresholds: optional device float[2]. */
+ARCO_API int arco_entropy_masks(const float* entropy, const int64_t* label_l, const int64_t* label_u, int64_t n_lab_px,
+                                int64_t n_unlab_px, float q_low, float q_high, float* low_mask, float* high_mask,
+                                float* thresholds, void* scratch, void* stream);
+/* The whole block in one call: teacher probabilities of both halves, student entropy of the unlabelled half, masks.
+   logits f32 [n, classes, space]; labels int64 [n, space]; outputs as in the two functions above.                       */
+ARCO_API int arco_prepare_contrast(const float* pred_u, const float* pred_l_teacher, const float* pred_u_teacher,
+                                   const int64_t* label_l, const int64_t* label_u, int64_t n_lab, int64_t n_unlab,
+                                   int32_t classes, int64_t space, float q_low, float q_high, float* prob_l_teacher,
+                                   float* prob_u_teacher, float* entropy, float* low_mask, float* high_mask,
+                                   float* thresholds, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,38 @@ SAMPLER_CASES = [
         (3000, 1, 17), (5000, 20, 18),
     ]
 ]
+
+
+# SURVEY.md section 8(f) rank 1 -- mask / threshold preparation (train_arco_2d.py:345-393, train_arco_3d.py:315-353):
+# (name, n_lab, n_unlab, classes, spatial, alpha_t, ignore_frac, logit quantisation step (0 = none), seed)
+PREPARE_CASES = [
+    ("prep2d_a14", 2, 2, 4, (24, 20), 14.0, 0.05, 0.0, 101),
+    ("prep2d_a20", 1, 3, 4, (16, 16), 20.0, 0.0, 0.0, 102),
+    ("prep2d_ties", 2, 2, 4, (32, 32), 7.4, 0.10, 0.5, 103),       # coarse logits -> many exactly equal entropies
+    ("prep2d_c19", 1, 2, 19, (12, 12), 3.0, 0.05, 0.0, 104),
+    ("prep3d_c2", 1, 2, 2, (8, 8, 6), 11.2, 0.05, 0.0, 105),
+    ("prep2d_a0", 1, 1, 4, (8, 8), 0.0, 0.0, 0.0, 106),           # last epoch: alpha_t = 0 -> thresholds = min / max
+]
+
+
+def prepare_inputs(case):
+    """Machine-independent inputs of a PREPARE case (integers scaled to floats, no libm involved)."""
+    import numpy as np
+    import torch
+    name, n_lab, n_unlab, C, spatial, alpha_t, ign, quant, seed = case
+    rs = np.random.RandomState(seed)
+
+    def logits(b):
+        x = rs.randint(-4096, 4096, size=(b, C) + tuple(spatial)).astype(np.float32) / 1024.0
+        if quant:
+            x = np.round(x / quant) * quant
+        return torch.from_numpy(x.astype(np.float32))
+
+    def labels(b):
+        lab = rs.randint(0, C, size=(b,) + tuple(spatial)).astype(np.int64)
+        if ign:
+            lab[rs.rand(*lab.shape) < ign] = -1
+        return torch.from_numpy(lab)
+
+    return dict(pred_l=logits(n_lab), pred_u=logits(n_unlab), pred_l_teacher=logits(n_lab), pred_u_teacher=logits(n_unlab),
+                train_l_label=labels(n_lab), train_u_aug_label=labels(n_unlab), alpha_t=float(alpha_t), num_classes=C)

@@ -32,7 +32,7 @@ import loss_helper as ref3d        # noqa: E402  5-D volumes  (file names are in
 import loss_helper_3d as ref2d     # noqa: E402  4-D images
 
 from arco_b200.synth import exact_case, make_bank   # noqa: E402
-from cases import CASES, SAMPLER_CASES              # noqa: E402
+from cases import CASES, PREPARE_CASES, SAMPLER_CASES, prepare_inputs   # noqa: E402
 
 
 def run_case(spec):
@@ -104,6 +104,39 @@ def run_samplers():
     return out
 
 
+def _trainer_block(path, three_d):
+    """The trainer's own ``with torch.no_grad():`` mask-preparation block and its ``label_onehot`` def, as source text read
+    from the reference tree at generation time (train_arco_2d.py:345-393 + :492-498 / train_arco_3d.py:315-353 + :463-469)."""
+    import textwrap
+    lines = open(path).read().split("\n")
+    start = next(i for i, ln in enumerate(lines) if ln.strip() == "with torch.no_grad():" and "alpha_t" in "".join(lines[i - 4:i]))
+    end = next(i for i in range(start, len(lines)) if lines[i].strip().startswith("reco_loss = compute_contra_memobank_loss"))
+    block = textwrap.dedent("\n".join(lines[start:end]))
+    d0 = next(i for i, ln in enumerate(lines) if ln.startswith("def label_onehot("))
+    d1 = next(i for i in range(d0 + 1, len(lines)) if lines[i].startswith("def ") or lines[i].startswith("if __name__"))
+    return "\n".join(lines[d0:d1]) + "\n" + block
+
+
+def run_prepare_case(case):
+    """Execute the reference trainer's own lines on the case's tensors (CPU) and record what they leave behind."""
+    import argparse
+    import torch.nn.functional as F
+    x = prepare_inputs(case)
+    three_d = len(case[4]) == 3
+    src = _trainer_block("/root/reference/code/train_arco_3d.py" if three_d else "/root/reference/code/train_arco_2d.py", three_d)
+    ns = dict(torch=torch, np=np, F=F, args=argparse.Namespace(num_classes=x["num_classes"], weak_threshold=0.7),
+              pred_l=x["pred_l"], pred_u=x["pred_u"], pred_l_teacher=x["pred_l_teacher"], pred_u_teacher=x["pred_u_teacher"],
+              pred_all=torch.cat((x["pred_l"], x["pred_u"])), train_l_label=x["train_l_label"],
+              train_u_aug_label=x["train_u_aug_label"], train_u_aug_logits=torch.rand(x["train_u_aug_label"].shape),
+              alpha_t=x["alpha_t"])
+    exec(compile(src, "<reference trainer block>", "exec"), ns)
+    return dict(low_thresh=np.float32(ns["low_thresh"]), high_thresh=np.float32(ns["high_thresh"]),
+                low_mask_all=ns["low_mask_all"].numpy().astype(np.uint8), high_mask_all=ns["high_mask_all"].numpy().astype(np.uint8),
+                prob_l_teacher=ns["prob_l_teacher"].numpy(), prob_u_teacher=ns["prob_u_teacher"].numpy(),
+                entropy=ns["entropy"].numpy(), label_l=ns["label_l"].numpy().astype(np.uint8),
+                label_u=ns["label_u"].numpy().astype(np.uint8))
+
+
 def main():
     import warnings
     warnings.filterwarnings("ignore")
@@ -114,6 +147,12 @@ def main():
         losses = [float(res[f"s{t}_loss"]) for t in range(spec.steps)]
         print(f"{spec.name:16s} loss={losses} new_keys={res[f's{spec.steps-1}_new_keys'].tolist()} "
               f"calls={res[f's{spec.steps-1}_call_high'].tolist()} {os.path.getsize(path)/1024:.0f} KB")
+    for case in PREPARE_CASES:
+        res = run_prepare_case(case)
+        path = os.path.join(HERE, case[0] + ".npz")
+        np.savez_compressed(path, **res)
+        print(f"{case[0]:16s} thresholds=({res['low_thresh']!r}, {res['high_thresh']!r}) low={int(res['low_mask_all'].sum())} "
+              f"high={int(res['high_mask_all'].sum())} {os.path.getsize(path)/1024:.0f} KB")
     path = os.path.join(HERE, "samplers.npz")
     np.savez_compressed(path, **run_samplers())
     print("samplers.npz", f"{os.path.getsize(path)/1024:.0f} KB")
