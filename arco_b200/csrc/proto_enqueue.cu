@@ -670,10 +670,13 @@ __global__ void __launch_bounds__(128) proto_finalize_kernel(const float* __rest
 bool proto_tc_supported(const arco_dims& d);
 int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank* bank, const arco_ws_layout& L, char* ws,
                     int rows, cudaStream_t st);
+bool proto_tc32_supported(const arco_dims& d);
+int launch_proto_tc32(const arco_dims& d, const void* rep_teacher, const arco_bank* bank, const arco_ws_layout& L, char* ws,
+                      int rows, cudaStream_t st);
 
 struct ProtoCfg {
     int kind;         // 0 scalar fallback (proto_enqueue_kernel), 1 pipelined (proto_pipe_kernel), 2 small (proto_small_kernel),
-                      // 3 tensor cores (proto_tc_kernel, bf16)
+                      // 3 tensor cores (proto_tc_kernel, bf16), 4 tensor cores (proto_tc32_kernel, fp32 as TF32 hi + lo)
     int nch;          // lanes per stream
     int epl;          // feature dims per lane
     int dchunk;       // feature dims per CTA
@@ -691,6 +694,10 @@ static ProtoCfg proto_cfg(const arco_dims& d) {
     const char* tc_env = getenv("ARCO_PROTO_TC");
     if (proto_tc_supported(d) && !(tc_env && tc_env[0] == '0')) { c.kind = 3; c.nch = 0; c.epl = 0; c.dchunk = d.feat; c.smem = 0; return c; }
     if (vec && d.classes <= 3 && (d.feat == 16 || d.feat == 32)) { c.kind = 2; c.nch = 0; c.epl = 0; c.dchunk = d.feat; c.smem = 0; return c; }
+    const char* tc32_env = getenv("ARCO_PROTO_TC32");
+    // one 128-row box per step (D <= 128) leaves the tensor path latency-bound per 32-pixel step: measured 0.111 vs 0.050 ms
+    // at D = 64, so the CUDA-core pipeline keeps those shapes (ARCO_PROTO_TC32=2 forces the tensor path, =0 disables it)
+    if (proto_tc32_supported(d) && !(tc32_env && tc32_env[0] == '0') && (d.feat > 128 || (tc32_env && tc32_env[0] == '2'))) { c.kind = 4; c.nch = 0; c.epl = 0; c.dchunk = d.feat; c.smem = 0; return c; }
     if (vec) {
         c.kind = 1;
         c.epl = (d.classes <= 8 && d.feat >= 32) ? 8 : 4;
@@ -732,7 +739,7 @@ static int proto_occ(const ProtoCfg& c) {
 static void proto_grid(const arco_dims& d, int* ndc, int* groups) {
     const ProtoCfg c = proto_cfg(d);
     if (c.kind == 2) { *ndc = 1; *groups = sm_count() * 4; return; }
-    if (c.kind == 3) { *ndc = 1; *groups = sm_count(); return; }
+    if (c.kind == 3 || c.kind == 4) { *ndc = 1; *groups = sm_count(); return; }
     *ndc = (d.feat + c.dchunk - 1) / c.dchunk;
     int occ = d.rep_dtype == ARCO_BF16 ? proto_occ<__nv_bfloat16>(c) : proto_occ<float>(c);
     // without a device (CPU-only build box) assume the shared-memory bound
@@ -807,6 +814,7 @@ extern "C" int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher
     p.vec_ok = arco::proto_vec_ok(d);
     int rc;
     if (arco::proto_cfg(d).kind == 3) rc = arco::launch_proto_tc(d, rep_teacher, bank, L, ws, groups, st);
+    else if (arco::proto_cfg(d).kind == 4) rc = arco::launch_proto_tc32(d, rep_teacher, bank, L, ws, groups, st);
     else rc = d.rep_dtype == ARCO_BF16 ? arco::launch_proto<__nv_bfloat16>(d, p, groups, st)
                                        : arco::launch_proto<float>(d, p, groups, st);
     if (rc != ARCO_OK) return rc;

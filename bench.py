@@ -406,7 +406,10 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
             traffic = None
     k = "proto_enqueue"
     kname = ("arco::proto_tc_kernel (tcgen05 + TMA)" if spec.dtype == "bf16" and spec.classes <= 16 and spec.feat >= 64
-             else "arco::proto_small_kernel" if spec.classes <= 3 and spec.feat in (16, 32) else "arco::proto_pipe_kernel")
+             else "arco::proto_small_kernel" if spec.classes <= 3 and spec.feat in (16, 32)
+             else "arco::proto_tc32_kernel (tcgen05 kind::tf32, hi + lo passes, TMA)"
+             if spec.dtype != "bf16" and spec.feat > 128 and os.environ.get("ARCO_PROTO_TC32", "1") != "0"
+             else "arco::proto_pipe_kernel")
     roof = {"kernel": kname + " + proto_finalize_kernel (<2% of the call)", "bound": "hbm",
             "achieved": stages[k]["gbs"], "peak": peak, "unit": "GB/s", "frac": stages[k]["frac_hbm"],
             "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg[k], "ms_per_launch": ms[k],
