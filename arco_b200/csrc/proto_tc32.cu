@@ -11,9 +11,9 @@
 // (If the hardware rounded instead of truncating, hi + lo would be off by a TF32 ulp -- 5e-4 relative -- and the 2e-5
 // prototype parity tests of tests/test_gpu_shapes.py would fail; they pass.)
 //
-// Roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer (hi of step k, then lo of step k-1), warp 4 builder (one
-// thread per pixel of the 32-pixel step: one-hot tile, FIFO ordinals, key list), warps 2-3 + 6-7 copy the keys out of the
-// raw box and then convert it; warps 0-3 run the TMEM -> partial-row epilogue.  Stage = all D rows of a 32-pixel step
+// Roles (384 threads): warp 0 TMA producer, warp 1 issues the hi passes, warp 5 the lo passes (own accumulators, summed in
+// the epilogue), warp 4 builder (one thread per pixel of the 32-pixel step: one-hot tile, FIFO ordinals, key list), warps
+// 2-3 + 6-11 copy the keys out of the raw box and then convert it; warps 0-3 run the TMEM -> partial-row epilogue.  Stage = all D rows of a 32-pixel step
 // (NDB boxes of 128 rows x 128 B) + the one-hot tile; as many stages as fit (6 at D <= 256, 3 at D = 512).
 #include <cuda.h>
 #include <stdlib.h>
@@ -68,7 +68,7 @@ __device__ long long g_tc32_trace[8][512];
 #define T32_STAMP(role, it) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constant__ CUtensorMap tmap, ProtoTc32Params p) {
+__global__ void __launch_bounds__(384, 1) proto_tc32_kernel(const __grid_constant__ CUtensorMap tmap, ProtoTc32Params p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int NDB = p.NDB, NST = p.NST;
@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constan
             bar_init(&full_bar[s], 1); bar_init(&bfull_bar[s], 1); bar_init(&kfull_bar[s], 1);
             bar_init(&hidone_bar[s], 1); bar_init(&lo_bar[s], 1); bar_init(&empty_bar[s], 1);
         }
-        bar_init(&done_bar, 1);
+        bar_init(&done_bar, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < ARCO_MAX_CLASSES) { s_skip[tid] = p.plan->bank_skip[tid]; s_base[tid] = p.plan->bank_write_base[tid]; }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s_tmem)), "r"(128));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&s_tmem)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -113,6 +113,18 @@ __global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constan
         const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
         const int64_t left = S - s_tile;
         return (int)min((int64_t)(ARCO_TILE / T32_KPX), (left + T32_KPX - 1) / T32_KPX);
+    };
+
+    auto issue = [&](uint32_t k, bool first, uint32_t col0) {                   // all MMAs of one pass over stage k % NST
+        const uint32_t a0 = s32(base + (size_t)(k % NST) * stage_bytes);
+        const uint32_t b0 = a0 + NDB * T32_BOX_BYTES;
+        // feature block outer, K step inner (interleaving the accumulators measured 12 % slower)
+        for (int db = 0; db < NDB; ++db) {
+#pragma unroll
+            for (int kk = 0; kk < T32_KPX / 8; ++kk)
+                umma_tf32(tmem + col0 + db * p.NCLS, umma_desc(a0 + db * T32_BOX_BYTES + kk * 32), umma_desc(b0 + kk * 32), idesc,
+                          (!first || kk > 0) ? 1u : 0u);
+        }
     };
 
     if (warp == 0) {
@@ -135,44 +147,32 @@ __global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constan
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t it = 0;
-            auto issue = [&](uint32_t k, bool first) {                   // all MMAs of one pass over stage k % NST
-                const uint32_t a0 = s32(base + (size_t)(k % NST) * stage_bytes);
-                const uint32_t b0 = a0 + NDB * T32_BOX_BYTES;
-                for (int db = 0; db < NDB; ++db) {
-#pragma unroll
-                    for (int kk = 0; kk < T32_KPX / 8; ++kk)
-                        umma_tf32(tmem + db * p.NCLS, umma_desc(a0 + db * T32_BOX_BYTES + kk * 32), umma_desc(b0 + kk * 32), idesc,
-                                  (!first || kk > 0) ? 1u : 0u);
-                }
-            };
-            for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
-                const int ns = steps_in_tile(t);
-                for (int st = 0; st < ns; ++st, ++it) {
-                    const int s = it % NST;
-                    const uint32_t ph = (it / NST) & 1;
-                    bar_wait(&full_bar[s], ph);
-                    T32_STAMP(1, it);
-                    bar_wait(&bfull_bar[s], ph);
-                    T32_STAMP(2, it);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    issue(it, it == 0);                                   // hi pass: the raw box
-                    umma_commit(&hidone_bar[s]);
-                    if (it > 0) {                                         // lo pass of the previous step (converted meanwhile)
-                        const uint32_t k = it - 1;
-                        bar_wait(&lo_bar[k % NST], (k / NST) & 1);
-                        T32_STAMP(3, k);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        issue(k, false);
-                        umma_commit(&empty_bar[k % NST]);
-                    }
-                }
-            }
-            if (it > 0) {
-                const uint32_t k = it - 1;
-                bar_wait(&lo_bar[k % NST], (k / NST) & 1);
+            // hi passes only; the lo passes are issued by warp 5 into their OWN accumulators (TMEM columns 128..255), so two
+            // threads feed the tensor core (one thread issuing both passes was the bottleneck: ~0.33 us per pass and step)
+            uint32_t total = 0;
+            for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) total += steps_in_tile(t);
+            for (uint32_t k = 0; k < total; ++k) {
+                const int s = k % NST;
+                const uint32_t ph = (k / NST) & 1;
+                bar_wait(&full_bar[s], ph);
+                bar_wait(&bfull_bar[s], ph);
+                T32_STAMP(1, k);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue(k, false);
+                issue(k, k == 0, 0u);
+                umma_commit(&hidone_bar[s]);
+                T32_STAMP(2, k);
+            }
+            umma_commit(&done_bar);
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            uint32_t total = 0;
+            for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) total += steps_in_tile(t);
+            for (uint32_t k = 0; k < total; ++k) {
+                bar_wait(&lo_bar[k % NST], (k / NST) & 1);
+                T32_STAMP(3, k);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue(k, k == 0, 128u);
                 umma_commit(&empty_bar[k % NST]);
             }
             umma_commit(&done_bar);
@@ -243,9 +243,10 @@ __global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constan
             t = t_next;
         }
     } else if (warp == 2 || warp == 3 || warp >= 6) {
-        // ---- copiers / converters: keys out of the raw box, then x <- x - (x & 0xFFFFE000) in place for the lo pass ----
-        const int ct = (warp < 4 ? (warp - 2) * 32 : 64 + (warp - 6) * 32) + lane;
-        const uint32_t t_off = (uint32_t)(ct >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
+        // ---- copiers / converters (8 warps: 2-3, 6-11): keys out of the raw box, then x <- x - (x & 0xFFFFE000) in place for the lo pass ----
+        const int ct = (warp < 4 ? (warp - 2) * 32 : 64 + (warp - 6) * 32) + lane;          // 0..255
+        const int cr = ct & 127;                                                           // feature row inside a box
+        const uint32_t t_off = (uint32_t)(cr >> 3) * 1024u + (uint32_t)(cr & 7) * 128u;
         uint32_t it = 0;
         for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
             const int ns = steps_in_tile(t);
@@ -262,41 +263,44 @@ __global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constan
                         const uint32_t e = s_keys[s][k];
                         const uint32_t kp = e & 63u;
                         const int64_t row = (int64_t)(e >> 6) * p.D;
-                        const uint32_t src = stage_a + ((((kp >> 2) ^ (uint32_t)(ct & 7))) << 4) + ((kp & 3u) << 2);
-                        uint32_t v[T32_MAX_DB];
+                        const uint32_t src = stage_a + ((((kp >> 2) ^ (uint32_t)(cr & 7))) << 4) + ((kp & 3u) << 2);
+                        uint32_t v[T32_MAX_DB / 2];
 #pragma unroll
-                        for (int i = 0; i < T32_MAX_DB; ++i)
-                            if (ct + i * T32_ROWS < p.D)
-                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[i]) : "r"(src + (uint32_t)i * T32_BOX_BYTES));
+                        for (int i = 0; i < T32_MAX_DB / 2; ++i) {                          // boxes (ct >> 7), (ct >> 7) + 2
+                            const int db = (ct >> 7) + 2 * i;
+                            if (db * T32_ROWS + cr < p.D)
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[i]) : "r"(src + (uint32_t)db * T32_BOX_BYTES));
+                        }
 #pragma unroll
-                        for (int i = 0; i < T32_MAX_DB; ++i) {
-                            const int d = ct + i * T32_ROWS;
+                        for (int i = 0; i < T32_MAX_DB / 2; ++i) {
+                            const int d = ((ct >> 7) + 2 * i) * T32_ROWS + cr;
                             if (d < p.D) p.bank_rows[row + d] = __uint_as_float(v[i]);
                         }
                     }
                 }
+                if (nkeys) asm volatile("bar.sync 2, 256;" ::: "memory");   // every key is copied before anyone rewrites the box
                 bar_wait(&hidone_bar[s], ph);                            // the hi pass has read the raw box
                 if (ct == 0) T32_STAMP(6, it);
                 const uint32_t box_a = s32(stage) + (uint32_t)ct * 16u;
                 const int n16 = NDB * (T32_BOX_BYTES / 16);              // multiple of 1024
-                for (int i0 = 0; i0 < n16; i0 += 512) {                  // 4 independent 16-byte chunks per thread in flight
+                for (int i0 = 0; i0 < n16; i0 += 1024) {                 // 4 independent 16-byte chunks per thread in flight
                     uint32_t u[4][4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                                      : "=r"(u[j][0]), "=r"(u[j][1]), "=r"(u[j][2]), "=r"(u[j][3])
-                                     : "r"(box_a + (uint32_t)(i0 + j * 128) * 16u));
+                                     : "r"(box_a + (uint32_t)(i0 + j * 256) * 16u));
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             u[j][e] = __float_as_uint(__fsub_rn(__uint_as_float(u[j][e]), __uint_as_float(u[j][e] & 0xFFFFE000u)));
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(box_a + (uint32_t)(i0 + j * 128) * 16u),
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(box_a + (uint32_t)(i0 + j * 256) * 16u),
                                      "r"(u[j][0]), "r"(u[j][1]), "r"(u[j][2]), "r"(u[j][3]) : "memory");
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (ct == 0) { bar_arrive(&lo_bar[s]); T32_STAMP(7, it); }
             }
         }
@@ -311,9 +315,9 @@ __global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constan
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int db = 0; db < NDB; ++db) {
             for (int c0 = 0; c0 < p.NCLS; c0 += 16) {
-                uint32_t v[16];
+                uint32_t v[16], w[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) v[c] = 0u;
+                for (int c = 0; c < 16; ++c) v[c] = w[c] = 0u;
                 if (any) {
                     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + db * p.NCLS + c0;
                     asm volatile(
@@ -321,7 +325,14 @@ __global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constan
                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                         : "r"(taddr));
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                          "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                        : "r"(taddr + 128u));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(w[c]));   // hi + lo
                 }
                 const int d = db * T32_ROWS + warp * 32 + lane;
                 if (d < p.D) {
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc32_kernel(const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -388,7 +399,7 @@ int launch_proto_tc32(const arco_dims& d, const void* rep_teacher, const arco_ba
     p.NCLS = d.classes <= 16 ? 16 : 32;
     const size_t smem = proto_tc32_smem(d);
     ARCO_CUDA_CHECK(cudaFuncSetAttribute(proto_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    proto_tc32_kernel<<<rows, 256, smem, st>>>(map, p);
+    proto_tc32_kernel<<<rows, 384, smem, st>>>(map, p);
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
 }

@@ -29,6 +29,18 @@ __device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
             : "memory");
     }
 }
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool bar_test(uint64_t* b, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(s32(b)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

@@ -27,7 +27,7 @@ out = np.zeros((8, 512), np.int64)
 fn = _cabi.lib.arco_debug_tc32_trace
 fn.restype = C.c_int
 assert fn(out.ctypes.data_as(C.c_void_p)) == 0
-names = ["prod:empty", "mma:full", "mma:bfull", "mma:lo_rdy", "bld:empty", "bld:kfull", "cvt:hidone", "cvt:done"]
+names = ["prod:empty", "mma:hi_beg", "mma:hi_end", "mma:lo_rdy", "bld:empty", "bld:kfull", "cvt:hidone", "cvt:done"]
 t0 = out[0, 0]
 us = lambda v: (v - t0) / 1.965e3
 print("step " + " ".join(f"{n:>10s}" for n in names))
@@ -35,6 +35,7 @@ for it in list(range(0, 10)) + list(range(300, 316)):
     print(f"{it:4d} " + " ".join(f"{us(out[r, it]):10.2f}" for r in range(8)))
 d = np.diff(out[:, 100:480], axis=1) / 1.965e3
 print("mean period (us):", {names[r]: round(float(d[r].mean()), 3) for r in range(8)})
+print("hi pass issue + commit (us): %.3f" % float((us(out[2, 100:480]) - us(out[1, 100:480])).mean()))
 print("issue->full %.2f | full->hidone(seen by cvt) %.2f | convert %.2f | cvt done->lo seen by mma %.2f" % (
     float((us(out[1, 100:480]) - us(out[0, 100:480])).mean()), float((us(out[6, 100:480]) - us(out[1, 100:480])).mean()),
     float((us(out[7, 100:480]) - us(out[6, 100:480])).mean()), float((us(out[3, 100:480]) - us(out[7, 100:480])).mean())))
