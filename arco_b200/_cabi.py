@@ -52,6 +52,7 @@ class Plan(C.Structure):
         ("bank_len", _I32x), ("bank_head", _I32x),
         ("queue_ptr", _I64x),
         ("inv_scale", C.c_float), ("status", C.c_uint32), ("scan_done", C.c_uint32), ("loss_done", C.c_uint32),
+        ("replanned", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -90,6 +91,7 @@ def _load():
         "arco_replan_global": (C.c_int, [dp, vp, vp, vp]),
         "arco_proto_enqueue": (C.c_int, [dp, vp, bp, vp, vp, vp]),
         "arco_sample": (C.c_int, [dp, i32, u64, u64, vp, vp, vp, vp]),
+        "arco_sample_if_replanned": (C.c_int, [dp, i32, u64, u64, vp, vp, vp, vp]),
         "arco_sample_one": (C.c_int, [i32, i64, i64, u64, u64, vp, vp, i64, vp]),
         "arco_infonce": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
         "arco_infonce_ema": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp]),

@@ -130,8 +130,9 @@ class _ContraLoss(torch.autograd.Function):
         plan_view = ws[layout.plan: layout.plan + C.sizeof(_cabi.Plan)]
         group, inject = st["group"], st["inject"]
         side = None
-        if inject is None and group is None:
-            # the sampler only needs the plan: run it on a side stream underneath the prototype pass
+        if inject is None:
+            # the sampler only needs the plan: run it on a side stream underneath the prototype pass (multi-GPU: on the
+            # rank-local plan, speculatively -- redone below only if the global valid-class list changes the plan)
             side = _side_stream(dev)
             side.wait_stream(stream)
             _cabi.check(lib.arco_sample(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(), idx_n.data_ptr(),
@@ -141,13 +142,15 @@ class _ContraLoss(torch.autograd.Function):
         if group is not None:
             # the one exchange step of the path: C*(D+1) fp64 sums + counts
             torch.distributed.all_reduce(proto_sums, group=group)
+            if side is not None:
+                stream.wait_stream(side)                    # the speculative sampler has read the local plan
             _cabi.check(lib.arco_replan_global(d, proto_sums.data_ptr(), wsp, sp), "arco_replan_global")
-        if side is not None:
+            if side is not None:
+                _cabi.check(lib.arco_sample_if_replanned(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(),
+                                                         idx_n.data_ptr(), wsp, sp), "arco_sample_if_replanned")
+        elif side is not None:
             stream.wait_stream(side)
-        elif inject is None:
-            _cabi.check(lib.arco_sample(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(), idx_n.data_ptr(),
-                                        wsp, sp), "arco_sample")
-        else:
+        if inject is not None:
             # parity tests: replay the reference's own indices, one (anchor, negative) pair per active position
             plan = _cabi.Plan.from_buffer_copy(plan_view.cpu().numpy().tobytes())
             active = [j for j in range(Cn) if plan.slot_active[j]]

@@ -40,6 +40,7 @@ struct SampleParams {
     int32_t* out;
     int32_t func;
     uint64_t seed, stream;
+    int32_t only_if_replanned;              // fused mode: do nothing unless arco_replan_global changed the plan
 };
 
 enum { PURPOSE_DRAW = 0, PURPOSE_PAD = 1, PURPOSE_UNIFORM = 2, PURPOSE_PERM = 3 };
@@ -127,6 +128,7 @@ sample_scan_kernel(SampleParams p) {
     const int call = blockIdx.x / kClusterSize;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ uint32_t s_warp[32];
+    if (p.only_if_replanned && p.plan->replanned == 0) return;            // uniform over the whole grid
     __shared__ uint32_t s_total;
     const Call c = decode_call(p, call);
     if (!c.active || c.uniform || c.strata || !c.drops) return;          // cluster-uniform
@@ -189,6 +191,7 @@ sample_scan_kernel(SampleParams p) {
 // row); out[t] = S[perm(t)] for t < min(|S|, shape), iid uniform pads after that (:170-180).
 __global__ void __launch_bounds__(kEmitThreads) sample_emit_kernel(SampleParams p) {
     const int call = blockIdx.y;
+    if (p.only_if_replanned && p.plan->replanned == 0) return;
     const Call c = decode_call(p, call);
     if (!c.active) return;
     const int64_t t0 = ((int64_t)blockIdx.x * kEmitThreads + threadIdx.x) * kEmitItems;
@@ -272,8 +275,8 @@ static int launch_sampler(const SampleParams& p, int calls, int64_t max_shape, c
 
 }  // namespace arco
 
-extern "C" int arco_sample(const arco_dims* dims, int32_t func, uint64_t seed, uint64_t step, int32_t* idx_anchor,
-                           int32_t* idx_neg, void* workspace, void* stream) {
+static int sample_impl(const arco_dims* dims, int32_t func, uint64_t seed, uint64_t step, int32_t* idx_anchor,
+                       int32_t* idx_neg, void* workspace, void* stream, int only_if_replanned) {
     ARCO_REQUIRE(dims && idx_anchor && idx_neg && workspace, "arco_sample: NULL argument");
     const arco_dims& d = *dims;
     ARCO_REQUIRE((int64_t)d.queries * d.negatives < (int64_t)1 << 30, "Q*N too large");
@@ -287,7 +290,18 @@ extern "C" int arco_sample(const arco_dims* dims, int32_t func, uint64_t seed, u
     p.scratch_stride = draws + draws / 4 + 4096;
     p.C = d.classes; p.Q = d.queries; p.N = d.negatives;
     p.func = func; p.seed = seed; p.stream = step;
+    p.only_if_replanned = only_if_replanned;
     return arco::launch_sampler(p, 2 * d.classes, draws > d.queries ? draws : d.queries, (cudaStream_t)stream);
+}
+
+extern "C" int arco_sample(const arco_dims* dims, int32_t func, uint64_t seed, uint64_t step, int32_t* idx_anchor,
+                           int32_t* idx_neg, void* workspace, void* stream) {
+    return sample_impl(dims, func, seed, step, idx_anchor, idx_neg, workspace, stream, 0);
+}
+
+extern "C" int arco_sample_if_replanned(const arco_dims* dims, int32_t func, uint64_t seed, uint64_t step, int32_t* idx_anchor,
+                                        int32_t* idx_neg, void* workspace, void* stream) {
+    return sample_impl(dims, func, seed, step, idx_anchor, idx_neg, workspace, stream, 1);
 }
 
 extern "C" int arco_sample_one(int32_t func, int64_t high, int64_t shape, uint64_t seed, uint64_t stream_id,

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(1024) scan_plan_kernel(ScanParams p) {
         pl->slot_active[pos] = active;
     }
     pl->inv_scale = nv > 1 ? 1.0f / ((float)p.Q * (float)nv) : 0.f;      // mean over Q, / valid_seg (:507-511)
+    pl->replanned = 0;
 }
 
 // Multi-GPU: after the per-class (feature sum, count) buffer has been all-reduced, the set of valid
@@ -119,9 +120,10 @@ __global__ void __launch_bounds__(1024) scan_plan_kernel(ScanParams p) {
 __global__ void replan_global_kernel(arco_plan* pl, const double* __restrict__ proto_sums, int C, int D, int Q) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int nv = 0;
+    uint32_t changed = 0;
     for (int k = 0; k < C; ++k)
-        if (proto_sums[(int64_t)k * (D + 1) + D] > 0.0) pl->valid_class[nv++] = k;
-    for (int k = nv; k < ARCO_MAX_CLASSES; ++k) pl->valid_class[k] = -1;
+        if (proto_sums[(int64_t)k * (D + 1) + D] > 0.0) { changed |= pl->valid_class[nv] != k; pl->valid_class[nv++] = k; }
+    for (int k = nv; k < ARCO_MAX_CLASSES; ++k) { changed |= pl->valid_class[k] != -1; pl->valid_class[k] = -1; }
     pl->n_valid = nv;
     for (int pos = 0; pos < ARCO_MAX_CLASSES; ++pos) {
         int active = 0;
@@ -129,9 +131,11 @@ __global__ void replan_global_kernel(arco_plan* pl, const double* __restrict__ p
             const int bank_cls = pl->valid_class[pos];
             active = (pl->n_anchor[pos] > 0 && pl->bank_len[bank_cls] > 0) ? 1 : 0;
         }
+        changed |= pl->slot_active[pos] != active;
         pl->slot_active[pos] = active;
     }
     pl->inv_scale = nv > 1 ? 1.0f / ((float)Q * (float)nv) : 0.f;
+    pl->replanned = changed;                 // a speculative rank-local sampler run must be redone (arco_sample_if_replanned)
 }
 
 }  // namespace arco

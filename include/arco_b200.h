@@ -102,6 +102,8 @@ typedef struct arco_plan {
     uint32_t status;                         /* ARCO_ST_* bits                                        */
     uint32_t scan_done;                      /* internal tickets                                      */
     uint32_t loss_done;
+    uint32_t replanned;                      /* arco_replan_global changed valid_class / slot_active  */
+    uint32_t reserved;
 } arco_plan;
 
 /* Device-resident ring-buffer memory bank (replaces the CPU list memobank[c] = [tensor[n,D]],
@@ -162,6 +164,10 @@ ARCO_API int arco_sample(const arco_dims* dims, int32_t func, uint64_t seed, uin
 
 /* Stand-alone sampler: out[i] for i < shape drawn exactly like the reference sampler `func` called
  * with (high, shape).  Used by the drop-in sampler functions and the distribution tests. */
+/* Multi-GPU: the sampler may run speculatively on the rank-local plan while the prototype pass and the all-reduce are in
+   flight; after arco_replan_global this call redraws only if the global valid-class list changed the plan (device flag). */
+ARCO_API int arco_sample_if_replanned(const arco_dims* dims, int32_t func, uint64_t seed, uint64_t step, int32_t* idx_anchor,
+                                      int32_t* idx_neg, void* workspace, void* stream);
 ARCO_API int arco_sample_one(int32_t func, int64_t high, int64_t shape, uint64_t seed, uint64_t stream_id,
                     int32_t* out, void* scratch, int64_t scratch_bytes, void* stream);
 

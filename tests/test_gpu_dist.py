@@ -17,55 +17,68 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _scenario(scenario, rank, world, dev):
     import arco_b200
     import oracle
     from arco_b200.sharded import shard_batch
     from arco_b200.synth import CaseSpec, exact_case, make_bank
+    spec = CaseSpec("dist", 2, 2, 4, (32, 32), 16, queries=32, negatives=8, bank_init="fill:60",
+                    caps=[80, 70, 70, 70], label_mode="absent:3" if scenario == 0 else "iid", seed=31 + scenario)
+    x = exact_case(spec, 0)
+    mine = shard_batch(x, spec.n_lab, rank, world)
+    if scenario == 1 and rank == 0:
+        # class 1 lives on rank 1 only: rank 0's local valid list [0, 2, 3] differs from the global [0, 1, 2, 3], so its
+        # speculative rank-local sampler run must be redone after arco_replan_global (plan.replanned)
+        for key in ("label_l", "label_u"):
+            lab = mine[key].clone()
+            lab[:, 0] = lab[:, 0] | lab[:, 1]
+            lab[:, 1] = 0
+            mine[key] = lab
+    bank_g, ptr_g, caps = make_bank(spec)
+    bank_c, ptr_c, _ = make_bank(spec)
+    g = {k: v.to(dev) for k, v in mine.items()}
+    rep_g = g["rep"].clone().requires_grad_(True)
+    dbg = {}
+    nk, loss = arco_b200.compute_contra_memobank_loss(
+        rep_g, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"], g["low_mask"], g["high_mask"],
+        bank_g, ptr_g, caps, g["rep_teacher"], delta_n=0.97, func="smc", num_queries=spec.queries,
+        num_negatives=spec.negatives, process_group=dist.group.WORLD, seed=5, _debug=dbg)
+    loss.backward()
+    torch.cuda.synchronize()
+    arco_b200.synchronize_bank(bank_g)
+    plan = bank_g[0].bank.last_plan
+    active = [j for j in range(spec.classes) if plan.slot_active[j]]
+    replay = []
+    for j in active:
+        replay += [dbg["idx_anchor"][j].long().cpu(), dbg["idx_neg"][j, : spec.queries * spec.negatives].long().cpu()]
+    it = iter(replay)
+    glob = dbg["proto_sums"].cpu()                        # all-reduced on the device
+
+    rep_c = mine["rep"].clone().requires_grad_(True)
+    res = oracle.contra_memobank_loss(
+        rep_c, mine["label_l"], mine["label_u"], mine["prob_l"], mine["prob_u"], mine["low_mask"], mine["high_mask"],
+        bank_c, ptr_c, caps, mine["rep_teacher"], delta_n=0.97, sampler=lambda h, s: next(it),
+        num_queries=spec.queries, num_negatives=spec.negatives, proto_sum_hook=lambda local: glob.clone())
+    res.loss.backward()
+    nv = int(plan.n_valid)
+    ok = (
+        [int(plan.valid_class[i]) for i in range(nv)] == res.valid_classes
+        and list(nk) == res.new_keys
+        and abs(float(loss.detach()) - float(res.loss.detach())) <= 1e-5 * max(1.0, abs(float(res.loss.detach())))
+        and float((rep_g.grad.cpu() - rep_c.grad).norm() / rep_c.grad.norm()) <= 1e-5
+    )
+    return dict(ok=bool(ok), loss=float(loss.detach()), oracle=float(res.loss.detach()), valid=res.valid_classes,
+                replanned=int(plan.replanned))
+
+
+def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dev = torch.device("cuda", rank)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        spec = CaseSpec("dist", 2, 2, 4, (32, 32), 16, queries=32, negatives=8, bank_init="fill:60",
-                        caps=[80, 70, 70, 70], label_mode="absent:3", seed=31)
-        x = exact_case(spec, 0)
-        mine = shard_batch(x, spec.n_lab, rank, world)
-        bank_g, ptr_g, caps = make_bank(spec)
-        bank_c, ptr_c, _ = make_bank(spec)
-        g = {k: v.to(dev) for k, v in mine.items()}
-        rep_g = g["rep"].clone().requires_grad_(True)
-        dbg = {}
-        nk, loss = arco_b200.compute_contra_memobank_loss(
-            rep_g, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"], g["low_mask"], g["high_mask"],
-            bank_g, ptr_g, caps, g["rep_teacher"], delta_n=0.97, func="smc", num_queries=spec.queries,
-            num_negatives=spec.negatives, process_group=dist.group.WORLD, seed=5, _debug=dbg)
-        loss.backward()
-        torch.cuda.synchronize()
-        arco_b200.synchronize_bank(bank_g)
-        plan = bank_g[0].bank.last_plan
-        active = [j for j in range(spec.classes) if plan.slot_active[j]]
-        replay = []
-        for j in active:
-            replay += [dbg["idx_anchor"][j].long().cpu(), dbg["idx_neg"][j, : spec.queries * spec.negatives].long().cpu()]
-        it = iter(replay)
-        glob = dbg["proto_sums"].cpu()                        # all-reduced on the device
-
-        rep_c = mine["rep"].clone().requires_grad_(True)
-        res = oracle.contra_memobank_loss(
-            rep_c, mine["label_l"], mine["label_u"], mine["prob_l"], mine["prob_u"], mine["low_mask"], mine["high_mask"],
-            bank_c, ptr_c, caps, mine["rep_teacher"], delta_n=0.97, sampler=lambda h, s: next(it),
-            num_queries=spec.queries, num_negatives=spec.negatives, proto_sum_hook=lambda local: glob.clone())
-        res.loss.backward()
-        nv = int(plan.n_valid)
-        ok = (
-            [int(plan.valid_class[i]) for i in range(nv)] == res.valid_classes
-            and list(nk) == res.new_keys
-            and abs(float(loss) - float(res.loss)) <= 1e-5 * max(1.0, abs(float(res.loss)))
-            and float((rep_g.grad.cpu() - rep_c.grad).norm() / rep_c.grad.norm()) <= 1e-5
-        )
-        out[rank] = dict(ok=bool(ok), loss=float(loss), oracle=float(res.loss), valid=res.valid_classes)
+        out[rank] = [_scenario(sc, rank, world, dev) for sc in range(2)]
     finally:
         dist.destroy_process_group()
 
@@ -78,5 +91,8 @@ def test_two_gpu_sharded_loss_matches_oracle():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         res = dict(out)
-    assert all(res[r]["ok"] for r in range(world)), res
-    assert res[0]["valid"] == res[1]["valid"]
+    for sc in range(2):
+        assert all(res[r][sc]["ok"] for r in range(world)), res
+        assert res[0][sc]["valid"] == res[1][sc]["valid"]
+    assert res[0][0]["replanned"] == 0 and res[1][0]["replanned"] == 0          # same valid list everywhere
+    assert res[0][1]["replanned"] == 1 and res[0][1]["valid"] == [0, 1, 2, 3]    # rank 0 had to redraw
