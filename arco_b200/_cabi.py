@@ -70,7 +70,9 @@ class StepIO(C.Structure):
         "momentum_on", "proto_out")] + [
         ("seed", C.c_uint64), ("step", C.c_uint64),
         ("delta_p", C.c_float), ("delta_n", C.c_float), ("temp", C.c_float), ("ema_decay", C.c_float),
-        ("low_rank", C.c_int32), ("high_rank", C.c_int32), ("func", C.c_int32), ("reserved", C.c_int32)]
+        ("low_rank", C.c_int32), ("high_rank", C.c_int32), ("func", C.c_int32), ("reserved", C.c_int32),
+        ("exchange_peers", C.c_void_p), ("exchange_local", C.c_void_p), ("exchange_seq", C.c_uint64),
+        ("exchange_slot", C.c_int64), ("exchange_rank", C.c_int32), ("exchange_world", C.c_int32)]
 
 
 def _load():
@@ -91,6 +93,7 @@ def _load():
         "arco_replan_global": (C.c_int, [dp, vp, vp, vp]),
         "arco_proto_enqueue": (C.c_int, [dp, vp, bp, vp, vp, vp]),
         "arco_sample": (C.c_int, [dp, i32, u64, u64, vp, vp, vp, vp]),
+        "arco_proto_allreduce_p2p": (C.c_int, [dp, vp, i32, i32, u64, i64, vp, vp, vp]),
         "arco_sample_if_replanned": (C.c_int, [dp, i32, u64, u64, vp, vp, vp, vp]),
         "arco_sample_one": (C.c_int, [i32, i64, i64, u64, u64, vp, vp, i64, vp]),
         "arco_infonce": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),

@@ -84,6 +84,44 @@ def _side_stream(dev: torch.device, which: int = 0) -> torch.cuda.Stream:
     return st
 
 
+_P2P = {}                # (group id, device index, n) -> peer-mapped exchange buffer state, or None when unavailable
+P2P_EXCHANGE_USED = False
+
+
+def _p2p_exchange(group, dev: torch.device, n: int):
+    """Symmetric (peer-mapped) buffer for the one exchange step of the multi-GPU path, created once per
+    (process group, device, C*(D+1)).  Returns None -- the caller then uses an NCCL all-reduce -- when torch's symmetric
+    memory cannot map the peers (no NVLink/P2P, older torch) or ``ARCO_P2P_ALLREDUCE=0``."""
+    key = (id(group), dev.index, n)
+    if key in _P2P:
+        return _P2P[key]
+    state = None
+    if os.environ.get("ARCO_P2P_ALLREDUCE", "1") != "0":
+        try:
+            import torch.distributed._symmetric_memory as symm
+            world = torch.distributed.get_world_size(group)
+            rank = torch.distributed.get_rank(group)
+            slot = (n + 63) // 64 * 64
+            buf = symm.empty(2 * slot + 64, dtype=torch.float64, device=dev)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) == world and all(ptrs):
+                torch.cuda.synchronize(dev)
+                torch.distributed.barrier(group)            # every rank's flags are zero before anyone signals
+                state = dict(buf=buf, hdl=hdl, rank=rank, world=world, slot=slot, seq=0,
+                             peers=torch.tensor(ptrs, dtype=torch.int64, device=dev))
+        except Exception:                                   # noqa: BLE001 -- any failure means "use NCCL"
+            state = None
+        # the decision must be the same on every rank: the exchange is a collective
+        flag = torch.tensor([1 if state is not None else 0], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            state = None
+    _P2P[key] = state
+    return state
+
+
 def _flat(t: torch.Tensor, lead: int) -> torch.Tensor:
     """Contiguous view with the trailing spatial axes flattened (``lead`` leading axes kept)."""
     t = t.contiguous()
@@ -99,8 +137,11 @@ class _ContraLoss(torch.autograd.Function):
         sp = stream.cuda_stream
         lib = _cabi.lib
         layout = st["layout"]
-        if st["inject"] is None and st["group"] is None and st["debug"] is None:
-            return _ContraLoss._forward_fused(ctx, rep, st, dims, bank, layout, dev, sp)
+        if st["inject"] is None and st["debug"] is None:
+            # one FFI call; multi-GPU too when the exchange buffer could be peer-mapped (no NCCL call between the stages)
+            p2p = _p2p_exchange(st["group"], dev, dims.classes * (dims.feat + 1)) if st["group"] is not None else None
+            if st["group"] is None or p2p is not None:
+                return _ContraLoss._forward_fused(ctx, rep, st, dims, bank, layout, dev, sp, p2p)
         ws = torch.empty(layout.total_bytes, dtype=torch.uint8, device=dev)
         wsp = ws.data_ptr()
         Cn, Q, N, D = dims.classes, dims.queries, dims.negatives, dims.feat
@@ -125,6 +166,12 @@ class _ContraLoss(torch.autograd.Function):
             DELTA_P, float(st["delta_n"]), LOW_RANK, HIGH_RANK, wsp, sp), "arco_classify_count")
         _cabi.check(lib.arco_scan_plan(d, b, wsp, sp), "arco_scan_plan")
         proto_sums = torch.empty((Cn, D + 1), dtype=torch.float64, device=dev)
+        p2p = _p2p_exchange(st["group"], dev, Cn * (D + 1)) if st["group"] is not None else None
+        proto_local = proto_sums                            # where the prototype kernel writes this rank's sums
+        if p2p is not None:
+            p2p["seq"] += 1
+            off = (p2p["seq"] & 1) * p2p["slot"]
+            proto_local = p2p["buf"][off: off + Cn * (D + 1)]
         idx_a = torch.empty((Cn, Q), dtype=torch.int32, device=dev)
         idx_n = torch.empty((Cn, Q * max(N, 1)), dtype=torch.int32, device=dev)
         plan_view = ws[layout.plan: layout.plan + C.sizeof(_cabi.Plan)]
@@ -137,11 +184,18 @@ class _ContraLoss(torch.autograd.Function):
             side.wait_stream(stream)
             _cabi.check(lib.arco_sample(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(), idx_n.data_ptr(),
                                         wsp, side.cuda_stream), "arco_sample")
-        _cabi.check(lib.arco_proto_enqueue(d, st["rep_teacher"].data_ptr(), b, proto_sums.data_ptr(), wsp, sp),
+        _cabi.check(lib.arco_proto_enqueue(d, st["rep_teacher"].data_ptr(), b, proto_local.data_ptr(), wsp, sp),
                     "arco_proto_enqueue")
         if group is not None:
             # the one exchange step of the path: C*(D+1) fp64 sums + counts
-            torch.distributed.all_reduce(proto_sums, group=group)
+            if p2p is not None:
+                global P2P_EXCHANGE_USED
+                P2P_EXCHANGE_USED = True
+                _cabi.check(lib.arco_proto_allreduce_p2p(d, p2p["peers"].data_ptr(), p2p["rank"], p2p["world"], p2p["seq"],
+                                                         p2p["slot"], proto_sums.data_ptr(), wsp, sp),
+                            "arco_proto_allreduce_p2p")
+            else:
+                torch.distributed.all_reduce(proto_sums, group=group)
             if side is not None:
                 stream.wait_stream(side)                    # the speculative sampler has read the local plan
             _cabi.check(lib.arco_replan_global(d, proto_sums.data_ptr(), wsp, sp), "arco_replan_global")
@@ -208,7 +262,7 @@ class _ContraLoss(torch.autograd.Function):
         return loss.reshape(())
 
     @staticmethod
-    def _forward_fused(ctx, rep, st, dims, bank, layout, dev, sp):
+    def _forward_fused(ctx, rep, st, dims, bank, layout, dev, sp, p2p=None):
         """Production path: one allocation, one FFI call (arco_forward), no tensor views besides the loss."""
         Cn, Q, N, D = dims.classes, dims.queries, dims.negatives, dims.feat
         al = lambda n: (n + 255) & ~255
@@ -245,6 +299,14 @@ class _ContraLoss(torch.autograd.Function):
         io.seed, io.step = st["seed"], bank.step
         io.delta_p, io.delta_n, io.temp = DELTA_P, float(st["delta_n"]), float(st["temp"])
         io.low_rank, io.high_rank, io.func = LOW_RANK, HIGH_RANK, st["func"]
+        if p2p is not None:
+            global P2P_EXCHANGE_USED
+            P2P_EXCHANGE_USED = True
+            p2p["seq"] += 1
+            io.exchange_peers = p2p["peers"].data_ptr()
+            io.exchange_local = p2p["buf"].data_ptr() + (p2p["seq"] & 1) * p2p["slot"] * 8
+            io.exchange_seq, io.exchange_slot = p2p["seq"], p2p["slot"]
+            io.exchange_rank, io.exchange_world = p2p["rank"], p2p["world"]
         _cabi.check(_cabi.lib.arco_forward(C.byref(dims), C.byref(io), C.byref(bank.c_struct), base, sp), "arco_forward")
         plan_view = buf[layout.plan: layout.plan + C.sizeof(_cabi.Plan)]
         bank.post_step(plan_view)

@@ -1,4 +1,4 @@
-// One-call forward of the whole path (single GPU): classify -> scan/plan -> [sampler on a side stream] ->
+// One-call forward of the whole path (single GPU, or one batch shard with the peer-memory exchange step): classify -> scan/plan -> [sampler on a side stream] ->
 // prototype + enqueue -> InfoNCE, plus the optional early zero fill of grad_rep on a second side stream.
 // Same kernels and order as driving the stage entry points one by one (arco_b200/contra.py does that when an
 // all-reduce or injected indices sit between the stages); this entry exists to keep the host cost of a step at one
@@ -57,8 +57,22 @@ extern "C" int arco_forward(const arco_dims* dims, const arco_step_io* io, const
     if ((rc = arco_sample(dims, io->func, io->seed, io->step, io->idx_anchor, io->idx_neg, workspace, ss->s[0])) != ARCO_OK)
         return rc;
     ARCO_CUDA_CHECK(cudaEventRecord(ss->join_sample, ss->s[0]));
-    if ((rc = arco_proto_enqueue(dims, io->rep_teacher, bank, io->proto_sums, workspace, main_st)) != ARCO_OK) return rc;
-    ARCO_CUDA_CHECK(cudaStreamWaitEvent(main_st, ss->join_sample, 0));
+    const bool sharded = io->exchange_peers != nullptr;
+    ARCO_REQUIRE(!sharded || io->exchange_local, "arco_forward: exchange_local is NULL");
+    if ((rc = arco_proto_enqueue(dims, io->rep_teacher, bank, sharded ? io->exchange_local : io->proto_sums, workspace, main_st)) != ARCO_OK)
+        return rc;
+    if (sharded) {
+        // the one exchange step: global (feature sum, count) per class, then the valid-class list from the GLOBAL counts
+        if ((rc = arco_proto_allreduce_p2p(dims, io->exchange_peers, io->exchange_rank, io->exchange_world, io->exchange_seq,
+                                           io->exchange_slot, io->proto_sums, workspace, main_st)) != ARCO_OK)
+            return rc;
+        ARCO_CUDA_CHECK(cudaStreamWaitEvent(main_st, ss->join_sample, 0));    // the speculative sampler has read the local plan
+        if ((rc = arco_replan_global(dims, io->proto_sums, workspace, main_st)) != ARCO_OK) return rc;
+        if ((rc = arco_sample_if_replanned(dims, io->func, io->seed, io->step, io->idx_anchor, io->idx_neg, workspace, main_st)) != ARCO_OK)
+            return rc;
+    } else {
+        ARCO_CUDA_CHECK(cudaStreamWaitEvent(main_st, ss->join_sample, 0));
+    }
     if (io->momentum)
         rc = arco_infonce_ema(dims, io->rep, bank, io->proto_sums, io->idx_anchor, io->idx_neg, io->temp, io->loss,
                               io->grad_anchor, io->anchor_pix, io->logits, io->momentum, io->momentum_on, io->ema_decay,

@@ -313,7 +313,7 @@ def main_ours(args):
                 "classes": spec.classes, "spatial": list(spec.spatial), "feat": spec.feat, "rep_storage": spec.dtype,
                 "queries": spec.queries, "negatives": spec.negatives, "func": args.func,
                 "labels": "blocky16" if args.blocky else "iid", "banks": ("cold: the trainers' initial one-row banks" if COLD_BANK else "pre-filled to capacity (50000/30000 rows)") + (", bf16-exact rows in a bf16 ring" if spec.dtype == "bf16" else ", fp32 ring"),
-                "pixels_per_gpu": P, "parallelism": f"batch-shard x{world}, 1 all-reduce of C*(D+1) fp64" if world > 1 else "single GPU",
+                "pixels_per_gpu": P, "parallelism": (f"batch-shard x{world}, 1 exchange of C*(D+1) fp64 (" + ("own kernel over NVLink peer memory" if __import__("arco_b200.contra", fromlist=["x"]).P2P_EXCHANGE_USED else "NCCL all-reduce") + ")") if world > 1 else "single GPU",
                 "l2": l2_note, "timing": "CUDA events per step on the launching stream, max over ranks",
             },
             "clocks": clk, "gpu_launches": args.steps * (KERNELS_PER_STEP + (1 if world > 1 else 0)),

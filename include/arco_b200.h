@@ -166,6 +166,14 @@ ARCO_API int arco_sample(const arco_dims* dims, int32_t func, uint64_t seed, uin
  * with (high, shape).  Used by the drop-in sampler functions and the distribution tests. */
 /* Multi-GPU: the sampler may run speculatively on the rank-local plan while the prototype pass and the all-reduce are in
    flight; after arco_replan_global this call redraws only if the global valid-class list changed the plan (device flag). */
+/* Multi-GPU exchange step over NVLink peer memory instead of an NCCL all-reduce.  Every rank's
+   arco_proto_enqueue writes its C*(D+1) fp64 sums into slot (seq & 1) of a buffer mapped into all peers (layout in doubles:
+   [slot 0: slot_doubles][slot 1: slot_doubles][flags: one u64 per source rank, at least `world`]); this call signals the
+   peers, waits for them and adds the W slots in rank order into proto_sums_out (bit-identical on every rank).
+   peer_base_dev: device array of `world` addresses of that buffer as mapped for each rank; seq: 1, 2, 3, ... per call. */
+ARCO_API int arco_proto_allreduce_p2p(const arco_dims* dims, const uint64_t* peer_base_dev, int32_t rank, int32_t world,
+                                      uint64_t seq, int64_t slot_doubles, double* proto_sums_out, void* workspace,
+                                      void* stream);
 ARCO_API int arco_sample_if_replanned(const arco_dims* dims, int32_t func, uint64_t seed, uint64_t step, int32_t* idx_anchor,
                                       int32_t* idx_neg, void* workspace, void* stream);
 ARCO_API int arco_sample_one(int32_t func, int64_t high, int64_t shape, uint64_t seed, uint64_t stream_id,
@@ -224,10 +232,19 @@ typedef struct arco_step_io {
     uint64_t       seed, step;     /* Philox seed / per-step stream id of the sampler                  */
     float          delta_p, delta_n, temp, ema_decay;
     int32_t        low_rank, high_rank, func, reserved;
+    /* multi-GPU (batch shards); exchange_peers == NULL means single GPU.  See
+       arco_proto_allreduce_p2p for the buffer layout. */
+    const uint64_t* exchange_peers;   /* device array [exchange_world]: the exchange buffer as mapped for every rank  */
+    double*        exchange_local;    /* this rank's slot (exchange_seq & 1) of it: the prototype kernel writes here   */
+    uint64_t       exchange_seq;      /* 1, 2, 3, ... per call                                                         */
+    int64_t        exchange_slot;     /* doubles per slot                                                              */
+    int32_t        exchange_rank, exchange_world;
 } arco_step_io;
 
-/* The whole single-GPU forward in one call (same kernels and order as the stage entry points; the sampler and the
- * optional grad_rep zero fill run on library-owned side streams and are joined with events, no host sync). */
+/* The whole forward in one call (same kernels and order as the stage entry points; the sampler and the optional grad_rep
+ * zero fill run on library-owned side streams and are joined with events, no host sync).  With exchange_peers set it is
+ * the batch-sharded multi-GPU step: prototype sums -> arco_proto_allreduce_p2p -> arco_replan_global ->
+ * arco_sample_if_replanned -> InfoNCE, still one call and no NCCL. */
 ARCO_API int arco_forward(const arco_dims* dims, const arco_step_io* io, const arco_bank* bank, void* workspace,
                           void* stream);
 
