@@ -9,12 +9,15 @@
 
 namespace arco {
 
-__global__ void __launch_bounds__(256) fill_zero_kernel(uint4* __restrict__ dst, int64_t n16, unsigned char* tail,
-                                                         int tail_bytes) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = z;
-    if (blockIdx.x == 0 && threadIdx.x < tail_bytes) tail[threadIdx.x] = 0;
+// One 256-bit store per thread, one wave after another (no grid-stride loop): measured on B200 for 1.56 GB
+// (scripts/probe/fill_probe.cu) 7430 GB/s, against 6424 for persistent 16-byte grid-stride stores and 7215 for cudaMemsetAsync.
+__global__ void __launch_bounds__(256) fill_zero_kernel(unsigned char* __restrict__ dst, int64_t n32, int head_bytes, int tail_bytes) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n32) asm volatile("st.global.v8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"l"(dst + head_bytes + i * 32), "r"(0) : "memory");
+    if (blockIdx.x == 0) {                                   // unaligned head / short tail, byte-wise
+        if (threadIdx.x < head_bytes) dst[threadIdx.x] = 0;
+        if (threadIdx.x < tail_bytes) dst[head_bytes + n32 * 32 + threadIdx.x] = 0;
+    }
 }
 
 template <typename T>
@@ -43,16 +46,16 @@ __global__ void __launch_bounds__(128) grad_scatter_kernel(const float* __restri
 }  // namespace arco
 
 static int launch_fill(const arco_dims& d, void* grad_rep, cudaStream_t st) {
-    ARCO_REQUIRE(((uintptr_t)grad_rep & 15) == 0, "grad_rep must be 16-byte aligned");
     const int64_t elems = ((int64_t)d.n_lab + d.n_unlab) * d.feat * d.space;
     const int64_t bytes = elems * (d.rep_dtype == ARCO_BF16 ? 2 : 4);
-    const int64_t n16 = bytes / 16;
-    const int tail = (int)(bytes - n16 * 16);
-    int64_t blocks = (n16 + 256 * 8 - 1) / (256 * 8);
-    const int64_t cap = (int64_t)arco::sm_count() * 16;
-    if (blocks > cap) blocks = cap;
+    int head = (int)((32 - ((uintptr_t)grad_rep & 31)) & 31);           // bytes up to the first 32-byte boundary
+    if (head > bytes) head = (int)bytes;
+    const int64_t n32 = (bytes - head) / 32;
+    const int tail = (int)(bytes - head - n32 * 32);
+    int64_t blocks = (n32 + 255) / 256;
     if (blocks < 1) blocks = 1;
-    arco::fill_zero_kernel<<<(int)blocks, 256, 0, st>>>((uint4*)grad_rep, n16, (unsigned char*)grad_rep + n16 * 16, tail);
+    ARCO_REQUIRE(blocks < (1ll << 31), "grad_rep too large for one fill launch");
+    arco::fill_zero_kernel<<<(unsigned)blocks, 256, 0, st>>>((unsigned char*)grad_rep, n32, head, tail);
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
 }
