@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
     const int RS16 = p.RS16;                                      // odd, and RS16*8 >= KS*16: the pad stays zero
     float* a_hat = reinterpret_cast<float*>(smem_raw);            // [D]
     float* k0hat = a_hat + D;                                     // [D]
-    uint2* asf = reinterpret_cast<uint2*>(k0hat + D);             // [KS][12]  A-fragment rows 8-10 (a_hat terms)
-    float* s_part = reinterpret_cast<float*>(asf + KS * 12);      // [2][4][16][2]  per-warp partial (dot, |k|^2)
+    uint2* asf = reinterpret_cast<uint2*>(k0hat + D);             // [KS][16]  A-fragment rows 8-10 (a_hat terms) + 4 zero slots
+    float* s_part = reinterpret_cast<float*>(asf + KS * 16);      // [2][4][16][2]  per-warp partial (dot, |k|^2)
     uint4* stage = reinterpret_cast<uint4*>(s_part + 2 * 4 * MMA_KEYS * 2);   // [NSTG][16 * RS16]; G after the loop
     __shared__ __align__(8) uint64_t bars[NSTG];
     __shared__ float s_red[4][2];
@@ -544,12 +544,14 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
         const float inv_temp = 1.f / p.temp;
         const float z0 = ai.cos0 * inv_temp;
         // A-fragment rows 8..10 of every k-step: lane (g < 3, t) holds terms g of a_hat[16ks + 2t, +1] and [.. + 8, + 9]
-        for (int i = tid; i < KS * 12; i += 128) {
-            const int ks = i / 12, gg = (i % 12) >> 2, tt = i & 3;
+        // (slots 12..15 of a k-step are zero: the rows 11..15 of the A operand, read by the lanes with g >= 3)
+        for (int i = tid; i < KS * 16; i += 128) {
+            const int ks = i >> 4, gg = (i & 15) >> 2, tt = i & 3;
             const int d0 = 16 * ks + 2 * tt;
             auto av = [&](int d) { return d < D ? a_hat[d] : 0.f; };
-            asf[i] = make_uint2(bf16_term(av(d0), gg) | (bf16_term(av(d0 + 1), gg) << 16),
-                                bf16_term(av(d0 + 8), gg) | (bf16_term(av(d0 + 9), gg) << 16));
+            asf[i] = gg < 3 ? make_uint2(bf16_term(av(d0), gg) | (bf16_term(av(d0 + 1), gg) << 16),
+                                         bf16_term(av(d0 + 8), gg) | (bf16_term(av(d0 + 9), gg) << 16))
+                            : make_uint2(0u, 0u);
         }
         __syncthreads();
 
@@ -558,7 +560,7 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
         // ldmatrix lane address inside a stage: matrix i = lane >> 3 -> keys (i >> 1) * 8 + (lane & 7), dims + (i & 1) * 8
         const uint32_t lm_base = smem_u32(stage) +
                                  (uint32_t)(((lane >> 4) * 8 + (lane & 7)) * RS16 + ((lane >> 3) & 1) + 2 * ks_begin) * 16u;
-        const uint2* af_ptr = asf + ks_begin * 12 + (g < 3 ? g * 4 + t : 0);
+        const uint2* af_ptr = asf + ks_begin * 16 + (g < 3 ? g * 4 + t : 12 + t);
         float acc[8][4];
 #pragma unroll
         for (int m = 0; m < 8; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
@@ -576,8 +578,7 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
                 if (m < nks) {
                     uint32_t r[4];
                     ldsm_x4(r, sbase + (uint32_t)m * 32u);
-                    uint2 af = af_ptr[m * 12];
-                    if (g >= 3) af = make_uint2(0u, 0u);
+                    const uint2 af = af_ptr[m * 16];
                     mma_bf16_16816(c0, r[0], af.x, r[1], af.y, r[0], r[1]);
                     mma_bf16_16816(c1, r[2], af.x, r[3], af.y, r[2], r[3]);
                 }
@@ -613,14 +614,25 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
                 S2_lane += e * cosv;
                 if (p.logits && valid) p.logits[((int64_t)j * p.Q + q) * (1 + p.N) + 1 + c * MMA_KEYS + key] = cosv;
             }
-            // B fragment of pass 2: column g (< 3) = term g of the weights of keys (2t, 2t+1) and (2t+8, 2t+9)
-            const float w0 = __shfl_sync(0xffffffffu, coef, 2 * t), w1 = __shfl_sync(0xffffffffu, coef, 2 * t + 1);
-            const float w2 = __shfl_sync(0xffffffffu, coef, 2 * t + 8), w3 = __shfl_sync(0xffffffffu, coef, 2 * t + 9);
-            uint32_t b0 = 0u, b1 = 0u;
-            if (g < 3) {
-                b0 = bf16_term(w0, g) | (bf16_term(w1, g) << 16);
-                b1 = bf16_term(w2, g) | (bf16_term(w3, g) << 16);
+            // B fragment of pass 2: column g (< 3) = term g of the weights of keys (2t, 2t+1) and (2t+8, 2t+9).
+            // Every lane splits its own key's weight once; lanes 0-15 publish (hi | mid << 16), their mirrors 16-31 publish lo,
+            // so one shuffle per key fetches the term a lane's column needs.
+            uint32_t wpub;
+            {
+                const float hi = __bfloat162float(__float2bfloat16_rn(coef));
+                const float r1 = coef - hi;
+                const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+                const float lo = __bfloat162float(__float2bfloat16_rn(r1 - mid));
+                wpub = lane < MMA_KEYS ? ((__float_as_uint(hi) >> 16) | (__float_as_uint(mid) & 0xffff0000u)) : (__float_as_uint(lo) >> 16);
             }
+            const int src_hi = g == 2 ? MMA_KEYS : 0;
+            const uint32_t sh = g == 1 ? 16u : 0u;
+            const uint32_t u0 = (__shfl_sync(0xffffffffu, wpub, 2 * t + src_hi) >> sh) & 0xffffu;
+            const uint32_t u1 = (__shfl_sync(0xffffffffu, wpub, 2 * t + 1 + src_hi) >> sh) & 0xffffu;
+            const uint32_t u2 = (__shfl_sync(0xffffffffu, wpub, 2 * t + 8 + src_hi) >> sh) & 0xffffu;
+            const uint32_t u3 = (__shfl_sync(0xffffffffu, wpub, 2 * t + 9 + src_hi) >> sh) & 0xffffu;
+            const uint32_t b0 = g < 3 ? (u0 | (u1 << 16)) : 0u;
+            const uint32_t b1 = g < 3 ? (u2 | (u3 << 16)) : 0u;
             // ---- pass 2: G[dims of this warp] += K^T . W ----
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
@@ -740,7 +752,7 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
         p.RS16 = r16; p.KC = arco::MMA_KEYS;
         size_t stage_bytes = (size_t)nstg * arco::MMA_KEYS * r16 * 16;
         if (stage_bytes < (size_t)ks * 64) stage_bytes = (size_t)ks * 64;   // G[16*ks] lives there after the loop
-        const size_t sm = (size_t)2 * d.feat * 4 + (size_t)ks * 12 * 8 + 2 * 4 * arco::MMA_KEYS * 2 * 4 + stage_bytes;
+        const size_t sm = (size_t)2 * d.feat * 4 + (size_t)ks * 16 * 8 + 2 * 4 * arco::MMA_KEYS * 2 * 4 + stage_bytes;
         if (nstg == 1) {
             ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             arco::infonce_mma_kernel<1><<<grid, 128, sm, st>>>(p);
