@@ -31,7 +31,9 @@ LOW_RANK, HIGH_RANK = 3, 20    # loss_helper_3d.py:318
 _FUNC = {"smc": _cabi.FUNC_SMC, "asmc": _cabi.FUNC_ASMC}
 _GEOMETRY = {}                 # problem shape -> (arco_dims, workspace layout)
 _PREFILL_GRAD = os.environ.get("ARCO_PREFILL_GRAD", "1") != "0"   # zero-fill grad_rep during forward (side stream)
-_PREFILL_MIN_BYTES = 512 << 20
+# measured: pays from ~250 MB of rep (la3d 0.232 -> 0.218 ms), costs at 134 MB (acdc2d_loss 0.155 -> 0.181 ms: the extra side-stream
+# launches outweigh a 25 us fill)
+_PREFILL_MIN_BYTES = int(os.environ.get("ARCO_PREFILL_MIN_MB", "192")) << 20
 
 
 class LazyKeys(list):
