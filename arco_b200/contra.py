@@ -94,7 +94,7 @@ def _p2p_exchange(group, dev: torch.device, n: int):
     """Symmetric (peer-mapped) buffer for the one exchange step of the multi-GPU path, created once per
     (process group, device, C*(D+1)).  Returns None -- the caller then uses an NCCL all-reduce -- when torch's symmetric
     memory cannot map the peers (no NVLink/P2P, older torch) or ``ARCO_P2P_ALLREDUCE=0``."""
-    key = (id(group), dev.index, n)
+    key = (getattr(group, "group_name", None) or id(group), dev.index, n)
     if key in _P2P:
         return _P2P[key]
     state = None
