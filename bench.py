@@ -215,8 +215,11 @@ def main_ours(args):
     group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
+        # stdout carries exactly one JSON line: NCCL's version banner (printed at the VERSION and WARN debug levels) and any
+        # other NCCL log text go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]               # the banner ignores NCCL_DEBUG_FILE; unset prints nothing (verified)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
