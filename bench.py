@@ -419,6 +419,11 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
             "bytes_formula": "P_lv*D*e_t + K*D*(e_t+e_bank) + P  (SURVEY.md section 8(d) teacher-read and key terms + 1 code byte per pixel)",
             "note": "rep_teacher is channel-first, so every 32-byte sector that holds one low-valid pixel must be fetched: "
                     "with the iid 20% masks of this workload that is ALL of P*D*e_t; 'traffic' is the ncu-measured DRAM bytes"}
+    if traffic:
+        # the same launch against the DRAM bytes ncu counted for it (what the kernel really moved), next to the contract's
+        # algorithmic figure
+        roof["achieved_traffic"] = traffic / (ms[k] * 1e-3) / 1e9
+        roof["frac_traffic"] = roof["achieved_traffic"] / peak
     return stages, roof
 
 
