@@ -49,6 +49,9 @@ CASES = [
              label_mode="absent:1", momentum="rand", i_iter=7, seed=37),
     CaseSpec("momentum_zero", 2, 2, 4, (16, 16), 8, func="asmc", bank_init="fill:30", caps=[50, 30, 30, 30],
              momentum="zeros", i_iter=3, seed=41),
+    # far more queries than anchor candidates: every candidate is drawn many times, backward must accumulate (trap 8)
+    CaseSpec("dup_anchors", 1, 1, 4, (8, 8), 8, queries=64, negatives=4, func="smc", bank_init="fill:12",
+             caps=[20, 20, 20, 20], seed=43),
     # bf16 representation tensors (config 2); compared at bf16 tolerance
     CaseSpec("bf16_rep", 2, 2, 4, (16, 16), 16, func="smc", bank_init="fill:25",
              caps=[40, 40, 40, 40], dtype="bf16", seed=29),
