@@ -14,7 +14,7 @@ TILE = 1024
 F32, BF16 = 0, 1
 LABEL_ONEHOT_I64, LABEL_INDEX_I64 = 0, 1
 FUNC_UNIFORM, FUNC_SMC, FUNC_ASMC = 0, 1, 2
-ST_MULTI_HOT, ST_LABEL_RANGE = 1, 2
+ST_MULTI_HOT, ST_LABEL_RANGE, ST_INDEX_RANGE, ST_KEYS_DROPPED, ST_EXCHANGE_TIMEOUT = 1, 2, 4, 8, 0x80000000
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ARCO_B200_LIB") or os.path.join(_HERE, "lib", "libarco_b200.so")   # override: A/B builds
@@ -60,6 +60,7 @@ class Bank(C.Structure):
     _fields_ = [
         ("rows", C.c_void_p), ("head", C.c_void_p), ("len", C.c_void_p), ("queue_ptr", C.c_void_p),
         ("cap", _I32x), ("row_off", _I64x), ("row_dtype", C.c_int32), ("reserved", C.c_int32),
+        ("host_mirror", C.c_void_p), ("mirror_seq", C.c_uint64),
     ]
 
 
@@ -70,7 +71,7 @@ class StepIO(C.Structure):
         "momentum_on", "proto_out")] + [
         ("seed", C.c_uint64), ("step", C.c_uint64),
         ("delta_p", C.c_float), ("delta_n", C.c_float), ("temp", C.c_float), ("ema_decay", C.c_float),
-        ("low_rank", C.c_int32), ("high_rank", C.c_int32), ("func", C.c_int32), ("reserved", C.c_int32),
+        ("low_rank", C.c_int32), ("high_rank", C.c_int32), ("func", C.c_int32), ("ema_keep", C.c_float),
         ("exchange_peers", C.c_void_p), ("exchange_local", C.c_void_p), ("exchange_seq", C.c_uint64),
         ("exchange_slot", C.c_int64), ("exchange_rank", C.c_int32), ("exchange_world", C.c_int32)]
 
@@ -97,10 +98,11 @@ def _load():
         "arco_sample_if_replanned": (C.c_int, [dp, i32, u64, u64, vp, vp, vp, vp]),
         "arco_sample_one": (C.c_int, [i32, i64, i64, u64, u64, vp, vp, i64, vp]),
         "arco_infonce": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
-        "arco_infonce_ema": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp]),
+        "arco_infonce_ema": (C.c_int, [dp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
         "arco_grad_scatter": (C.c_int, [dp, vp, vp, vp, vp, vp]),
         "arco_grad_zero": (C.c_int, [dp, vp, vp]),
         "arco_grad_scatter_add": (C.c_int, [dp, vp, vp, vp, vp, vp]),
+        "arco_grad_scatter_sparse": (C.c_int, [dp, vp, vp, vp, vp, vp, vp]),
         "arco_forward": (C.c_int, [dp, C.POINTER(StepIO), bp, vp, vp]),
         "arco_export_list": (C.c_int, [dp, i32, i32, vp, i64, vp, vp, vp]),
         "arco_bank_read": (C.c_int, [bp, i32, i32, vp, vp]),

@@ -20,8 +20,9 @@ back to fp32 -- values never change.  ``ARCO_BANK_BF16=0`` forces fp32 storage.
 The caller's lists are adopted lazily on the first call: ``memobank[c]`` is replaced by a
 :class:`BankSlot` (a ``list`` subclass) whose element 0 still answers ``.shape[0]`` and row indexing in
 logical FIFO order, and ``queue_ptrlis[c][0]`` is refreshed from the device bookkeeping whenever the
-host mirror is refreshed (:meth:`DeviceMemoryBank.poll`, non-blocking, at the start of the next step;
-:meth:`DeviceMemoryBank.settle`, blocking, on any inspection).
+host mirror is refreshed: the last CTA of every step stores its ``arco_plan`` into a pinned, PCIe-mapped ring (zero-copy) and
+:meth:`DeviceMemoryBank.poll` (non-blocking, called at the start of the next step) applies the plans that have landed, so the pointer is normally one step late and never stale by more than the steps still in flight;
+:meth:`DeviceMemoryBank.settle` (blocking) is used on any inspection.
 """
 from __future__ import annotations
 
@@ -109,6 +110,10 @@ class DeviceMemoryBank:
         self._queue_ptrlis = queue_ptrlis
         self._plan_view = None          # device view of the last step's arco_plan
         self._dirty = False
+        self._edited = False            # rows replaced by the caller since the last settle: pending plans are stale
+        self._mirror = torch.zeros(self._MIRROR_SLOTS * self._MIRROR_STRIDE, dtype=torch.uint8, pin_memory=True)
+        self._mirror_np = self._mirror.numpy()
+        self._applied = 0               # last step number whose mirrored plan was applied (or skipped)
         self.last_plan: Optional[_cabi.Plan] = None
         self.step = 0
         self.c_struct = _cabi.Bank()
@@ -154,15 +159,57 @@ class DeviceMemoryBank:
         self.c_struct.row_dtype = _cabi.F32
 
     # ------------------------------------------------------------------ host mirror
+    _MIRROR_SLOTS = 8          # ring of pinned plan copies: the host may run this many steps ahead of the device
+    _MIRROR_STRIDE = 1536      # bytes per slot: arco_plan (1440 B) + u64 sequence number at offset sizeof(arco_plan)
+
+    def begin_step(self) -> None:
+        """Point the step about to be launched at its slot of the pinned mirror ring.  The LAST CTA of the step's
+        InfoNCE kernel stores the final ``arco_plan`` there through the PCIe-mapped address and then the step number
+        (zero-copy: no memcpy, no event, nothing on the stream), which is how ``queue_prtlis``, the bank lengths and the
+        label-error status reach the host without the step ever synchronising (see :meth:`poll`)."""
+        seq = self.step + 1
+        self.c_struct.host_mirror = self._mirror.data_ptr() + (seq % self._MIRROR_SLOTS) * self._MIRROR_STRIDE
+        self.c_struct.mirror_seq = seq
+
     def post_step(self, plan_view: torch.Tensor) -> None:
         """Remember the step's device-resident ``arco_plan`` (a view into its workspace); nothing is copied."""
         self._plan_view = plan_view
         self._dirty = True
+        self._edited = False
         self.step += 1
 
+    def _apply(self, plan: "_cabi.Plan", step: int) -> None:
+        for c in range(self.classes):
+            self.host_len[c] = int(plan.bank_len[c])
+            self.host_ptr[c] = int(plan.queue_ptr[c])
+            self._queue_ptrlis[c][0] = self.host_ptr[c]
+        self.last_plan = plan
+        if step == self.step and not self._edited:
+            self._dirty = False
+        self.check_status(plan.status)
+
     def poll(self, block: bool = False) -> Optional[_cabi.Plan]:
-        """Kept for API symmetry: the host mirrors are refreshed on demand by :meth:`settle`."""
-        return self.settle() if block else self.last_plan
+        """Non-blocking refresh of the host mirrors: the plan of every step that has FINISHED on the device is applied
+        in order -- ``queue_prtlis[c][0]``, the bank lengths, and the status bits (invalid labels raise ``ValueError``
+        here, i.e. at the start of the first step after the offending one has completed).  Never waits for the device
+        unless ``block``."""
+        if block:
+            return self.settle()
+        n = C.sizeof(_cabi.Plan)
+        while self._applied < self.step:
+            s_no = self._applied + 1
+            off = (s_no % self._MIRROR_SLOTS) * self._MIRROR_STRIDE
+            seq = int(self._mirror_np[off + n: off + n + 8].view("<u8")[0])
+            if seq < s_no:
+                break                                             # that step has not finished yet
+            self._applied = s_no
+            if seq > s_no:
+                continue                                          # slot already reused by step s_no + k*SLOTS: skip
+            raw = self._mirror_np[off: off + n].tobytes()
+            if int(self._mirror_np[off + n: off + n + 8].view("<u8")[0]) != s_no:
+                continue                                          # overwritten while being read
+            self._apply(_cabi.Plan.from_buffer_copy(raw), s_no)
+        return self.last_plan
 
     @staticmethod
     def check_status(status: int) -> None:
@@ -170,6 +217,13 @@ class DeviceMemoryBank:
             raise ValueError("label_l/label_u are not one-hot: some pixel has more than one non-zero class entry")
         if status & _cabi.ST_LABEL_RANGE:
             raise ValueError("integer label map contains a class id >= num_classes")
+        if status & _cabi.ST_INDEX_RANGE:
+            raise ValueError("a sample index was outside its candidate list / memory bank (it was clamped on the device)")
+        if status & _cabi.ST_KEYS_DROPPED:
+            raise ValueError("negative keys were counted but not enqueued: the C<=3 register prototype kernel needs "
+                             "low_rank >= num_classes")
+        if status & _cabi.ST_EXCHANGE_TIMEOUT:
+            raise RuntimeError("multi-GPU prototype exchange timed out waiting for a peer")
 
     def settle(self) -> Optional[_cabi.Plan]:
         """Read the device bookkeeping (host sync) and refresh the host mirrors, including the caller's
@@ -178,6 +232,8 @@ class DeviceMemoryBank:
         if not self._dirty:
             return self.last_plan
         self._dirty = False
+        self._edited = False
+        self._applied = self.step                                 # mirrored plans are superseded by the synchronous read below
         lens = self.len.cpu().tolist()
         ptrs = self.ptr.cpu().tolist()
         for c in range(self.classes):
@@ -217,6 +273,7 @@ class DeviceMemoryBank:
         self.len[cls] = n
         self.host_len[cls] = n
         self._dirty = True
+        self._edited = True
 
 
 def synchronize_bank(memobank: list) -> None:

@@ -17,6 +17,7 @@ There is no CPU path and no PyTorch fallback: non-CUDA tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import logging
 import os
 from typing import List, Optional
 
@@ -88,21 +89,47 @@ def _side_stream(dev: torch.device, which: int = 0) -> torch.cuda.Stream:
 
 _P2P = {}                # (group id, device index, n) -> peer-mapped exchange buffer state, or None when unavailable
 P2P_EXCHANGE_USED = False
+EXCHANGE_PLANE = None    # "nvlink-p2p" | "nccl": which data plane the last multi-GPU step used (also logged once per group)
+_log = logging.getLogger("arco_b200")
+
+
+def _agree(flag: bool, group, dev: torch.device) -> bool:
+    """True iff ``flag`` is true on EVERY rank (one MIN all-reduce)."""
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
 
 
 def _p2p_exchange(group, dev: torch.device, n: int):
     """Symmetric (peer-mapped) buffer for the one exchange step of the multi-GPU path, created once per
     (process group, device, C*(D+1)).  Returns None -- the caller then uses an NCCL all-reduce -- when torch's symmetric
-    memory cannot map the peers (no NVLink/P2P, older torch) or ``ARCO_P2P_ALLREDUCE=0``."""
+    memory cannot map the peers (no NVLink/P2P, older torch) or ``ARCO_P2P_ALLREDUCE=0``.
+
+    The decision is a collective and is taken in two agreed phases so that no rank can be left alone inside a
+    rendezvous: (1) every rank reports whether it CAN try (env switch, symmetric-memory module importable, every peer
+    device reachable with ``can_device_access_peer``) and only if all can do they enter ``symm.empty``/``rendezvous``;
+    (2) every rank reports whether the mapping succeeded.  Only the expected failure types are caught."""
+    global EXCHANGE_PLANE
     key = (getattr(group, "group_name", None) or id(group), dev.index, n)
     if key in _P2P:
         return _P2P[key]
-    state = None
-    if os.environ.get("ARCO_P2P_ALLREDUCE", "1") != "0":
+    world = torch.distributed.get_world_size(group)
+    rank = torch.distributed.get_rank(group)
+    symm, why = None, ""
+    if os.environ.get("ARCO_P2P_ALLREDUCE", "1") == "0":
+        why = "ARCO_P2P_ALLREDUCE=0"
+    else:
         try:
-            import torch.distributed._symmetric_memory as symm
-            world = torch.distributed.get_world_size(group)
-            rank = torch.distributed.get_rank(group)
+            import torch.distributed._symmetric_memory as symm          # noqa: WPS433
+        except ImportError as e:
+            why = f"torch symmetric memory unavailable ({e})"
+        if symm is not None:
+            ndev = torch.cuda.device_count()
+            if not all(torch.cuda.can_device_access_peer(dev.index, o) for o in range(ndev) if o != dev.index):
+                symm, why = None, "a peer GPU is not P2P-accessible"
+    state = None
+    if _agree(symm is not None, group, dev):
+        try:
             slot = (n + 63) // 64 * 64
             buf = symm.empty(2 * slot + 64, dtype=torch.float64, device=dev)
             buf.zero_()
@@ -113,15 +140,53 @@ def _p2p_exchange(group, dev: torch.device, n: int):
                 torch.distributed.barrier(group)            # every rank's flags are zero before anyone signals
                 state = dict(buf=buf, hdl=hdl, rank=rank, world=world, slot=slot, seq=0,
                              peers=torch.tensor(ptrs, dtype=torch.int64, device=dev))
-        except Exception:                                   # noqa: BLE001 -- any failure means "use NCCL"
+            else:
+                why = "rendezvous returned an incomplete peer pointer table"
+        except (RuntimeError, ValueError, AttributeError, TypeError) as e:
+            why = f"symmetric-memory rendezvous failed: {e}"
+        if not _agree(state is not None, group, dev):
             state = None
-        # the decision must be the same on every rank: the exchange is a collective
-        flag = torch.tensor([1 if state is not None else 0], dtype=torch.int32, device=dev)
-        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
-        if int(flag.item()) == 0:
-            state = None
+            why = why or "a peer could not map the exchange buffer"
+    elif not why:
+        why = "another rank cannot use peer memory"
+    EXCHANGE_PLANE = "nvlink-p2p" if state is not None else "nccl"
+    if rank == 0:
+        _log.info("arco_b200 multi-GPU exchange (C*(D+1)=%d fp64, world %d): %s%s", n, world,
+                  "own kernel over NVLink peer memory" if state is not None else "NCCL all-reduce",
+                  "" if state is not None else f" ({why})")
     _P2P[key] = state
     return state
+
+
+def _sampler_stream(seed, bank: DeviceMemoryBank, dev: torch.device):
+    """(Philox seed, per-step stream id) of the in-kernel sampler.
+
+    Explicit ``seed=``: deterministic replay -- stream id = number of steps this bank has seen (tests, benchmarks).
+    Default: behave like the reference, which CONSUMES global RNG state (Python ``random`` + torch's CPU generator,
+    loss_helper_3d.py:157-177): the seed is torch's CUDA seed mixed with the process's distributed rank (DDP ranks seeded
+    alike must not draw identical index streams), and the stream id is taken from -- and advances -- the device's
+    default CUDA generator offset, so a resumed run that restores (or re-seeds) torch's RNG state continues (or
+    replays) exactly like the reference would, instead of restarting at stream 0 whenever a bank is re-adopted."""
+    if seed is not None:
+        return int(seed) & (2 ** 64 - 1), bank.step
+    rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+    gen = torch.cuda.default_generators[dev.index]
+    off = int(gen.get_offset())
+    gen.set_offset(off + 4)                                  # one Philox counter block per step, never reused
+    s0 = (int(gen.initial_seed()) ^ ((rank + 1) * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
+    return s0, off // 4
+
+
+def _sparse_state(bank: DeviceMemoryBank, rep: torch.Tensor, rows: int):
+    """(grad_rep buffer, previous anchor pixels) of the opt-in sparse-gradient contract, kept per bank and shape."""
+    key = (tuple(rep.shape), rep.dtype, rows)
+    cache = bank.__dict__.setdefault("_sparse_grad", {})
+    st = cache.get(key)
+    if st is None:
+        cache.clear()                                        # one live shape per bank: do not pin several dense buffers
+        st = cache[key] = (torch.zeros(rep.shape, dtype=rep.dtype, device=rep.device),
+                           torch.full((rows,), -1, dtype=torch.int32, device=rep.device))
+    return st
 
 
 def _flat(t: torch.Tensor, lead: int) -> torch.Tensor:
@@ -139,7 +204,7 @@ class _ContraLoss(torch.autograd.Function):
         sp = stream.cuda_stream
         lib = _cabi.lib
         layout = st["layout"]
-        if st["inject"] is None and st["debug"] is None:
+        if st["inject"] is None and (st["debug"] is None or st["debug"].get("fused")):
             # one FFI call; multi-GPU too when the exchange buffer could be peer-mapped (no NCCL call between the stages)
             p2p = _p2p_exchange(st["group"], dev, dims.classes * (dims.feat + 1)) if st["group"] is not None else None
             if st["group"] is None or p2p is not None:
@@ -184,7 +249,7 @@ class _ContraLoss(torch.autograd.Function):
             # rank-local plan, speculatively -- redone below only if the global valid-class list changes the plan)
             side = _side_stream(dev)
             side.wait_stream(stream)
-            _cabi.check(lib.arco_sample(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(), idx_n.data_ptr(),
+            _cabi.check(lib.arco_sample(d, st["func"], st["seed"], st["step"], idx_a.data_ptr(), idx_n.data_ptr(),
                                         wsp, side.cuda_stream), "arco_sample")
         _cabi.check(lib.arco_proto_enqueue(d, st["rep_teacher"].data_ptr(), b, proto_local.data_ptr(), wsp, sp),
                     "arco_proto_enqueue")
@@ -202,7 +267,7 @@ class _ContraLoss(torch.autograd.Function):
                 stream.wait_stream(side)                    # the speculative sampler has read the local plan
             _cabi.check(lib.arco_replan_global(d, proto_sums.data_ptr(), wsp, sp), "arco_replan_global")
             if side is not None:
-                _cabi.check(lib.arco_sample_if_replanned(d, st["func"], st["seed"], bank.step, idx_a.data_ptr(),
+                _cabi.check(lib.arco_sample_if_replanned(d, st["func"], st["seed"], st["step"], idx_a.data_ptr(),
                                                          idx_n.data_ptr(), wsp, sp), "arco_sample_if_replanned")
         elif side is not None:
             stream.wait_stream(side)
@@ -239,7 +304,7 @@ class _ContraLoss(torch.autograd.Function):
                 d, st["rep_data"].data_ptr(), b, proto_sums.data_ptr(), idx_a.data_ptr(), idx_n.data_ptr(),
                 float(st["temp"]), loss.data_ptr(), g_anchor.data_ptr(), pix.data_ptr(),
                 logits.data_ptr() if logits is not None else None, mom.data_ptr(), mom_on.data_ptr(),
-                float(st["ema_decay"]), proto_out.data_ptr(), wsp, sp), "arco_infonce_ema")
+                float(st["ema_decay"]), float(1.0 - st["ema_decay"]), proto_out.data_ptr(), wsp, sp), "arco_infonce_ema")
             n_valid = ws[layout.plan + 384: layout.plan + 388].view(torch.int32)      # arco_plan.n_valid
             st["prototype_out"] = torch.where(n_valid <= 1, mom, proto_out)
         bank.post_step(plan_view)
@@ -253,6 +318,7 @@ class _ContraLoss(torch.autograd.Function):
         ctx.rep_shape = rep.shape
         ctx.rep_dtype = rep.dtype
         ctx.prefilled = None
+        ctx.sparse = st["sparse"]
         if st["prefill"]:
             # The dense grad_rep must be zero-filled whatever the inputs are (autograd contract, P*D*e bytes of
             # HBM writes).  Start that fill now on the side stream: it runs underneath the forward kernels, which
@@ -297,8 +363,10 @@ class _ContraLoss(torch.autograd.Function):
             mom_on = (mom != 0).any().to(torch.int32).reshape(1)
             proto_out = buf[o_mom: o_mom + Cn * Q * D * 4].view(torch.float32).view(mom.shape)
             proto_out.zero_()
-            io.momentum, io.momentum_on, io.proto_out, io.ema_decay = mom.data_ptr(), mom_on.data_ptr(), proto_out.data_ptr(), float(st["ema_decay"])
-        io.seed, io.step = st["seed"], bank.step
+            io.momentum, io.momentum_on, io.proto_out = mom.data_ptr(), mom_on.data_ptr(), proto_out.data_ptr()
+            # the reference forms (1 - ema_decay) as a Python double before it meets the float32 tensor (:491-495)
+            io.ema_decay, io.ema_keep = float(st["ema_decay"]), float(1.0 - st["ema_decay"])
+        io.seed, io.step = st["seed"], st["step"]
         io.delta_p, io.delta_n, io.temp = DELTA_P, float(st["delta_n"]), float(st["temp"])
         io.low_rank, io.high_rank, io.func = LOW_RANK, HIGH_RANK, st["func"]
         if p2p is not None:
@@ -317,10 +385,20 @@ class _ContraLoss(torch.autograd.Function):
             n_valid = buf[layout.plan + 384: layout.plan + 388].view(torch.int32)      # arco_plan.n_valid
             st["prototype_out"] = torch.where(n_valid <= 1, mom, proto_out)
         ctx.fused = (buf, base + o_ga, base + o_pix)
+        if st["debug"] is not None:
+            # views into the step's packed buffer (parity tests / bench.py's cross-rank check of the fused path)
+            st["debug"].update(
+                ws=buf, layout=layout, dims=dims,
+                proto_sums=buf[o_proto: o_proto + Cn * (D + 1) * 8].view(torch.float64).view(Cn, D + 1),
+                idx_anchor=buf[o_ia: o_ia + Cn * Q * 4].view(torch.int32).view(Cn, Q),
+                idx_neg=buf[o_in: o_in + Cn * Q * max(N, 1) * 4].view(torch.int32).view(Cn, Q * max(N, 1)),
+                anchor_pix=buf[o_pix: o_pix + Cn * Q * 4].view(torch.int32).view(Cn, Q),
+                grad_anchor=buf[o_ga: o_ga + Cn * Q * D * 4].view(torch.float32).view(Cn, Q, D), logits=None)
         ctx.dims = dims
         ctx.rep_shape = rep.shape
         ctx.rep_dtype = rep.dtype
         ctx.prefilled = [grad_buf] if grad_buf is not None else None
+        ctx.sparse = st["sparse"]
         return buf[o_loss: o_loss + 4].view(torch.float32).reshape(())
 
     @staticmethod
@@ -336,7 +414,14 @@ class _ContraLoss(torch.autograd.Function):
         stream = torch.cuda.current_stream(dev)
         sp = stream.cuda_stream
         pre = ctx.prefilled
-        if pre is not None and pre[0] is not None:
+        if ctx.sparse is not None:
+            # opt-in sparse-gradient contract: the op owns grad_rep across steps; it is zero except at the previous
+            # step's anchor pixels, which are cleared before this step's scatter (no P*D*e-byte fill)
+            grad_rep, prev_pix = ctx.sparse
+            _cabi.check(_cabi.lib.arco_grad_scatter_sparse(C.byref(ctx.dims), ga_ptr, pix_ptr, go.data_ptr(),
+                                                           grad_rep.data_ptr(), prev_pix.data_ptr(), sp),
+                        "arco_grad_scatter_sparse")
+        elif pre is not None and pre[0] is not None:
             grad_rep = pre[0]
             pre[0] = None                                   # a second backward (retain_graph) takes the slow path
             _cabi.check(_cabi.lib.arco_grad_scatter_add(C.byref(ctx.dims), ga_ptr, pix_ptr,
@@ -370,6 +455,7 @@ def compute_contra_memobank_loss(
     *,
     process_group=None,
     seed: Optional[int] = None,
+    sparse_grad: bool = False,
     _inject: Optional[dict] = None,
     _debug: Optional[dict] = None,
 ):
@@ -385,7 +471,16 @@ def compute_contra_memobank_loss(
 
     Keyword-only extensions: ``process_group`` (batch-sharded multi-GPU: one all-reduce of the per-class
     prototype sums), ``seed`` (Philox seed of the in-kernel sampler; defaults to torch's CUDA seed),
-    ``_inject`` / ``_debug`` (parity tests).
+    ``_inject`` / ``_debug`` (parity tests), and ``sparse_grad``.
+
+    ``sparse_grad=True`` is an OPT-IN deviation from the autograd contract that removes the largest byte term of the
+    step (the P*D*e-byte zero fill of the dense ``grad_rep``): the gradient handed to
+    autograd is a buffer the op keeps per memory bank and reuses every step -- all zero except the <= C*Q anchor
+    pixels of the current step; the previous step's pixels are cleared first.  The VALUES are identical to the default
+    path; what changes is ownership: the tensor is only valid until the next backward of this op on the same bank.
+    That is exactly how the trainers use it (``rep`` is the non-leaf output of ``q_representation``,
+    train_arco_2d.py:317-329: its gradient is consumed by the conv backward of the same ``loss.backward()``); do not
+    use it when ``rep`` is a leaf whose ``.grad`` you keep or accumulate across steps.
     """
     if not (torch.is_tensor(rep) and rep.is_cuda):
         raise RuntimeError("arco_b200.compute_contra_memobank_loss needs CUDA tensors: there is no CPU fallback")
@@ -447,6 +542,8 @@ def compute_contra_memobank_loss(
     with torch.cuda.device(dev):
         bank = DeviceMemoryBank.adopt(memobank, queue_prtlis, queue_size, D, dev, rep.dtype)
         bank.poll()                         # mirror finished steps (non-blocking): queue_prtlis, label errors
+        bank.begin_step()
+        sampler_seed, sampler_step = _sampler_stream(seed, bank, dev)
         key = (n_lab, n_unlab, Cn, D, S, int(num_queries), int(num_negatives), rep.dtype, label_kind, dev.index)
         cached = _GEOMETRY.get(key)
         if cached is None:
@@ -462,12 +559,15 @@ def compute_contra_memobank_loss(
             low_mask=low_mask.contiguous(), high_mask=high_mask.contiguous(),
             rep_teacher=rep_teacher.detach().contiguous(), rep_data=rep_data,
             delta_n=delta_n, temp=temp, func=_FUNC.get(func, _cabi.FUNC_UNIFORM),
-            seed=int(seed) if seed is not None else int(torch.cuda.initial_seed()) & (2 ** 63 - 1),
+            seed=sampler_seed, step=sampler_step,
             group=process_group, inject=_inject, debug=_debug, momentum=mom, ema_decay=ema_decay,
             # only worth its three extra host calls when the step is bandwidth- rather than launch-bound
             prefill=bool(rep.requires_grad and torch.is_grad_enabled() and _PREFILL_GRAD
                          and rep.numel() * rep.element_size() >= _PREFILL_MIN_BYTES),
         )
+        state["sparse"] = _sparse_state(bank, rep, Cn * int(num_queries)) if (sparse_grad and rep.requires_grad and torch.is_grad_enabled()) else None
+        if state["sparse"] is not None:
+            state["prefill"] = False
         loss = _ContraLoss.apply(rep, state)
     keys = LazyKeys(bank, Cn, state["plan_view"])
     if mom is not None:

@@ -20,6 +20,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
     double v;
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -39,10 +44,13 @@ __global__ void __launch_bounds__(1024) proto_allreduce_p2p_kernel(const unsigne
         st_release_sys(reinterpret_cast<unsigned long long*>(peer_base[tid]) + flag_off + rank, seq);
     if (tid < world && tid != rank) {
         const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(peer_base[rank]) + flag_off + tid;
-        long long spins = 0;
+        // a peer that never arrives must fail loudly, not hang: bound the wait by WALL time (10 s on %globaltimer; a
+        // poll over NVLink costs ~1 us, so a poll count would be minutes), raise the status bit, then trap
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned int polls = 0;
         while (ld_acquire_sys(mine) < seq) {
-            if (++spins > (1ll << 31)) {                      // a peer never arrived (seconds): fail loudly instead of hanging
-                if (status) atomicOr(status, 0x80000000u);
+            if ((++polls & 1023u) == 0 && globaltimer_ns() - t0 > 10000000000ull) {
+                if (status) { atomicOr(status, (uint32_t)ARCO_ST_EXCHANGE_TIMEOUT); __threadfence_system(); }
                 __trap();
             }
         }

@@ -76,7 +76,7 @@ extern "C" int arco_forward(const arco_dims* dims, const arco_step_io* io, const
     if (io->momentum)
         rc = arco_infonce_ema(dims, io->rep, bank, io->proto_sums, io->idx_anchor, io->idx_neg, io->temp, io->loss,
                               io->grad_anchor, io->anchor_pix, io->logits, io->momentum, io->momentum_on, io->ema_decay,
-                              io->proto_out, workspace, main_st);
+                              io->ema_keep, io->proto_out, workspace, main_st);
     else
         rc = arco_infonce(dims, io->rep, bank, io->proto_sums, io->idx_anchor, io->idx_neg, io->temp, io->loss,
                           io->grad_anchor, io->anchor_pix, io->logits, workspace, main_st);

@@ -43,6 +43,23 @@ __global__ void __launch_bounds__(128) grad_scatter_kernel(const float* __restri
         atomic_add_elem<T>(grad_rep + (b * D + d) * S + s, go * g_anchor[(int64_t)row * D + d]);
 }
 
+// Opt-in "sparse gradient" contract (arco_grad_scatter_sparse): grad_rep is a buffer the caller keeps across steps and that
+// is zero everywhere except at the previous step's anchor pixels, so instead of rewriting P*D*e bytes of zeros it is enough
+// to clear those <= C*Q pixel columns again before the new scatter.
+template <typename T>
+__global__ void __launch_bounds__(128) grad_unscatter_kernel(const int32_t* __restrict__ prev_pix, T* __restrict__ grad_rep,
+                                                              int D, int64_t S) {
+    const int pix = prev_pix[blockIdx.x];
+    if (pix < 0) return;
+    const int64_t b = pix / S, s = pix - b * S;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) grad_rep[(b * D + d) * S + s] = T(0.f);
+}
+
+__global__ void copy_pix_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
 }  // namespace arco
 
 static int launch_fill(const arco_dims& d, void* grad_rep, cudaStream_t st) {
@@ -90,4 +107,22 @@ extern "C" int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor
     int rc = launch_fill(*dims, grad_rep, (cudaStream_t)stream);
     if (rc != ARCO_OK) return rc;
     return launch_scatter(*dims, grad_anchor, anchor_pix, grad_out, grad_rep, (cudaStream_t)stream);
+}
+
+extern "C" int arco_grad_scatter_sparse(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
+                                        const float* grad_out, void* grad_rep, int32_t* prev_pix, void* stream) {
+    ARCO_REQUIRE(dims && grad_anchor && anchor_pix && grad_out && grad_rep && prev_pix, "arco_grad_scatter_sparse: NULL argument");
+    const arco_dims& d = *dims;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = d.classes * d.queries;
+    if (d.rep_dtype == ARCO_BF16)
+        arco::grad_unscatter_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(prev_pix, (__nv_bfloat16*)grad_rep, d.feat, d.space);
+    else
+        arco::grad_unscatter_kernel<float><<<rows, 128, 0, st>>>(prev_pix, (float*)grad_rep, d.feat, d.space);
+    ARCO_LAUNCH_CHECK();
+    int rc = launch_scatter(d, grad_anchor, anchor_pix, grad_out, grad_rep, st);
+    if (rc != ARCO_OK) return rc;
+    arco::copy_pix_kernel<<<(rows + 255) / 256, 256, 0, st>>>(anchor_pix, prev_pix, rows);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
 }

@@ -35,7 +35,9 @@ struct InfoParams {
     const float* momentum;       // [C][Q][D] or NULL
     const int32_t* momentum_on;  // device flag: momentum tensor has a non-zero entry (:489)
     float* proto_out;            // [C][Q][D] positive_feat written per (bank class, query) (:497), or NULL
-    float ema_decay;
+    void* host_mirror;           // arco_bank.host_mirror / mirror_seq
+    uint64_t mirror_seq;
+    float ema_decay, ema_keep;   // ema_keep = float32(1 - ema_decay) formed in DOUBLE by the caller, as the reference's Python scalar is (:491-495)
     int64_t row_off[ARCO_MAX_CLASSES];
     int32_t cap[ARCO_MAX_CLASSES];
     int64_t S;
@@ -111,7 +113,10 @@ __device__ __forceinline__ AnchorInfo info_prologue(const InfoParams& p, int j, 
     if (warp == 0) {
         const uint32_t n_anchor = pl->n_anchor[j];
         uint32_t idx = (uint32_t)p.idx_a[(int64_t)j * p.Q + q];
-        if (idx >= n_anchor) idx = n_anchor - 1;
+        if (idx >= n_anchor) {                                   // injected / foreign index out of range: flag it (the host raises), then stay in bounds
+            if (lane == 0) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE);
+            idx = n_anchor - 1;
+        }
         const uint32_t* off = p.off_anchor + (int64_t)j * (p.NT + 1);
         // largest tile lo with off[lo] <= idx: 32 probes per round instead of a dependent load per halving
         int lo = 0, hi = p.NT;
@@ -168,7 +173,7 @@ __device__ __forceinline__ AnchorInfo info_prologue(const InfoParams& p, int j, 
         if (p.momentum) {
             // positive = (1-a)*proto + a*momentum_prototype[valid_classes[i]][q]  (:490-495); prototype[...] = positive (:497)
             const int64_t mo = ((int64_t)bank_cls * p.Q + q) * D + d;
-            if (*p.momentum_on) k = (1.f - p.ema_decay) * k + p.ema_decay * p.momentum[mo];
+            if (*p.momentum_on) k = p.ema_keep * k + p.ema_decay * p.momentum[mo];
             if (p.proto_out) p.proto_out[mo] = k;
         }
         a_hat[d] = v;
@@ -248,6 +253,18 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
         for (int i = 0; i < 128; ++i) s += s_fold[i];
         p.loss[0] = s;
     }
+    if (p.host_mirror) {
+        // zero-copy host mirror of the step summary (arco_bank.host_mirror): plan words, system fence, sequence number
+        const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(p.plan);
+        volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(p.host_mirror);
+        for (int i = tid; i < (int)(sizeof(arco_plan) / 4); i += 128) dst[i] = src[i];
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<char*>(p.host_mirror) + sizeof(arco_plan)),
+                         "l"((unsigned long long)p.mirror_seq) : "memory");
+        }
+    }
 }
 
 // MAXIT: 16-byte chunks per lane in pass 2 (ceil(chunks per row / 32)); BF16BANK: the ring stores bf16 rows
@@ -307,7 +324,7 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
             __syncwarp();
             if (lane < nv) {
                 int r = my_idx[chunk * KC + lane];
-                r = min(max(r, 0), blen - 1);
+                if (r < 0 || r >= blen) { atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
                 int phys = bhead + r;
                 if (phys >= cap) phys -= cap;
                 bulk_g2s(wstage + (size_t)lane * RS16, bank + (int64_t)phys * row_bytes, row_bytes, &bars[warp]);
@@ -529,7 +546,7 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
             if (lane == 0) mbar_expect_tx(&bars[s], (uint32_t)nv * row_bytes);
             __syncwarp();
             if (lane < nv) {
-                r = min(max(r, 0), blen - 1);
+                if (r < 0 || r >= blen) { atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
                 int phys = bhead + r;
                 if (phys >= cap) phys -= cap;
                 bulk_g2s(stage + (size_t)s * stage_u4 + (size_t)lane * RS16, bank + (int64_t)phys * row_bytes, row_bytes, &bars[s]);
@@ -685,7 +702,7 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
 static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
                         const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
                         float* grad_anchor, int32_t* anchor_pix, float* logits, const float* momentum,
-                        const int32_t* momentum_on, float ema_decay, float* proto_out, void* workspace, void* stream) {
+                        const int32_t* momentum_on, float ema_decay, float ema_keep, float* proto_out, void* workspace, void* stream) {
     ARCO_REQUIRE(dims && rep && bank && proto_sums && idx_anchor && idx_neg && loss && grad_anchor && anchor_pix &&
                      workspace, "arco_infonce: NULL argument");
     const arco_dims& d = *dims;
@@ -702,7 +719,8 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     p.plan = (arco_plan*)(ws + L.plan);
     p.loss = loss; p.g_anchor = grad_anchor; p.anchor_pix = anchor_pix; p.logits = logits;
     p.loss_parts = (float*)(ws + L.loss_parts);
-    p.momentum = momentum; p.momentum_on = momentum_on; p.proto_out = proto_out; p.ema_decay = ema_decay;
+    p.momentum = momentum; p.momentum_on = momentum_on; p.proto_out = proto_out; p.ema_decay = ema_decay; p.ema_keep = ema_keep;
+    p.host_mirror = bank->host_mirror; p.mirror_seq = bank->mirror_seq;
     ARCO_REQUIRE(momentum == nullptr || momentum_on != nullptr, "momentum needs the device flag momentum_on");
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
     p.S = d.space; p.C = d.classes; p.D = d.feat; p.Q = d.queries; p.N = d.negatives;
@@ -774,15 +792,15 @@ extern "C" int arco_infonce(const arco_dims* dims, const void* rep, const arco_b
                             const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
                             float* grad_anchor, int32_t* anchor_pix, float* logits, void* workspace, void* stream) {
     return infonce_impl(dims, rep, bank, proto_sums, idx_anchor, idx_neg, temp, loss, grad_anchor, anchor_pix, logits,
-                        nullptr, nullptr, 0.f, nullptr, workspace, stream);
+                        nullptr, nullptr, 0.f, 1.f, nullptr, workspace, stream);
 }
 
 extern "C" int arco_infonce_ema(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
                                 const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
                                 float* grad_anchor, int32_t* anchor_pix, float* logits, const float* momentum,
-                                const int32_t* momentum_on, float ema_decay, float* proto_out, void* workspace,
-                                void* stream) {
+                                const int32_t* momentum_on, float ema_decay, float ema_keep, float* proto_out,
+                                void* workspace, void* stream) {
     ARCO_REQUIRE(momentum && momentum_on && proto_out, "arco_infonce_ema: NULL momentum argument");
     return infonce_impl(dims, rep, bank, proto_sums, idx_anchor, idx_neg, temp, loss, grad_anchor, anchor_pix, logits,
-                        momentum, momentum_on, ema_decay, proto_out, workspace, stream);
+                        momentum, momentum_on, ema_decay, ema_keep, proto_out, workspace, stream);
 }

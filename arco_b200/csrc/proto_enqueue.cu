@@ -596,6 +596,11 @@ __global__ void __launch_bounds__(256) proto_small_kernel(ProtoParams p) {
     for (int c = 0; c < CC; ++c)
 #pragma unroll
         for (int d = 0; d < DD; ++d) acc[c][d] = 0.f;
+    // This kernel never writes ring rows.  That is exact for the reference's low_rank = 3 >= C (no class can rank in [3,20),
+    // trap 3); a C-ABI caller that passed a smaller low_rank gets keys COUNTED by classify/scan_plan that nobody enqueues:
+    // flag it (the Python layer raises) instead of silently exposing stale ring rows.
+    if (blockIdx.x == 0 && tid < CC && p.plan->n_key[tid] != 0)
+        atomicOr(const_cast<uint32_t*>(&p.plan->status), (uint32_t)ARCO_ST_KEYS_DROPPED);
 
     for (int64_t g = (int64_t)blockIdx.x * 256 + tid; g < groups; g += (int64_t)gridDim.x * 256) {
         const int64_t b = g / gps, s = (g - b * gps) * PER16;

@@ -53,9 +53,14 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
-    ap.add_argument("--aten-gpu", action="store_true",
-                    help="also time the oracle port's torch/ATen ops ON THE GPU (the reference's own op mix, CPU banks "
-                         "uploaded per class like loss_helper_3d.py:466) as a like-for-like GPU baseline")
+    ap.add_argument("--no-aten-gpu", action="store_true",
+                    help="skip timing the oracle port's torch/ATen ops ON THE GPU (the reference's own op mix, CPU banks "
+                         "uploaded per class like loss_helper_3d.py:466): the like-for-like GPU baseline, on by default at N=1")
+    ap.add_argument("--aten-gpu", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0,
+                    help="--impl reference: seconds the whole CPU run may take; the batch is the largest n+n that fits")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="only the headline workload: skip the `configs` block (acdc2d_loss, la3d, la3d cold bank, cityscapes)")
     return ap.parse_args()
 
 
@@ -134,23 +139,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference / CPU arm: the oracle port on host cores, bounded sample of the same workload
 # --------------------------------------------------------------------------------------------------
-def cpu_sample_spec(workload):
-    from arco_b200.synth import WORKLOADS
-    cfg = dict(WORKLOADS[workload])
-    cfg["n_lab"], cfg["n_unlab"] = 1, 1          # bounded sample: one labelled + one unlabelled image/volume
-    return cfg
-
-
-def run_cpu(workload, steps, warmup, func):
-    import numpy as np
+def _cpu_steps(workload, n_lab, n_unlab, steps, warmup, func):
     import torch
 
     import oracle
-    from arco_b200.synth import CaseSpec, bench_bank, bench_inputs
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = cpu_sample_spec(workload)
-    spec, x = bench_inputs(workload, torch.device("cpu"), seed=1337, n_lab=cfg["n_lab"], n_unlab=cfg["n_unlab"])
+    from arco_b200.synth import bench_bank, bench_inputs
+    spec, x = bench_inputs(workload, torch.device("cpu"), seed=1337, n_lab=n_lab, n_unlab=n_unlab)
     memobank, ptrs, caps = bench_bank(spec, cold=COLD_BANK)
     sampler = {"smc": oracle.grid_strata_sample, "asmc": oracle.grid_antithetic_sample}.get(func)
     rep = x["rep"].float().requires_grad_(True)           # CPU bf16 kernels are not what the reference ran on
@@ -167,26 +161,59 @@ def run_cpu(workload, steps, warmup, func):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
+    return spec, sum(times) / len(times)
+
+
+def run_cpu(workload, steps, warmup, func, budget_s=150.0):
+    """The oracle port on all host threads.  The batch is the LARGEST n+n (labelled + unlabelled, up to the workload's
+    own) whose `warmup + steps` passes fit `budget_s`, found by timing one 1+1 pass first (CPU cost is close to linear in
+    the batch: per-class fixed work -- bank gather, samplers -- amortises, so a larger sample can only favour the CPU)."""
+    import torch
+    from arco_b200.synth import WORKLOADS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    full = WORKLOADS[workload]
+    t_probe0 = time.perf_counter()
+    spec, t1 = _cpu_steps(workload, 1, 1, 1, 0, func)
+    probe_s = time.perf_counter() - t_probe0
+    n = 1
+    if full["n_lab"] == full["n_unlab"]:
+        left = budget_s - probe_s
+        while n < full["n_lab"] and (n + 1) * t1 * (steps + warmup) * 1.15 <= left:
+            n += 1
+    if n > 1 or steps > 1 or warmup > 0:
+        spec, t = _cpu_steps(workload, n, n, steps, warmup, func)
+    else:
+        t = t1
+    ms = 1e3 * t
     px = spec.pixels
-    sample = (f"{workload} shape with batch reduced to 1 labelled + 1 unlabelled "
+    same = (n == full["n_lab"] and n == full["n_unlab"])
+    sample = (f"{workload} shape, batch {n} labelled + {n} unlabelled of the workload's {full['n_lab']}+{full['n_unlab']} "
               f"({px} pixels/step, D={spec.feat}, C={spec.classes}, Q=256, N=512, fp32 on CPU), "
-              f"{steps} timed steps after {warmup} warm-up, oracle port (torch CPU ops)")
+              f"{steps} timed steps after {warmup} warm-up, oracle port (torch CPU ops); batch chosen to fit a {budget_s:.0f} s budget")
     return dict(value=px / (ms * 1e-3) / 1e6, unit=UNIT, cores=cores, kind="port", sample=sample, ms_per_step=ms,
-                threads=torch.get_num_threads()), spec
+                threads=torch.get_num_threads(), batch=[n, n],
+                same_config=(True if same else f"batch reduced to {n}+{n} of {full['n_lab']}+{full['n_unlab']} (CPU time box); "
+                             "everything else identical; fp32 on CPU where the GPU arm stores rep in " + full["dtype"])), spec
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, spec = run_cpu(args.workload, max(1, args.steps), max(0, args.warmup), args.func)
+    from arco_b200.synth import WORKLOADS
+    base, spec = run_cpu(args.workload, max(1, args.steps), max(0, args.warmup), args.func, budget_s=args.cpu_budget)
+    full = WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "CPU arm: oracle port of the reference loss on host cores; "
-                   "the Python reference itself cannot travel to the GPU box", "sample": base["sample"]},
+        "config": {"workload": args.workload, "batch_per_gpu": sum(base["batch"]), "labelled_per_gpu": base["batch"][0],
+                   "classes": spec.classes, "spatial": list(spec.spatial), "feat": spec.feat, "rep_storage": "f32",
+                   "queries": spec.queries, "negatives": spec.negatives, "func": args.func,
+                   "workload_batch": full["n_lab"] + full["n_unlab"], "same_config": base["same_config"],
+                   "note": "CPU arm: oracle port of the reference loss (same ATen op mix) on host cores; "
+                           "the Python reference itself cannot travel to the GPU box", "sample": base["sample"]},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -197,6 +224,109 @@ def main_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, group, steps, warmup, func, blocky, cold,
+                     with_stages=True, check_ranks=False, sparse_grad=False):
+    """One workload, device-timed: W warm-up steps, then `steps` forward+backward passes, each bracketed by CUDA events on
+    the launching stream; max over ranks.  Returns the block that goes into the JSON line (headline or `configs`)."""
+    from arco_b200.synth import bench_bank, bench_inputs
+    spec, x = bench_inputs(name, dev, seed=1337 + rank, blocky=blocky)
+    memobank, ptrs, caps = bench_bank(spec, seed=1337 + rank, cold=cold)
+    rep = x["rep"].requires_grad_(True)
+    P = spec.pixels
+    kw = dict(delta_n=0.97, func=func, num_queries=spec.queries, num_negatives=spec.negatives, temp=0.5,
+              process_group=group, seed=1337)
+    if sparse_grad:
+        kw["sparse_grad"] = True
+
+    class _Consumer(torch.autograd.Function):
+        # stands in for the layer that produced `rep` (q_representation's conv, train_arco_2d.py:317-329): it receives
+        # grad_rep and passes nothing on, so the sparse-gradient variant is timed the way a trainer uses it (rep is NOT a
+        # leaf; a leaf's AccumulateGrad would deep-copy the op-owned buffer)
+        @staticmethod
+        def forward(ctx, t):
+            return t.view_as(t)
+
+        @staticmethod
+        def backward(ctx, g):
+            return None
+
+    def step(inputs=x, rep_t=rep):
+        rep_t.grad = None
+        rep_in = _Consumer.apply(rep_t) if sparse_grad else rep_t
+        _, loss = arco_b200.compute_contra_memobank_loss(
+            rep_in, inputs["label_l"], inputs["label_u"], inputs["prob_l"], inputs["prob_u"], inputs["low_mask"],
+            inputs["high_mask"], memobank, ptrs, caps, inputs["rep_teacher"], **kw)
+        loss.backward()
+        return loss
+
+    in_bytes = sum(x[k].numel() * x[k].element_size() for k in
+                   ("rep", "rep_teacher", "label_l", "label_u", "prob_l", "prob_u", "low_mask", "high_mask"))
+    flush = None
+    l2_note = "inputs (%.0f MB) exceed the 126 MB L2" % (in_bytes / 1e6)
+    if in_bytes < 400e6:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        l2_note = "L2 flushed (256 MB write) between timed steps"
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, warmup)):
+        step()
+    sync_all()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    sync_all()
+    t_begin = time.perf_counter()
+    for i in range(steps):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        starts[i].record()
+        step()
+        ends[i].record()
+    sync_all()
+    t_end = time.perf_counter()
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    out = {
+        "workload": name + ("+cold_bank" if cold else "") + ("+blocky" if blocky else "") + ("+sparse_grad" if sparse_grad else ""),
+        "ms_per_step": total_ms / steps, "value": world * P * steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "steps": steps,
+        "pixels_per_gpu": P, "rep_storage": spec.dtype, "l2": l2_note,
+    }
+    ctx = dict(spec=spec, x=x, rep=rep, memobank=memobank, ptrs=ptrs, caps=caps, kw=kw, flush=flush, sync_all=sync_all,
+               window=(t_begin, t_end))
+    if check_ranks and world > 1:
+        # multi-GPU correctness bit the driver can see: one more step through the SAME fused path with the step's
+        # global prototype sums kept, all-gathered, and compared bit for bit with rank 0's
+        dbg = {"fused": True}
+        rep.grad = None
+        _, loss = arco_b200.compute_contra_memobank_loss(
+            rep, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"], memobank, ptrs, caps,
+            x["rep_teacher"], _debug=dbg, **kw)
+        mine = dbg["proto_sums"].clone().view(torch.int64).flatten()
+        allp = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allp, mine)
+        same = all(bool(torch.equal(allp[0], a)) for a in allp)
+        counts = dbg["proto_sums"][:, -1].sum().item()
+        out["multi_gpu_check"] = {"proto_sums_bit_identical_on_all_ranks": same, "ranks": world,
+                                  "global_low_valid_pixels": counts, "exchange": __import__("arco_b200.contra", fromlist=["x"]).EXCHANGE_PLANE}
+        assert same, "global prototype sums differ between ranks"
+    if with_stages and rank == 0:
+        stages, roof = stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush)
+        out["stages"], out["roofline"] = stages, roof
+        m = stages["_measured"]
+        e_t = 2 if spec.dtype == "bf16" else 4
+        whole = sum(v["alg_bytes"] for k, v in stages.items() if not k.startswith("_"))
+        out["step_alg_bytes"] = whole
+        out["step_frac_hbm"] = whole / (out["ms_per_step"] * 1e-3) / 1e9 / peaks()[0]
+    return out, ctx
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -223,74 +353,28 @@ def main_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
+    import gc
+
     import arco_b200
     from arco_b200 import _cabi
-    from arco_b200.synth import bench_bank, bench_inputs
-
-    spec, x = bench_inputs(args.workload, dev, seed=1337 + rank, blocky=args.blocky)
-    memobank, ptrs, caps = bench_bank(spec, seed=1337 + rank, cold=COLD_BANK)
-    rep = x["rep"].requires_grad_(True)
-    P = spec.pixels
-    kw = dict(delta_n=0.97, func=args.func, num_queries=spec.queries, num_negatives=spec.negatives, temp=0.5,
-              process_group=group, seed=1337)
-
-    def step(inputs=x, rep_t=rep):
-        rep_t.grad = None
-        _, loss = arco_b200.compute_contra_memobank_loss(
-            rep_t, inputs["label_l"], inputs["label_u"], inputs["prob_l"], inputs["prob_u"], inputs["low_mask"],
-            inputs["high_mask"], memobank, ptrs, caps, inputs["rep_teacher"], **kw)
-        loss.backward()
-        return loss
-
-    in_bytes = sum(x[k].numel() * x[k].element_size() for k in
-                   ("rep", "rep_teacher", "label_l", "label_u", "prob_l", "prob_u", "low_mask", "high_mask"))
-    flush = None
-    l2_note = "inputs (%.0f MB) exceed the 126 MB L2" % (in_bytes / 1e6)
-    if in_bytes < 400e6:
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-        l2_note = "L2 flushed (256 MB write) between timed steps"
-
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    for _ in range(max(3, args.warmup)):
-        step()
-    sync_all()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sync_all()
-    clocks.mark_begin()
-    for i in range(args.steps):
-        if flush is not None:
-            flush.fill_(i & 0xff)
-        starts[i].record()
-        step()
-        ends[i].record()
-    sync_all()
-    clocks.mark_end()
+    clocks.mark_begin()          # narrowed to the headline's timed region below
+    head, ctx = measure_workload(torch, dist, arco_b200, _cabi, args.workload, dev, rank, world, group, args.steps,
+                                 args.warmup, args.func, args.blocky, COLD_BANK, check_ranks=True)
+    clocks.t0, clocks.t1 = ctx["window"]
     clk = clocks.stop() if rank == 0 else None
-    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * P * args.steps / (total_ms * 1e-3) / 1e6
-
-    # ------------------------------------------------------------------ per-stage timing + roofline (rank 0 view)
-    stages, roof = stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush)
+    spec, x, P = ctx["spec"], ctx["x"], ctx["spec"].pixels
+    ms_per_step, value = head["ms_per_step"], head["value"]
+    stages, roof = head.get("stages"), head.get("roofline")
 
     # ------------------------------------------------------------------ end-to-end with host buffers
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(torch, arco_b200, spec, x, memobank, ptrs, caps, dev, kw, world,
-                      args.e2e_steps or max(3, args.steps // 4), sync_all)
+        e2e = run_e2e(torch, arco_b200, spec, x, ctx["memobank"], ctx["ptrs"], ctx["caps"], dev, ctx["kw"], world,
+                      args.e2e_steps or max(3, args.steps // 4), ctx["sync_all"])
         if world > 1:
             tt = torch.tensor([e2e["_total_ms"]], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -298,13 +382,35 @@ def main_ours(args):
         e2e["value"] = world * P * e2e["steps"] / (e2e.pop("_total_ms") * 1e-3) / 1e6
 
     aten = None
-    if rank == 0 and world == 1 and args.aten_gpu:
+    if rank == 0 and world == 1 and not args.no_aten_gpu:
         aten = run_aten_gpu(torch, spec, x, dev, args.func)
+        aten["speedup_of_this_op"] = aten["ms_per_step"] / ms_per_step
+    bank_dtype = ctx["memobank"][0].bank.row_dtype
+    del ctx, x
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ the other BASELINE.json configs, same run, same N
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        todo = [("acdc2d_loss", False, False), ("la3d", False, False), ("la3d", True, False), ("cityscapes", False, False),
+                (args.workload, COLD_BANK, True)]
+        for name, cold, sparse in todo:
+            if name == args.workload and cold == COLD_BANK and not sparse:
+                continue
+            blk, c2 = measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, group, max(5, args.steps // 2),
+                                       args.warmup, "asmc" if name == "la3d" else args.func, args.blocky, cold,
+                                       check_ranks=(name == "cityscapes"), sparse_grad=sparse)
+            configs[blk["workload"]] = blk
+            del c2
+            gc.collect()
+            torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _ = run_cpu(args.workload, 5, 1, args.func)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu, _ = run_cpu(args.workload, 2, 1, args.func, budget_s=25.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "same_config")}
 
     if rank == 0:
         line = {
@@ -315,12 +421,14 @@ def main_ours(args):
                 "workload": args.workload, "batch_per_gpu": spec.batch, "labelled_per_gpu": spec.n_lab,
                 "classes": spec.classes, "spatial": list(spec.spatial), "feat": spec.feat, "rep_storage": spec.dtype,
                 "queries": spec.queries, "negatives": spec.negatives, "func": args.func,
-                "labels": "blocky16" if args.blocky else "iid", "banks": ("cold: the trainers' initial one-row banks" if COLD_BANK else "pre-filled to capacity (50000/30000 rows)") + (", bf16-exact rows in a bf16 ring" if spec.dtype == "bf16" else ", fp32 ring"),
+                "labels": "blocky16" if args.blocky else "iid", "banks": ("cold: the trainers' initial one-row banks" if COLD_BANK else "pre-filled to capacity (50000/30000 rows)") + (", bf16-exact rows in a bf16 ring" if bank_dtype == torch.bfloat16 else ", fp32 ring"),
                 "pixels_per_gpu": P, "parallelism": (f"batch-shard x{world}, 1 exchange of C*(D+1) fp64 (" + ("own kernel over NVLink peer memory" if __import__("arco_b200.contra", fromlist=["x"]).P2P_EXCHANGE_USED else "NCCL all-reduce") + ")") if world > 1 else "single GPU",
-                "l2": l2_note, "timing": "CUDA events per step on the launching stream, max over ranks",
+                "l2": head["l2"], "timing": "CUDA events per step on the launching stream, max over ranks",
             },
             "clocks": clk, "gpu_launches": args.steps * (KERNELS_PER_STEP + (1 if world > 1 else 0)),
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "aten_gpu_baseline": aten, "stages": stages,
+            "step_alg_bytes": head.get("step_alg_bytes"), "step_frac_hbm": head.get("step_frac_hbm"),
+            "multi_gpu_check": head.get("multi_gpu_check"), "configs": configs,
         }
         print(json.dumps(line))
     if world > 1:

@@ -48,7 +48,14 @@ enum { ARCO_LABEL_ONEHOT_I64 = 0, ARCO_LABEL_INDEX_I64 = 1 };
 /* sampler kinds: reference `func` argument, loss_helper_3d.py:327-338 */
 enum { ARCO_FUNC_UNIFORM = 0, ARCO_FUNC_SMC = 1, ARCO_FUNC_ASMC = 2 };
 /* device status bits (arco_plan.status) */
-enum { ARCO_ST_MULTI_HOT = 1, ARCO_ST_LABEL_RANGE = 2 };
+enum {
+    ARCO_ST_MULTI_HOT = 1,        /* a one-hot label pixel has more than one non-zero class entry                 */
+    ARCO_ST_LABEL_RANGE = 2,      /* an integer label map holds a class id >= classes                             */
+    ARCO_ST_INDEX_RANGE = 4,      /* an injected / caller-provided sample index was outside its list (clamped)    */
+    ARCO_ST_KEYS_DROPPED = 8,     /* keys were counted but the selected prototype kernel cannot enqueue them
+                                     (register kernel for C <= 3: only legal with low_rank >= classes)            */
+    ARCO_ST_EXCHANGE_TIMEOUT = (int)0x80000000u  /* multi-GPU exchange: a peer never raised its flag (10 s)       */
+};
 
 /* Problem geometry.  Mirrors the shapes at the reference call site. */
 typedef struct arco_dims {
@@ -118,6 +125,12 @@ typedef struct arco_bank {
     int64_t  row_off[ARCO_MAX_CLASSES];
     int32_t  row_dtype;                       /* ARCO_F32 | ARCO_BF16                  */
     int32_t  reserved;
+    /* Optional zero-copy host mirror of the step summary: NULL, or a DEVICE-ACCESSIBLE address of pinned host memory with
+       room for sizeof(arco_plan) + 8 bytes.  The last CTA of arco_infonce stores the final arco_plan there and then
+       mirror_seq as a uint64 at offset sizeof(arco_plan) (system-scope release), so the host can follow new_keys,
+       queue_prtlis and the status bits by polling memory -- no memcpy, no event, no synchronisation. */
+    void*    host_mirror;
+    uint64_t mirror_seq;
 } arco_bank;
 
 ARCO_API const char* arco_version(void);
@@ -189,13 +202,15 @@ ARCO_API int arco_infonce(const arco_dims* dims, const void* rep, const arco_ban
                  void* workspace, void* stream);
 
 /* (a11) same with the optional EMA prototypes (momentum_prototype, loss_helper_3d.py:488-497): positive =
- * (1-ema_decay)*class_mean + ema_decay*momentum[bank_class][q] when *momentum_on != 0; the positive actually used is
- * written to proto_out[bank_class][q][:] (the reference's returned `prototype`).  momentum, proto_out: f32 [C,Q,D]. */
+ * ema_keep*class_mean + ema_decay*momentum[bank_class][q] when *momentum_on != 0; the positive actually used is
+ * written to proto_out[bank_class][q][:] (the reference's returned `prototype`).  momentum, proto_out: f32 [C,Q,D].
+ * ema_keep = (float)(1.0 - (double)decay): the reference forms 1 - ema_decay as a Python double before it meets the
+ * float32 tensor (:491-495); 1.f - (float)decay differs from that by 1.3e-5 relative at decay = 0.999. */
 ARCO_API int arco_infonce_ema(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
                               const int32_t* idx_anchor, const int32_t* idx_neg, float temp,
                               float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits,
-                              const float* momentum, const int32_t* momentum_on, float ema_decay, float* proto_out,
-                              void* workspace, void* stream);
+                              const float* momentum, const int32_t* momentum_on, float ema_decay, float ema_keep,
+                              float* proto_out, void* workspace, void* stream);
 
 /* (a10) backward: grad_rep[B,D,S] = 0, then += grad_out * grad_anchor at the anchor pixels
  * (duplicates accumulate, trap 8).  grad_out: device f32 scalar. */
@@ -207,6 +222,13 @@ ARCO_API int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor, 
 ARCO_API int arco_grad_zero(const arco_dims* dims, void* grad_rep, void* stream);
 ARCO_API int arco_grad_scatter_add(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
                                    const float* grad_out, void* grad_rep, void* stream);
+
+/* Opt-in sparse-gradient contract (not the reference's; arco_b200's `sparse_grad=True`): grad_rep is a buffer the CALLER
+ * keeps alive across steps, all zero except at the pixels listed in prev_pix (int32 [C*Q], -1 = none; all -1 and an all-zero
+ * buffer before the first call).  Clears those <= C*Q pixel columns, scatters this step's gradient (duplicates accumulate,
+ * trap 8) and records this step's pixels in prev_pix: ~C*Q*D*(4+3e) bytes instead of the P*D*e-byte dense zero fill. */
+ARCO_API int arco_grad_scatter_sparse(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
+                                      const float* grad_out, void* grad_rep, int32_t* prev_pix, void* stream);
 
 /* Every device pointer of one single-GPU forward step, for arco_forward. */
 typedef struct arco_step_io {
@@ -231,7 +253,8 @@ typedef struct arco_step_io {
     float*         proto_out;
     uint64_t       seed, step;     /* Philox seed / per-step stream id of the sampler                  */
     float          delta_p, delta_n, temp, ema_decay;
-    int32_t        low_rank, high_rank, func, reserved;
+    int32_t        low_rank, high_rank, func;
+    float          ema_keep;       /* (float)(1.0 - (double)ema_decay), see arco_infonce_ema                       */
     /* multi-GPU (batch shards); exchange_peers == NULL means single GPU.  See
        arco_proto_allreduce_p2p for the buffer layout. */
     const uint64_t* exchange_peers;   /* device array [exchange_world]: the exchange buffer as mapped for every rank  */

@@ -1,0 +1,15 @@
+#!/bin/bash
+# compute-sanitizer pass over every kernel family (run on the GPU box; logs under gpurun_out/sanitizer/).
+# memcheck: out-of-bounds / misaligned global, shared and local accesses; racecheck: shared-memory hazards between the
+# warp roles of the hand-rolled mbarrier pipelines; synccheck: illegal barrier use; initcheck: reads of uninitialised
+# global memory (the workspace is a fresh torch.empty every step).
+mkdir -p gpurun_out/sanitizer
+CS=${CS:-/usr/local/cuda/bin/compute-sanitizer}
+for tool in memcheck racecheck synccheck initcheck; do
+  extra=""
+  [ "$tool" = "racecheck" ] && extra="--racecheck-report all"
+  [ "$tool" = "initcheck" ] && extra="--track-unused-memory no"
+  timeout ${SAN_TIMEOUT:-900} $CS --tool $tool $extra --print-limit 40 --error-exitcode 77 \
+      --log-file gpurun_out/sanitizer/$tool.log python scripts/sanitize_run.py "$@" > gpurun_out/sanitizer/$tool.out 2>&1
+  echo "$tool rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer/$tool.log | tail -1)"
+done

@@ -1,0 +1,70 @@
+"""Workload driven under compute-sanitizer (scripts/sanitize.sh): smoke() plus one small case per kernel variant --
+tcgen05 bf16 prototype kernel (TMA + mbarrier ring + tcgen05.commit hand-offs), TF32 prototype kernel (TMEM A operand),
+pipelined / register / scalar CUDA-core variants, the cluster (DSMEM) sampler, the mma.sync and FFMA InfoNCE kernels with
+cp.async.bulk gathers, ring overflow, mask/threshold preparation and the dense tcgen05 similarity.
+Sizes are tiny: the sanitizer serialises and instruments every access."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import __graft_entry__ as entry  # noqa: E402
+import arco_b200  # noqa: E402
+from arco_b200.synth import CaseSpec, exact_case, make_bank  # noqa: E402
+
+SPECS = [
+    CaseSpec("tc_bf16", 1, 2, 4, (24, 24), 496, queries=16, negatives=12, dtype="bf16", bank_init="fill:80", caps=[120] * 4),
+    CaseSpec("tc32_c19", 1, 1, 19, (32, 32), 256, queries=8, negatives=16, bank_init="fill:40", caps=[64] * 19),
+    CaseSpec("tc32_d512", 1, 1, 5, (16, 32), 512, queries=8, negatives=8, bank_init="fill:40", caps=[64] * 5),
+    CaseSpec("pipe8", 1, 1, 4, (32, 32), 64, queries=16, negatives=16, bank_init="fill:100", caps=[150] * 4),
+    CaseSpec("pipe4_bf16_c19", 1, 1, 19, (32, 32), 48, queries=8, negatives=5, dtype="bf16", bank_init="fill:40", caps=[64] * 19),
+    CaseSpec("small_la", 1, 1, 2, (16, 16, 12), 16, queries=16, negatives=8, bank_init="randn1", func="asmc"),
+    CaseSpec("scalar_odd", 1, 2, 5, (9, 7, 5), 24, queries=12, negatives=3, bank_init="fill:50", caps=[64] * 5),
+    CaseSpec("overflow_tc", 1, 2, 5, (32, 32), 128, queries=8, negatives=8, dtype="bf16", bank_init="fill:10",
+             caps=[16, 12, 12, 12, 12], mask_frac=0.9, steps=2),
+    CaseSpec("grid_sampler", 2, 2, 4, (48, 48), 32, queries=64, negatives=64, bank_init="fill:400", caps=[500] * 4, func="asmc"),
+]
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    only = sys.argv[1:] or None
+    if only is None or "smoke" in only:
+        entry.smoke()
+    for spec in SPECS:
+        if only is not None and spec.name not in only:
+            continue
+        bank, ptr, caps = make_bank(spec)
+        if spec.dtype == "bf16":
+            for m in bank:
+                m[0] = m[0].to(torch.bfloat16).to(torch.float32)
+        for step in range(spec.steps):
+            g = {k: v.to(dev) for k, v in exact_case(spec, step).items()}
+            for fused in (False, True):
+                rep = g["rep"].clone().requires_grad_(True)
+                kw = {} if fused else {"_debug": {}}
+                _, loss = arco_b200.compute_contra_memobank_loss(
+                    rep, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"], g["low_mask"], g["high_mask"], bank, ptr, caps,
+                    g["rep_teacher"], delta_n=spec.delta_n, func=spec.func, num_queries=spec.queries,
+                    num_negatives=spec.negatives, temp=spec.temp, seed=77, **kw)
+                loss.backward()
+                torch.cuda.synchronize()
+                assert torch.isfinite(loss)
+        print("ok", spec.name, float(loss))
+    if only is None or "prepare" in only:
+        n, c, s = 2, 4, 64 * 64
+        gen = torch.Generator(device=dev).manual_seed(3)
+        pu, plt, put = (torch.randn(n, c, 64, 64, device=dev, generator=gen) for _ in range(3))
+        ll = torch.randint(0, c, (n, 64, 64), device=dev, generator=gen)
+        lu = torch.randint(-1, c, (n, 64, 64), device=dev, generator=gen)
+        out = arco_b200.prepare_contrast_inputs(pu, plt, put, ll, lu, 20.0)
+        torch.cuda.synchronize()
+        print("ok prepare", sorted(out)[:4])
+
+
+if __name__ == "__main__":
+    main()
