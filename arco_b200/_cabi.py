@@ -60,7 +60,7 @@ class Bank(C.Structure):
     _fields_ = [
         ("rows", C.c_void_p), ("head", C.c_void_p), ("len", C.c_void_p), ("queue_ptr", C.c_void_p),
         ("cap", _I32x), ("row_off", _I64x), ("row_dtype", C.c_int32), ("reserved", C.c_int32),
-        ("host_mirror", C.c_void_p), ("mirror_seq", C.c_uint64),
+        ("host_mirror", C.c_void_p), ("mirror_seq", C.c_uint64), ("host_queue_ptr", C.c_void_p),
     ]
 
 

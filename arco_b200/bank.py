@@ -105,23 +105,37 @@ class DeviceMemoryBank:
         self.head = head.to(self.device)
         self.len = length.to(self.device)
         self.ptr = ptr.to(self.device)
-        self.host_len = [int(x) for x in length[: self.classes]]
-        self.host_ptr = [int(x) for x in ptr[: self.classes]]
-        self._queue_ptrlis = queue_ptrlis
         self._plan_view = None          # device view of the last step's arco_plan
         self._dirty = False
-        self._edited = False            # rows replaced by the caller since the last settle: pending plans are stale
-        self._mirror = torch.zeros(self._MIRROR_SLOTS * self._MIRROR_STRIDE, dtype=torch.uint8, pin_memory=True)
+        self._edited = False            # rows replaced by the caller since the last step
+        # Pinned, PCIe-mapped host mirror the device writes by itself (zero-copy; see begin_step / poll):
+        #   [_MIRROR_SLOTS x _MIRROR_STRIDE] ring of finished steps' arco_plan + sequence number,
+        #   then int64[MAX_CLASSES] "live" queue pointers -- the caller's queue_prtlis[c] are rebound to 1-element views of
+        #   this array, so they follow the device with no host work at all.
+        self._mirror = torch.zeros(self._MIRROR_SLOTS * self._MIRROR_STRIDE + 8 * _cabi.MAX_CLASSES, dtype=torch.uint8,
+                                   pin_memory=True)
         self._mirror_np = self._mirror.numpy()
-        self._applied = 0               # last step number whose mirrored plan was applied (or skipped)
-        self.last_plan: Optional[_cabi.Plan] = None
+        n_plan = C.sizeof(_cabi.Plan)
+        words = self._mirror_np[: self._MIRROR_SLOTS * self._MIRROR_STRIDE].reshape(self._MIRROR_SLOTS, self._MIRROR_STRIDE)
+        self._seq_np = words[:, n_plan: n_plan + 8].view("<u8").reshape(-1)                       # [slots]
+        self._status_np = words[:, _cabi.Plan.status.offset: _cabi.Plan.status.offset + 4].view("<u4").reshape(-1)
+        self._ptr_alias = self._mirror[self._MIRROR_SLOTS * self._MIRROR_STRIDE:].view(torch.int64)   # [MAX_CLASSES]
+        self._ptr_alias[: self.classes] = ptr[: self.classes]
+        self._applied = 0               # last step number whose mirrored plan was looked at
+        self._latest = None             # (slot, step) of the newest plan that landed
+        self._host_len0 = [int(x) for x in length[: self.classes]]
+        self._plan_cache = (None, None)
+        self._settled_plan: Optional[_cabi.Plan] = None
+        self._settled_step = -1
         self.step = 0
+        self._bind_pointers(queue_ptrlis)
         self.c_struct = _cabi.Bank()
         self.c_struct.rows = self.rows.data_ptr()
         self.c_struct.row_dtype = _cabi.BF16 if narrow else _cabi.F32
         self.c_struct.head = self.head.data_ptr()
         self.c_struct.len = self.len.data_ptr()
         self.c_struct.queue_ptr = self.ptr.data_ptr()
+        self.c_struct.host_queue_ptr = self._ptr_alias.data_ptr()
         for c in range(self.classes):
             self.c_struct.cap[c] = self.caps[c]
             self.c_struct.row_off[c] = self.row_off[c]
@@ -140,7 +154,7 @@ class DeviceMemoryBank:
                 raise ValueError("memobank was adopted for a different device / feature size / class count")
             if [int(q) for q in queue_size] != bank.caps:
                 raise ValueError("queue_size changed after the memory bank was adopted")
-            bank._queue_ptrlis = queue_ptrlis
+            bank._bind_pointers(queue_ptrlis)
             if rep_dtype != torch.bfloat16:
                 bank.widen()                     # fp32 keys are not bf16-exact in general
             return bank
@@ -162,11 +176,25 @@ class DeviceMemoryBank:
     _MIRROR_SLOTS = 8          # ring of pinned plan copies: the host may run this many steps ahead of the device
     _MIRROR_STRIDE = 1536      # bytes per slot: arco_plan (1440 B) + u64 sequence number at offset sizeof(arco_plan)
 
+    def _bind_pointers(self, queue_ptrlis: list) -> None:
+        """Rebind the caller's ``queue_prtlis[c]`` to 1-element views of the pinned live-pointer array (like
+        ``memobank[c]`` is rebound to a :class:`BankSlot`): the device stores the reference's pointer values there at the
+        end of every step, so ``queue_prtlis[c][0]`` follows the device without any host-side work."""
+        views = self.__dict__.get("_alias_views")
+        if views is None:
+            views = self._alias_views = [self._ptr_alias[c: c + 1] for c in range(self.classes)]
+        if queue_ptrlis is self.__dict__.get("_queue_ptrlis") and queue_ptrlis[0] is views[0]:
+            return                                                # the steady state: one identity check per step
+        self._queue_ptrlis = queue_ptrlis
+        for c in range(self.classes):
+            if queue_ptrlis[c] is not views[c]:
+                queue_ptrlis[c] = views[c]
+
     def begin_step(self) -> None:
         """Point the step about to be launched at its slot of the pinned mirror ring.  The LAST CTA of the step's
-        InfoNCE kernel stores the final ``arco_plan`` there through the PCIe-mapped address and then the step number
-        (zero-copy: no memcpy, no event, nothing on the stream), which is how ``queue_prtlis``, the bank lengths and the
-        label-error status reach the host without the step ever synchronising (see :meth:`poll`)."""
+        InfoNCE kernel stores the final ``arco_plan`` there through the PCIe-mapped address, then the live queue pointers
+        and the step number (zero-copy: no memcpy, no event, nothing on the stream), which is how ``queue_prtlis``, the
+        bank lengths and the label-error status reach the host without the step ever synchronising (see :meth:`poll`)."""
         seq = self.step + 1
         self.c_struct.host_mirror = self._mirror.data_ptr() + (seq % self._MIRROR_SLOTS) * self._MIRROR_STRIDE
         self.c_struct.mirror_seq = seq
@@ -176,40 +204,65 @@ class DeviceMemoryBank:
         self._plan_view = plan_view
         self._dirty = True
         self._edited = False
+        self._settled_plan = None
         self.step += 1
 
-    def _apply(self, plan: "_cabi.Plan", step: int) -> None:
-        for c in range(self.classes):
-            self.host_len[c] = int(plan.bank_len[c])
-            self.host_ptr[c] = int(plan.queue_ptr[c])
-            self._queue_ptrlis[c][0] = self.host_ptr[c]
-        self.last_plan = plan
-        if step == self.step and not self._edited:
-            self._dirty = False
-        self.check_status(plan.status)
-
     def poll(self, block: bool = False) -> Optional[_cabi.Plan]:
-        """Non-blocking refresh of the host mirrors: the plan of every step that has FINISHED on the device is applied
-        in order -- ``queue_prtlis[c][0]``, the bank lengths, and the status bits (invalid labels raise ``ValueError``
-        here, i.e. at the start of the first step after the offending one has completed).  Never waits for the device
-        unless ``block``."""
+        """Non-blocking look at the host mirror: for every step that has FINISHED on the device since the last call, the
+        status word is checked (invalid labels / indices raise ``ValueError`` here, i.e. at the start of the first step
+        after the offending one has completed) and the newest landed plan is remembered for :attr:`host_len` /
+        :attr:`last_plan`.  Two 8-byte reads per finished step; never waits for the device unless ``block``."""
         if block:
             return self.settle()
-        n = C.sizeof(_cabi.Plan)
+        slots = self._MIRROR_SLOTS
         while self._applied < self.step:
             s_no = self._applied + 1
-            off = (s_no % self._MIRROR_SLOTS) * self._MIRROR_STRIDE
-            seq = int(self._mirror_np[off + n: off + n + 8].view("<u8")[0])
+            slot = s_no % slots
+            seq = int(self._seq_np[slot])
             if seq < s_no:
                 break                                             # that step has not finished yet
             self._applied = s_no
             if seq > s_no:
-                continue                                          # slot already reused by step s_no + k*SLOTS: skip
-            raw = self._mirror_np[off: off + n].tobytes()
-            if int(self._mirror_np[off + n: off + n + 8].view("<u8")[0]) != s_no:
-                continue                                          # overwritten while being read
-            self._apply(_cabi.Plan.from_buffer_copy(raw), s_no)
-        return self.last_plan
+                continue                                          # slot already reused by step s_no + k*slots: skip
+            status = int(self._status_np[slot])
+            self._latest = (slot, s_no)
+            if s_no == self.step and not self._edited:
+                self._dirty = False
+            if status:
+                self.check_status(status)
+        return None
+
+    def _landed_plan(self) -> Optional[_cabi.Plan]:
+        """The newest mirrored plan, parsed on demand (None if none has landed or its slot was reused meanwhile)."""
+        if self._latest is None:
+            return None
+        slot, s_no = self._latest
+        if self._plan_cache[0] == s_no:
+            return self._plan_cache[1]
+        off = slot * self._MIRROR_STRIDE
+        raw = self._mirror_np[off: off + C.sizeof(_cabi.Plan)].tobytes()
+        if int(self._seq_np[slot]) != s_no:
+            return None
+        plan = _cabi.Plan.from_buffer_copy(raw)
+        self._plan_cache = (s_no, plan)
+        return plan
+
+    @property
+    def host_ptr(self) -> List[int]:
+        """Reference pointer values (loss_helper_3d.py:24-30) as of the last step that finished on the device."""
+        return [int(v) for v in self._ptr_alias[: self.classes].tolist()]
+
+    @property
+    def host_len(self) -> List[int]:
+        """Bank lengths as of the newest step whose plan has landed on the host (no synchronisation)."""
+        plan = self._landed_plan()
+        if plan is None or self._edited:
+            return list(self._host_len0)
+        return [int(plan.bank_len[c]) for c in range(self.classes)]
+
+    @property
+    def last_plan(self) -> Optional[_cabi.Plan]:
+        return self._settled_plan if self._settled_plan is not None else self._landed_plan()
 
     @staticmethod
     def check_status(status: int) -> None:
@@ -233,17 +286,17 @@ class DeviceMemoryBank:
             return self.last_plan
         self._dirty = False
         self._edited = False
-        self._applied = self.step                                 # mirrored plans are superseded by the synchronous read below
         lens = self.len.cpu().tolist()
-        ptrs = self.ptr.cpu().tolist()
-        for c in range(self.classes):
-            self.host_len[c] = int(lens[c])
-            self.host_ptr[c] = int(ptrs[c])
-            self._queue_ptrlis[c][0] = self.host_ptr[c]
+        ptrs = self.ptr.cpu().tolist()                            # (stream-ordered copy: every launched step has finished)
+        self._applied = self.step
+        self._latest = None
+        self._host_len0 = [int(v) for v in lens[: self.classes]]
+        self._ptr_alias[: self.classes] = torch.tensor(ptrs[: self.classes], dtype=torch.int64)
         if self._plan_view is not None:
-            self.last_plan = _cabi.Plan.from_buffer_copy(self._plan_view.cpu().numpy().tobytes())
-            self.check_status(self.last_plan.status)
-        return self.last_plan
+            self._settled_plan = _cabi.Plan.from_buffer_copy(self._plan_view.cpu().numpy().tobytes())
+            self._settled_step = self.step
+            self.check_status(self._settled_plan.status)
+        return self._settled_plan
 
     def length(self, cls: int) -> int:
         self.settle()
@@ -271,7 +324,8 @@ class DeviceMemoryBank:
         self.rows[self.row_off[cls]: self.row_off[cls] + n] = value.to(self.device, self.rows.dtype)
         self.head[cls] = 0
         self.len[cls] = n
-        self.host_len[cls] = n
+        self._host_len0 = self.host_len
+        self._host_len0[cls] = n
         self._dirty = True
         self._edited = True
 

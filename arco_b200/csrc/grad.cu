@@ -4,7 +4,7 @@
 // index backward (zeros + index_put_(accumulate=True) for the rows picked at loss_helper_3d.py:377,
 // 455-457).  Here: one streaming zero-fill (P*D*e_g bytes written, the mandatory HBM term) and one
 // scatter of grad_out * grad_anchor into the <= C*Q anchor pixels.  Duplicated anchors (sampling
-// with replacement, trap 8) accumulate through atomics.
+// with replacement, trap 8) are summed in a fixed order by the first query that holds the pixel (no atomics).
 #include "arco_common.cuh"
 
 namespace arco {
@@ -20,27 +20,46 @@ __global__ void __launch_bounds__(256) fill_zero_kernel(unsigned char* __restric
     }
 }
 
-template <typename T>
-__device__ __forceinline__ void atomic_add_elem(T* p, float v);
-template <>
-__device__ __forceinline__ void atomic_add_elem<float>(float* p, float v) { atomicAdd(p, v); }
-template <>
-__device__ __forceinline__ void atomic_add_elem<__nv_bfloat16>(__nv_bfloat16* p, float v) {
-    atomicAdd(p, __float2bfloat16(v));
-}
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
+// One CTA per (position j, query q).  Sampling is with replacement, so several queries of one position may hold the SAME
+// pixel (trap 8: the reference's index_put_(accumulate=True) sums them).  Instead of atomics -- whose order, and with a
+// bf16 grad_rep whose per-add rounding, changes from run to run -- the FIRST query of every pixel sums all its duplicates
+// in ascending query order in fp32 and stores once: deterministic, one rounding, no read-modify-write.  (A pixel belongs to
+// one class, so duplicates never cross positions; grad_rep is zero at every touched pixel on entry.)
 template <typename T>
 __global__ void __launch_bounds__(128) grad_scatter_kernel(const float* __restrict__ g_anchor,
                                                             const int32_t* __restrict__ anchor_pix,
                                                             const float* __restrict__ grad_out, T* __restrict__ grad_rep,
-                                                            int D, int64_t S) {
+                                                            int D, int64_t S, int Q) {
+    extern __shared__ int32_t s_pix[];                       // [Q] pixels of this position
+    __shared__ int s_follower;
     const int row = blockIdx.x;
     const int pix = anchor_pix[row];
-    if (pix < 0) return;
+    if (pix < 0) return;                                     // block-uniform
+    const int j = row / Q, q = row - j * Q;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_follower = 0;
+    __syncthreads();
+    bool earlier = false;
+    for (int k = tid; k < Q; k += 128) {
+        const int v = anchor_pix[j * Q + k];
+        s_pix[k] = v;
+        earlier |= (k < q) && (v == pix);
+    }
+    if (earlier) s_follower = 1;
+    __syncthreads();
+    if (s_follower) return;                                  // an earlier query owns this pixel
     const float go = *grad_out;
     const int64_t b = pix / S, s = pix - b * S;
-    for (int d = threadIdx.x; d < D; d += blockDim.x)
-        atomic_add_elem<T>(grad_rep + (b * D + d) * S + s, go * g_anchor[(int64_t)row * D + d]);
+    for (int d = tid; d < D; d += 128) {
+        float acc = 0.f;
+        for (int k = q; k < Q; ++k)                          // block-uniform trip count and branch; s_pix reads broadcast
+            if (s_pix[k] == pix) acc += go * g_anchor[(int64_t)(j * Q + k) * D + d];
+        grad_rep[(b * D + d) * S + s] = from_float<T>(acc);
+    }
 }
 
 // Opt-in "sparse gradient" contract (arco_grad_scatter_sparse): grad_rep is a buffer the caller keeps across steps and that
@@ -80,12 +99,13 @@ static int launch_fill(const arco_dims& d, void* grad_rep, cudaStream_t st) {
 static int launch_scatter(const arco_dims& d, const float* grad_anchor, const int32_t* anchor_pix, const float* grad_out,
                           void* grad_rep, cudaStream_t st) {
     const int rows = d.classes * d.queries;
+    ARCO_REQUIRE(d.queries <= 11264, "num_queries > 11264: the per-position pixel list no longer fits the scatter kernel's shared memory");
     if (d.rep_dtype == ARCO_BF16)
-        arco::grad_scatter_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(grad_anchor, anchor_pix, grad_out,
-                                                                        (__nv_bfloat16*)grad_rep, d.feat, d.space);
+        arco::grad_scatter_kernel<__nv_bfloat16><<<rows, 128, (size_t)d.queries * 4, st>>>(grad_anchor, anchor_pix, grad_out,
+                                                                                           (__nv_bfloat16*)grad_rep, d.feat, d.space, d.queries);
     else
-        arco::grad_scatter_kernel<float><<<rows, 128, 0, st>>>(grad_anchor, anchor_pix, grad_out, (float*)grad_rep,
-                                                                d.feat, d.space);
+        arco::grad_scatter_kernel<float><<<rows, 128, (size_t)d.queries * 4, st>>>(grad_anchor, anchor_pix, grad_out, (float*)grad_rep,
+                                                                                   d.feat, d.space, d.queries);
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
 }

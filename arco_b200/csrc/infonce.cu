@@ -35,7 +35,8 @@ struct InfoParams {
     const float* momentum;       // [C][Q][D] or NULL
     const int32_t* momentum_on;  // device flag: momentum tensor has a non-zero entry (:489)
     float* proto_out;            // [C][Q][D] positive_feat written per (bank class, query) (:497), or NULL
-    void* host_mirror;           // arco_bank.host_mirror / mirror_seq
+    void* host_mirror;           // arco_bank.host_mirror / mirror_seq / host_queue_ptr
+    int64_t* host_queue_ptr;
     uint64_t mirror_seq;
     float ema_decay, ema_keep;   // ema_keep = float32(1 - ema_decay) formed in DOUBLE by the caller, as the reference's Python scalar is (:491-495)
     int64_t row_off[ARCO_MAX_CLASSES];
@@ -258,6 +259,7 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
         const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(p.plan);
         volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(p.host_mirror);
         for (int i = tid; i < (int)(sizeof(arco_plan) / 4); i += 128) dst[i] = src[i];
+        if (p.host_queue_ptr && tid < p.C) reinterpret_cast<volatile long long*>(p.host_queue_ptr)[tid] = p.plan->queue_ptr[tid];
         __threadfence_system();
         __syncthreads();
         if (tid == 0) {
@@ -720,7 +722,7 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     p.loss = loss; p.g_anchor = grad_anchor; p.anchor_pix = anchor_pix; p.logits = logits;
     p.loss_parts = (float*)(ws + L.loss_parts);
     p.momentum = momentum; p.momentum_on = momentum_on; p.proto_out = proto_out; p.ema_decay = ema_decay; p.ema_keep = ema_keep;
-    p.host_mirror = bank->host_mirror; p.mirror_seq = bank->mirror_seq;
+    p.host_mirror = bank->host_mirror; p.mirror_seq = bank->mirror_seq; p.host_queue_ptr = bank->host_queue_ptr;
     ARCO_REQUIRE(momentum == nullptr || momentum_on != nullptr, "momentum needs the device flag momentum_on");
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
     p.S = d.space; p.C = d.classes; p.D = d.feat; p.Q = d.queries; p.N = d.negatives;

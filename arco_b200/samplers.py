@@ -85,7 +85,7 @@ def dequeue_and_enqueue(keys, queue, queue_ptr, queue_size):
         bank.replace_rows(c, merged)
         ptr = queue_size if full else (int(queue_ptr) + n) % queue_size
         bank.ptr[c] = ptr
-        bank.host_ptr[c] = ptr
+        bank._ptr_alias[c] = ptr
     else:
         merged = torch.cat((queue[0], keys.detach().to(queue[0].device)), dim=0)
         full = merged.shape[0] >= queue_size

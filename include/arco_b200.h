@@ -131,6 +131,7 @@ typedef struct arco_bank {
        queue_prtlis and the status bits by polling memory -- no memcpy, no event, no synchronisation. */
     void*    host_mirror;
     uint64_t mirror_seq;
+    int64_t* host_queue_ptr;                  /* NULL, or device-accessible pinned int64[C]: the live queue_prtlis values */
 } arco_bank;
 
 ARCO_API const char* arco_version(void);
@@ -218,7 +219,9 @@ ARCO_API int arco_grad_scatter(const arco_dims* dims, const float* grad_anchor, 
                       const float* grad_out, void* grad_rep, void* stream);
 
 /* The two halves of arco_grad_scatter, so that a caller can run the (input-independent) zero fill early on
- * a side stream, underneath the forward kernels, and only scatter in backward. */
+ * a side stream, underneath the forward kernels, and only scatter in backward.  arco_grad_scatter_add expects the
+ * zero-filled buffer: per pixel the duplicates of a position are summed in ascending query order in fp32 and STORED once
+ * (deterministic; no atomics), so a non-zero value already at an anchor pixel would be overwritten, not added to. */
 ARCO_API int arco_grad_zero(const arco_dims* dims, void* grad_rep, void* stream);
 ARCO_API int arco_grad_scatter_add(const arco_dims* dims, const float* grad_anchor, const int32_t* anchor_pix,
                                    const float* grad_out, void* grad_rep, void* stream);

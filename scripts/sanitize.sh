@@ -8,8 +8,7 @@ CS=${CS:-/usr/local/cuda/bin/compute-sanitizer}
 for tool in memcheck racecheck synccheck initcheck; do
   extra=""
   [ "$tool" = "racecheck" ] && extra="--racecheck-report all"
-  [ "$tool" = "initcheck" ] && extra="--track-unused-memory no"
-  timeout ${SAN_TIMEOUT:-900} $CS --tool $tool $extra --print-limit 40 --error-exitcode 77 \
+  timeout ${SAN_TIMEOUT:-900} $CS --tool $tool $extra --print-limit 400 --error-exitcode 77 \
       --log-file gpurun_out/sanitizer/$tool.log python scripts/sanitize_run.py "$@" > gpurun_out/sanitizer/$tool.out 2>&1
   echo "$tool rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer/$tool.log | tail -1)"
 done

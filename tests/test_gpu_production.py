@@ -236,3 +236,37 @@ def test_out_of_range_injected_index_is_flagged():
         x["rep_teacher"], delta_n=0.97, num_queries=q, num_negatives=n, _inject={"anchor": anchors, "neg": negs})
     with pytest.raises(ValueError, match="sample index"):
         list(keys)
+
+
+@pytest.mark.parametrize("workload,batch", [("acdc2d_loss", None), ("acdc2d_trainstep", (2, 2))])
+def test_sparse_grad_contract_matches_the_dense_gradient(workload, batch):
+    """Opt-in ``sparse_grad=True``: the op-owned gradient buffer (previous step's anchor pixels cleared, no dense zero
+    fill) must hold exactly the values of the default dense ``grad_rep``, step after step."""
+    import arco_b200
+    dev = torch.device("cuda", 0)
+    n_lab, n_unlab = batch if batch else (None, None)
+    grads = {}
+    for sparse in (False, True):
+        spec, x = bench_inputs(workload, dev, seed=13, n_lab=n_lab, n_unlab=n_unlab)
+        bank, ptr, caps = bench_bank(spec, seed=5)
+        got = []
+        for step in range(3):
+            leaf = x["rep"].clone().requires_grad_(True)
+            rep = leaf * 1                                       # non-leaf, as in the trainers (output of q_representation)
+            seen = []
+            rep.register_hook(lambda g, seen=seen: seen.append(g.clone()))
+            _, loss = arco_b200.compute_contra_memobank_loss(
+                rep, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"], bank, ptr, caps,
+                x["rep_teacher"], delta_n=0.97, func="smc", num_queries=Q, num_negatives=N, seed=4242 + step,
+                sparse_grad=sparse)
+            loss.backward()
+            torch.cuda.synchronize()
+            got.append((loss.detach().clone(), seen[0]))
+        grads[sparse] = got
+        del x, bank
+        gc.collect()
+        torch.cuda.empty_cache()
+    for (l0, g0), (l1, g1) in zip(grads[False], grads[True]):
+        assert torch.equal(l0, l1)
+        assert torch.equal(g0, g1)
+        assert float(g0.float().abs().sum()) > 0

@@ -17,6 +17,9 @@ SPECS = [
     CaseSpec("pipe8_f32", 2, 2, 4, (48, 48), 64, queries=32, negatives=16, bank_init="fill:100", caps=[150] * 4),
     CaseSpec("pipe8_f32_d200", 1, 1, 8, (32, 32), 200, queries=16, negatives=7, bank_init="fill:64", caps=[100] * 8),
     CaseSpec("pipe4_f32_c19", 1, 1, 19, (32, 64), 256, queries=8, negatives=16, bank_init="fill:40", caps=[64] * 19),
+    CaseSpec("tc32_f32_d512", 1, 2, 5, (32, 48), 512, queries=8, negatives=8, bank_init="fill:40", caps=[64] * 5),
+    CaseSpec("tc32_f32_d384_c16", 2, 1, 16, (40, 40), 384, queries=8, negatives=8, bank_init="fill:40", caps=[64] * 16, mask_frac=0.6),
+    CaseSpec("tc32_f32_d132_ragged", 1, 1, 3, (24, 28), 132, queries=8, negatives=8, bank_init="fill:40", caps=[64] * 3),
     CaseSpec("pipe4_bf16_c19", 1, 1, 19, (32, 32), 48, queries=8, negatives=5, dtype="bf16", bank_init="fill:40", caps=[64] * 19),
     CaseSpec("small_la", 1, 1, 2, (16, 16, 12), 16, queries=16, negatives=8, bank_init="randn1", func="asmc"),
     CaseSpec("small_c3_d32_bf16", 1, 2, 3, (32, 40), 32, queries=8, negatives=8, dtype="bf16", bank_init="fill:30", caps=[40] * 3),
