@@ -10,6 +10,7 @@ import ctypes as C
 import os
 
 MAX_CLASSES = 32
+COUNTER_WORDS = 64
 TILE = 1024
 F32, BF16 = 0, 1
 LABEL_ONEHOT_I64, LABEL_INDEX_I64 = 0, 1
@@ -52,7 +53,7 @@ class Plan(C.Structure):
         ("bank_len", _I32x), ("bank_head", _I32x),
         ("queue_ptr", _I64x),
         ("inv_scale", C.c_float), ("status", C.c_uint32), ("scan_done", C.c_uint32), ("loss_done", C.c_uint32),
-        ("replanned", C.c_uint32), ("reserved", C.c_uint32),
+        ("replanned", C.c_uint32), ("proto_done", C.c_uint32), ("proto_done2", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -60,7 +61,7 @@ class Bank(C.Structure):
     _fields_ = [
         ("rows", C.c_void_p), ("head", C.c_void_p), ("len", C.c_void_p), ("queue_ptr", C.c_void_p),
         ("cap", _I32x), ("row_off", _I64x), ("row_dtype", C.c_int32), ("reserved", C.c_int32),
-        ("host_mirror", C.c_void_p), ("mirror_seq", C.c_uint64), ("host_queue_ptr", C.c_void_p),
+        ("host_mirror", C.c_void_p), ("mirror_seq", C.c_uint64), ("host_queue_ptr", C.c_void_p), ("counters", C.c_void_p),
     ]
 
 
@@ -90,6 +91,7 @@ def _load():
         "arco_workspace_layout": (C.c_int, [dp, C.POINTER(WsLayout)]),
         "arco_label_onehot": (C.c_int, [vp, vp, i64, i32, i64, vp]),
         "arco_classify_count": (C.c_int, [dp, vp, vp, vp, vp, vp, vp, f32, f32, i32, i32, vp, vp]),
+        "arco_classify_plan": (C.c_int, [dp, vp, vp, vp, vp, vp, vp, f32, f32, i32, i32, bp, vp, vp]),
         "arco_scan_plan": (C.c_int, [dp, bp, vp, vp]),
         "arco_replan_global": (C.c_int, [dp, vp, vp, vp]),
         "arco_proto_enqueue": (C.c_int, [dp, vp, bp, vp, vp, vp]),

@@ -136,6 +136,8 @@ class DeviceMemoryBank:
         self.c_struct.len = self.len.data_ptr()
         self.c_struct.queue_ptr = self.ptr.data_ptr()
         self.c_struct.host_queue_ptr = self._ptr_alias.data_ptr()
+        self._counters = torch.zeros(_cabi.COUNTER_WORDS, dtype=torch.int32, device=self.device)   # self-cleaning tickets
+        self.c_struct.counters = self._counters.data_ptr()
         for c in range(self.classes):
             self.c_struct.cap[c] = self.caps[c]
             self.c_struct.row_off[c] = self.row_off[c]

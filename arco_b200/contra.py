@@ -8,8 +8,8 @@ spatial axes are flattened to ``S`` and never permuted.
 
 Pipeline (all on ``torch.cuda.current_stream()``, no host synchronisation in forward or backward):
 
-  arco_classify_count -> arco_scan_plan -> arco_proto_enqueue -> [NCCL all-reduce of the C x (D+1)
-  fp64 prototype sums] -> arco_sample (or injected indices) -> arco_infonce        (forward)
+  arco_classify_plan (classify + scans + plan) -> arco_proto_enqueue (+ fp64 finalize) -> [exchange of the
+  C x (D+1) fp64 prototype sums] -> arco_sample (or injected indices) -> arco_infonce        (forward)
   arco_grad_scatter                                                                 (backward)
 
 There is no CPU path and no PyTorch fallback: non-CUDA tensors raise.
@@ -224,14 +224,18 @@ class _ContraLoss(torch.autograd.Function):
             _cabi.check(lib.arco_grad_zero(d, buf.data_ptr(), side0.cuda_stream), "arco_grad_zero")
             st["grad_buf"], st["side"] = buf, side0
 
-        _cabi.check(lib.arco_classify_count(
-            d, st["label_l"].data_ptr() if st["label_l"] is not None else None,
-            st["label_u"].data_ptr() if st["label_u"] is not None else None,
-            st["prob_l"].data_ptr() if st["prob_l"] is not None else None,
-            st["prob_u"].data_ptr() if st["prob_u"] is not None else None,
-            st["low_mask"].data_ptr(), st["high_mask"].data_ptr(),
-            DELTA_P, float(st["delta_n"]), LOW_RANK, HIGH_RANK, wsp, sp), "arco_classify_count")
-        _cabi.check(lib.arco_scan_plan(d, b, wsp, sp), "arco_scan_plan")
+        ins = (st["label_l"].data_ptr() if st["label_l"] is not None else None,
+               st["label_u"].data_ptr() if st["label_u"] is not None else None,
+               st["prob_l"].data_ptr() if st["prob_l"] is not None else None,
+               st["prob_u"].data_ptr() if st["prob_u"] is not None else None,
+               st["low_mask"].data_ptr(), st["high_mask"].data_ptr(),
+               DELTA_P, float(st["delta_n"]), LOW_RANK, HIGH_RANK)
+        if st["debug"] is not None and st["debug"].get("legacy_scan"):
+            # the two-launch form of the C ABI (memset + classify, then the stand-alone scan/plan kernel)
+            _cabi.check(lib.arco_classify_count(d, *ins, wsp, sp), "arco_classify_count")
+            _cabi.check(lib.arco_scan_plan(d, b, wsp, sp), "arco_scan_plan")
+        else:
+            _cabi.check(lib.arco_classify_plan(d, *ins, b, wsp, sp), "arco_classify_plan")
         proto_sums = torch.empty((Cn, D + 1), dtype=torch.float64, device=dev)
         p2p = _p2p_exchange(st["group"], dev, Cn * (D + 1)) if st["group"] is not None else None
         proto_local = proto_sums                            # where the prototype kernel writes this rank's sums

@@ -12,6 +12,7 @@
 // so every global access is a 16-byte vector (int64 labels: two per pixel pair).  HBM-bound:
 // algorithmic bytes = P * (8C + 4C + 8) read + P written.
 #include "arco_common.cuh"
+#include "plan_common.cuh"
 
 namespace arco {
 
@@ -31,7 +32,73 @@ struct ClassifyParams {
     int32_t n_lab, C, tpi, NT;
     int32_t label_kind, low_rank, high_rank;
     float delta_p, delta_n;
+    // arco_classify_plan only: scan + plan run in this launch's tail (see classify_tail)
+    uint32_t* ctr;             // bank->counters: [0,32) low-valid totals, [32] status, [33] tiles done, [34] rows scanned
+    uint32_t* off_anchor;
+    uint32_t* off_key;
+    PlanBank bank;
+    int32_t Q;
 };
+
+enum { CTR_STATUS = 32, CTR_TILES = 33, CTR_ROWS = 34 };
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Tail of arco_classify_plan, entered by every CTA after its tile's counts are written.  The min(NT, 2C) CTAs that finish
+// LAST wait until every tile is done (they took their ticket after their own stores, so everything they wait for is
+// already running or finished -- at most 2C <= 64 CTAs ever spin), scan one row of tile counts each (row = anchor or key
+// counts of one class), and the last scanner derives the plan with one warp and re-zeroes the persistent counters.
+__device__ __forceinline__ void classify_tail(const ClassifyParams& p) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    __shared__ int s_role;
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const int n_scan = min(p.NT, 2 * p.C);
+    if (tid == 0) {
+        __threadfence();
+        const uint32_t t = atomicAdd(&p.ctr[CTR_TILES], 1u);
+        s_role = (int)t >= p.NT - n_scan ? (int)t - (p.NT - n_scan) : -1;
+    }
+    __syncthreads();
+    const int role = s_role;
+    if (role < 0) return;
+    if (tid == 0) {
+        while (ld_acquire_gpu(&p.ctr[CTR_TILES]) < (uint32_t)p.NT) __nanosleep(40);
+    }
+    __syncthreads();
+    for (int row = role; row < 2 * p.C; row += n_scan) {
+        const int c = row % p.C;
+        const bool is_key = row >= p.C;
+        const uint32_t* cnt = (is_key ? p.cnt_key : p.cnt_anchor) + (int64_t)c * p.NT;
+        uint32_t* off = (is_key ? p.off_key : p.off_anchor) + (int64_t)c * (p.NT + 1);
+        const uint32_t total = scan_row_block<256>(cnt, off, p.NT, s_warp, &s_carry);
+        if (tid == 0) { if (is_key) p.plan->n_key[c] = total; else p.plan->n_anchor[c] = total; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(&p.ctr[CTR_ROWS], 1u) == (uint32_t)n_scan - 1;
+    }
+    __syncthreads();
+    if (!s_last || tid >= 32) return;
+    __threadfence();
+    volatile arco_plan* vpl = p.plan;
+    volatile uint32_t* vc = p.ctr;
+    const bool on = tid < p.C;
+    const uint32_t lv = on ? vc[tid] : 0u;
+    const uint32_t status = vc[CTR_STATUS];
+    derive_plan_warp(p.plan, p.bank, p.C, p.Q, lv, on ? vpl->n_anchor[tid] : 0u, on ? vpl->n_key[tid] : 0u, status);
+    // leave the persistent counters zero for the next step
+    __syncwarp();
+    vc[tid] = 0u;
+    if (tid == 0) { vc[CTR_STATUS] = 0u; vc[CTR_TILES] = 0u; vc[CTR_ROWS] = 0u; }
+}
+
 
 template <int NV>
 struct PixVec;
@@ -54,7 +121,7 @@ struct PixVec<1> {
 };
 
 // NV = pixels per thread per pass (4: vector path, 1: scalar path for unaligned / odd S)
-template <int NV>
+template <int NV, bool TAIL>
 __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p) {
     __shared__ uint32_t s_anchor[ARCO_MAX_CLASSES], s_key[ARCO_MAX_CLASSES], s_lv[ARCO_MAX_CLASSES];
     __shared__ uint32_t s_flagged, s_status;
@@ -178,11 +245,15 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p) {
     if (tid < C) {
         p.cnt_anchor[(int64_t)tid * p.NT + tile] = s_anchor[tid];
         p.cnt_key[(int64_t)tid * p.NT + tile] = s_key[tid];
-        if (s_lv[tid]) atomicAdd(&p.plan->lv_count[tid], s_lv[tid]);
+        if (s_lv[tid]) atomicAdd(TAIL ? &p.ctr[tid] : &p.plan->lv_count[tid], s_lv[tid]);
     }
     if (tid == 0) {
         p.tile_flagged[tile] = s_flagged;
-        if (s_status) atomicOr(&p.plan->status, s_status);
+        if (s_status) atomicOr(TAIL ? &p.ctr[CTR_STATUS] : &p.plan->status, s_status);
+    }
+    if (TAIL) {
+        __syncthreads();
+        classify_tail(p);
     }
 }
 
@@ -214,10 +285,9 @@ extern "C" int arco_label_onehot(const int64_t* labels, float* out, int64_t batc
     return ARCO_OK;
 }
 
-extern "C" int arco_classify_count(const arco_dims* dims, const int64_t* label_l, const int64_t* label_u,
-                                   const float* prob_l, const float* prob_u, const float* low_mask,
-                                   const float* high_mask, float delta_p, float delta_n, int32_t low_rank,
-                                   int32_t high_rank, void* workspace, void* stream) {
+static int classify_launch(const arco_dims* dims, const int64_t* label_l, const int64_t* label_u, const float* prob_l,
+                           const float* prob_u, const float* low_mask, const float* high_mask, float delta_p, float delta_n,
+                           int32_t low_rank, int32_t high_rank, const arco_bank* bank, void* workspace, void* stream) {
     ARCO_REQUIRE(dims && workspace, "arco_classify_count: NULL dims/workspace");
     const arco_dims& d = *dims;
     ARCO_REQUIRE(d.classes >= 1 && d.classes <= ARCO_MAX_CLASSES, "classes must be in [1, 32]");
@@ -229,7 +299,8 @@ extern "C" int arco_classify_count(const arco_dims* dims, const int64_t* label_l
     arco::compute_layout(d, &L);
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
-    ARCO_CUDA_CHECK(cudaMemsetAsync(ws + L.plan, 0, sizeof(arco_plan), st));
+    const bool tail = bank != nullptr;
+    if (!tail) ARCO_CUDA_CHECK(cudaMemsetAsync(ws + L.plan, 0, sizeof(arco_plan), st));
 
     arco::ClassifyParams p;
     p.label_l = label_l; p.label_u = label_u; p.prob_l = prob_l; p.prob_u = prob_u;
@@ -242,12 +313,46 @@ extern "C" int arco_classify_count(const arco_dims* dims, const int64_t* label_l
     p.S = d.space; p.n_lab = d.n_lab; p.C = d.classes; p.tpi = L.tiles_per_image; p.NT = L.n_tiles;
     p.label_kind = d.label_kind; p.low_rank = low_rank; p.high_rank = high_rank;
     p.delta_p = delta_p; p.delta_n = delta_n;
+    p.ctr = nullptr; p.off_anchor = (uint32_t*)(ws + L.off_anchor); p.off_key = (uint32_t*)(ws + L.off_key); p.Q = d.queries;
+    p.bank.head = nullptr; p.bank.len = nullptr; p.bank.ptr = nullptr;
+    for (int c = 0; c < ARCO_MAX_CLASSES; ++c) p.bank.cap[c] = 0;
+    if (tail) {
+        ARCO_REQUIRE(bank->counters != nullptr, "arco_classify_plan: bank->counters is NULL (needs ARCO_COUNTER_WORDS zeroed uint32)");
+        p.ctr = bank->counters;
+        p.bank.head = bank->head; p.bank.len = bank->len; p.bank.ptr = bank->queue_ptr;
+        for (int c = 0; c < d.classes; ++c) {
+            ARCO_REQUIRE(bank->cap[c] > 0, "queue_size must be positive");
+            p.bank.cap[c] = bank->cap[c];
+        }
+    }
 
     auto aligned16 = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
     const bool vec = (d.space % 4 == 0) && aligned16(label_l) && aligned16(label_u) && aligned16(prob_l) &&
                      aligned16(prob_u) && aligned16(low_mask) && aligned16(high_mask);
-    if (vec) arco::classify_kernel<4><<<L.n_tiles, 256, 0, st>>>(p);
-    else arco::classify_kernel<1><<<L.n_tiles, 256, 0, st>>>(p);
+    if (tail) {
+        if (vec) arco::classify_kernel<4, true><<<L.n_tiles, 256, 0, st>>>(p);
+        else arco::classify_kernel<1, true><<<L.n_tiles, 256, 0, st>>>(p);
+    } else {
+        if (vec) arco::classify_kernel<4, false><<<L.n_tiles, 256, 0, st>>>(p);
+        else arco::classify_kernel<1, false><<<L.n_tiles, 256, 0, st>>>(p);
+    }
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
+}
+
+extern "C" int arco_classify_count(const arco_dims* dims, const int64_t* label_l, const int64_t* label_u,
+                                   const float* prob_l, const float* prob_u, const float* low_mask,
+                                   const float* high_mask, float delta_p, float delta_n, int32_t low_rank,
+                                   int32_t high_rank, void* workspace, void* stream) {
+    return classify_launch(dims, label_l, label_u, prob_l, prob_u, low_mask, high_mask, delta_p, delta_n, low_rank, high_rank,
+                           nullptr, workspace, stream);
+}
+
+extern "C" int arco_classify_plan(const arco_dims* dims, const int64_t* label_l, const int64_t* label_u,
+                                  const float* prob_l, const float* prob_u, const float* low_mask,
+                                  const float* high_mask, float delta_p, float delta_n, int32_t low_rank,
+                                  int32_t high_rank, const arco_bank* bank, void* workspace, void* stream) {
+    ARCO_REQUIRE(bank != nullptr, "arco_classify_plan: NULL bank");
+    return classify_launch(dims, label_l, label_u, prob_l, prob_u, low_mask, high_mask, delta_p, delta_n, low_rank, high_rank,
+                           bank, workspace, stream);
 }

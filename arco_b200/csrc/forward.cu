@@ -1,5 +1,5 @@
-// One-call forward of the whole path (single GPU, or one batch shard with the peer-memory exchange step): classify -> scan/plan -> [sampler on a side stream] ->
-// prototype + enqueue -> InfoNCE, plus the optional early zero fill of grad_rep on a second side stream.
+// One-call forward of the whole path (single GPU, or one batch shard with the peer-memory exchange step): classify+scan+plan (one launch)
+// -> [sampler on a side stream] -> prototype + enqueue + fp64 finalize (one launch) -> InfoNCE, plus the optional early zero fill of grad_rep on a second side stream.
 // Same kernels and order as driving the stage entry points one by one (arco_b200/contra.py does that when an
 // all-reduce or injected indices sit between the stages); this entry exists to keep the host cost of a step at one
 // FFI call, which matters for the launch-bound small shapes (ACDC 256x256 D=64, LA 112x112x80 D=16).
@@ -47,10 +47,10 @@ extern "C" int arco_forward(const arco_dims* dims, const arco_step_io* io, const
         if ((rc = arco_grad_zero(dims, io->grad_prefill, ss->s[1])) != ARCO_OK) return rc;
         ARCO_CUDA_CHECK(cudaEventRecord(ss->join_fill, ss->s[1]));
     }
-    if ((rc = arco_classify_count(dims, io->label_l, io->label_u, io->prob_l, io->prob_u, io->low_mask, io->high_mask,
-                                  io->delta_p, io->delta_n, io->low_rank, io->high_rank, workspace, main_st)) != ARCO_OK)
+    // classify + ordered-compaction scans + plan in ONE launch (no memset: self-cleaning counters in bank->counters)
+    if ((rc = arco_classify_plan(dims, io->label_l, io->label_u, io->prob_l, io->prob_u, io->low_mask, io->high_mask,
+                                 io->delta_p, io->delta_n, io->low_rank, io->high_rank, bank, workspace, main_st)) != ARCO_OK)
         return rc;
-    if ((rc = arco_scan_plan(dims, bank, workspace, main_st)) != ARCO_OK) return rc;
     // the sampler only needs the plan: run it underneath the prototype pass
     ARCO_CUDA_CHECK(cudaEventRecord(ss->fork, main_st));
     ARCO_CUDA_CHECK(cudaStreamWaitEvent(ss->s[0], ss->fork, 0));

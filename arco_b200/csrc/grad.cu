@@ -34,30 +34,41 @@ __global__ void __launch_bounds__(128) grad_scatter_kernel(const float* __restri
                                                             const int32_t* __restrict__ anchor_pix,
                                                             const float* __restrict__ grad_out, T* __restrict__ grad_rep,
                                                             int D, int64_t S, int Q) {
-    extern __shared__ int32_t s_pix[];                       // [Q] pixels of this position
-    __shared__ int s_follower;
+    extern __shared__ int32_t s_dup[];                       // [Q] later queries of this position that hold the same pixel
+    __shared__ int s_ndup;
     const int row = blockIdx.x;
     const int pix = anchor_pix[row];
     if (pix < 0) return;                                     // block-uniform
     const int j = row / Q, q = row - j * Q;
     const int tid = threadIdx.x;
-    if (tid == 0) s_follower = 0;
-    __syncthreads();
-    bool earlier = false;
+    bool earlier = false, later = false;
     for (int k = tid; k < Q; k += 128) {
-        const int v = anchor_pix[j * Q + k];
-        s_pix[k] = v;
-        earlier |= (k < q) && (v == pix);
+        const bool same = anchor_pix[j * Q + k] == pix;
+        earlier |= same && k < q;
+        later |= same && k > q;
     }
-    if (earlier) s_follower = 1;
-    __syncthreads();
-    if (s_follower) return;                                  // an earlier query owns this pixel
+    if (__syncthreads_or(earlier)) return;                   // an earlier query owns this pixel
+    const int any_later = __syncthreads_or(later);
+    if (any_later) {                                         // rare: ordered list of the duplicates, built by one warp
+        if (tid < 32) {
+            int n = 0;
+            for (int k0 = q + 1; k0 < Q; k0 += 32) {
+                const int k = k0 + tid;
+                const bool same = k < Q && anchor_pix[j * Q + k] == pix;
+                const uint32_t bal = __ballot_sync(0xffffffffu, same);
+                if (same) s_dup[n + __popc(bal & ((1u << tid) - 1u))] = k;
+                n += __popc(bal);
+            }
+            if (tid == 0) s_ndup = n;
+        }
+        __syncthreads();
+    }
+    const int ndup = any_later ? s_ndup : 0;
     const float go = *grad_out;
     const int64_t b = pix / S, s = pix - b * S;
     for (int d = tid; d < D; d += 128) {
-        float acc = 0.f;
-        for (int k = q; k < Q; ++k)                          // block-uniform trip count and branch; s_pix reads broadcast
-            if (s_pix[k] == pix) acc += go * g_anchor[(int64_t)(j * Q + k) * D + d];
+        float acc = go * g_anchor[(int64_t)row * D + d];
+        for (int i = 0; i < ndup; ++i) acc += go * g_anchor[(int64_t)(j * Q + s_dup[i]) * D + d];
         grad_rep[(b * D + d) * S + s] = from_float<T>(acc);
     }
 }

@@ -253,6 +253,7 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
         float s = 0.f;
         for (int i = 0; i < 128; ++i) s += s_fold[i];
         p.loss[0] = s;
+        p.plan->loss_done = 0;                               // re-arm: the entry point may run again on the same plan
     }
     if (p.host_mirror) {
         // zero-copy host mirror of the step summary (arco_bank.host_mirror): plan words, system fence, sequence number

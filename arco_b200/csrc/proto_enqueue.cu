@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "arco_common.cuh"
+#include "proto_tail.cuh"
 
 namespace arco {
 
@@ -35,6 +36,8 @@ struct ProtoParams {
     int32_t B, C, D, tpi, NT, NDC;
     int32_t vec_ok;        // 16-byte loads along S are legal
     int32_t bank_bf16;     // ring rows are bf16 (only with a bf16 rep_teacher: the narrowing is exact)
+    double* proto_sums;    // [C][D+1] fp64, written by the in-kernel finalize (proto_tail.cuh)
+    int32_t rows;          // partial rows (CTA groups)
 };
 
 // four floats that came from bf16 values -> their four bf16 bit patterns (exact: the low halves are zero)
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(256) proto_enqueue_kernel(ProtoParams p) {
         }
         *reinterpret_cast<float4*>(p.partials + ((int64_t)grp * C + c) * D + d0 + 4 * k) = s;
     }
+    proto_finalize_tail(p.partials, p.rows, C, D, const_cast<arco_plan*>(p.plan), p.proto_sums);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -575,6 +579,7 @@ __global__ void __launch_bounds__(256, 2) proto_pipe_kernel(ProtoParams p) {
         }
         *reinterpret_cast<float4*>(p.partials + ((int64_t)grp * C + c) * D + d0 + EPL * k + 4 * h) = sum;
     }
+    proto_finalize_tail(p.partials, p.rows, C, D, const_cast<arco_plan*>(p.plan), p.proto_sums);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -648,36 +653,17 @@ __global__ void __launch_bounds__(256) proto_small_kernel(ProtoParams p) {
         for (int w = 0; w < 8; ++w) v += s_part[w][tid];
         p.partials[(int64_t)blockIdx.x * CC * DD + tid] = v;
     }
-}
-
-// One warp per output element: lanes stride over the partial rows (independent loads in flight), then a
-// fixed-order shuffle tree in fp64 -- deterministic, and the fp64 buffer is what a multi-GPU caller all-reduces.
-__global__ void __launch_bounds__(128) proto_finalize_kernel(const float* __restrict__ partials, int rows, int C, int D,
-                                                            const arco_plan* __restrict__ plan,
-                                                            double* __restrict__ proto_sums) {
-    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (i >= C * (D + 1)) return;
-    const int c = i / (D + 1), d = i % (D + 1);
-    if (d == D) {
-        if (lane == 0) proto_sums[i] = (double)plan->lv_count[c];
-        return;
-    }
-    double s = 0.0;
-    for (int r = lane; r < rows; r += 32) s += (double)partials[((int64_t)r * C + c) * D + d];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) proto_sums[i] = s;
+    proto_finalize_tail(p.partials, p.rows, CC, DD, const_cast<arco_plan*>(p.plan), p.proto_sums);
 }
 
 // Kernel variant for a problem: the 8-dims-per-lane kernel needs 16-byte vector loads and its 8 KB * C
 // stream accumulators to fit beside the tile; otherwise the 4-dims-per-lane kernel (4 KB * C) runs.
 bool proto_tc_supported(const arco_dims& d);
 int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank* bank, const arco_ws_layout& L, char* ws,
-                    int rows, cudaStream_t st);
+                    int rows, double* proto_sums, cudaStream_t st);
 bool proto_tc32_supported(const arco_dims& d);
 int launch_proto_tc32(const arco_dims& d, const void* rep_teacher, const arco_bank* bank, const arco_ws_layout& L, char* ws,
-                      int rows, cudaStream_t st);
+                      int rows, double* proto_sums, cudaStream_t st);
 
 struct ProtoCfg {
     int kind;         // 0 scalar fallback (proto_enqueue_kernel), 1 pipelined (proto_pipe_kernel), 2 small (proto_small_kernel),
@@ -815,16 +801,13 @@ extern "C" int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher
     int ndc, groups;
     arco::proto_grid(d, &ndc, &groups);
     p.NDC = ndc;
+    p.proto_sums = proto_sums; p.rows = groups;
     ARCO_REQUIRE(((uintptr_t)rep_teacher & 15) == 0, "rep_teacher must be 16-byte aligned");
     p.vec_ok = arco::proto_vec_ok(d);
     int rc;
-    if (arco::proto_cfg(d).kind == 3) rc = arco::launch_proto_tc(d, rep_teacher, bank, L, ws, groups, st);
-    else if (arco::proto_cfg(d).kind == 4) rc = arco::launch_proto_tc32(d, rep_teacher, bank, L, ws, groups, st);
+    if (arco::proto_cfg(d).kind == 3) rc = arco::launch_proto_tc(d, rep_teacher, bank, L, ws, groups, proto_sums, st);
+    else if (arco::proto_cfg(d).kind == 4) rc = arco::launch_proto_tc32(d, rep_teacher, bank, L, ws, groups, proto_sums, st);
     else rc = d.rep_dtype == ARCO_BF16 ? arco::launch_proto<__nv_bfloat16>(d, p, groups, st)
                                        : arco::launch_proto<float>(d, p, groups, st);
-    if (rc != ARCO_OK) return rc;
-    const int n = d.classes * (d.feat + 1);
-    arco::proto_finalize_kernel<<<(n + 3) / 4, 128, 0, st>>>(p.partials, groups, d.classes, d.feat, p.plan, proto_sums);
-    ARCO_LAUNCH_CHECK();
-    return ARCO_OK;
+    return rc;
 }

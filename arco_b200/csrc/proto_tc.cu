@@ -17,6 +17,7 @@
 
 #include "arco_common.cuh"
 #include "tc_common.cuh"
+#include "proto_tail.cuh"
 
 namespace arco {
 
@@ -35,6 +36,7 @@ struct ProtoTcParams {
     void* bank_rows;
     int32_t bank_bf16;
     float* partials;
+    double* proto_sums;          // [C][D+1] fp64, written by the in-kernel finalize (proto_tail.cuh)
     int64_t row_off[ARCO_MAX_CLASSES];
     int32_t cap[ARCO_MAX_CLASSES];
     int64_t S;
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
     if (tid == 0) TC_CTA(3);
+    proto_finalize_tail(p.partials, (int)gridDim.x, p.C, p.D, const_cast<arco_plan*>(p.plan), p.proto_sums);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -324,7 +327,7 @@ size_t proto_tc_smem(const arco_dims& d) {
 }
 
 int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank* bank, const arco_ws_layout& L, char* ws,
-                    int rows, cudaStream_t st) {
+                    int rows, double* proto_sums, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
     ARCO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     for (int c = 0; c < d.classes; ++c)
@@ -349,6 +352,7 @@ int launch_proto_tc(const arco_dims& d, const void* rep_teacher, const arco_bank
     p.bank_rows = bank->rows;
     p.bank_bf16 = bank->row_dtype == ARCO_BF16;
     p.partials = (float*)(ws + L.partials);
+    p.proto_sums = proto_sums;
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
     p.S = d.space; p.B = d.n_lab + d.n_unlab; p.C = d.classes; p.D = d.feat;
     p.tpi = L.tiles_per_image; p.NT = L.n_tiles; p.NDB = (d.feat + TC_ROWS - 1) / TC_ROWS;

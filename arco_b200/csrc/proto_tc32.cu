@@ -30,6 +30,7 @@
 
 #include "arco_common.cuh"
 #include "tc_common.cuh"
+#include "proto_tail.cuh"
 
 namespace arco {
 
@@ -48,6 +49,7 @@ struct ProtoTc32Params {
     const arco_plan* plan;
     float* bank_rows;
     float* partials;
+    double* proto_sums;          // [C][D+1] fp64, written by the in-kernel finalize (proto_tail.cuh)
     int64_t row_off[ARCO_MAX_CLASSES];
     int32_t cap[ARCO_MAX_CLASSES];
     int64_t S;
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(384, 1) proto_tc32_kernel(const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    proto_finalize_tail(p.partials, (int)gridDim.x, p.C, p.D, const_cast<arco_plan*>(p.plan), p.proto_sums);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -409,7 +412,7 @@ size_t proto_tc32_smem(const arco_dims& d) {
 }
 
 int launch_proto_tc32(const arco_dims& d, const void* rep_teacher, const arco_bank* bank, const arco_ws_layout& L, char* ws,
-                      int rows, cudaStream_t st) {
+                      int rows, double* proto_sums, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
     ARCO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     ARCO_REQUIRE(bank->row_dtype == ARCO_F32, "an fp32 representation head needs an fp32 ring");
@@ -434,6 +437,7 @@ int launch_proto_tc32(const arco_dims& d, const void* rep_teacher, const arco_ba
     p.plan = (const arco_plan*)(ws + L.plan);
     p.bank_rows = (float*)bank->rows;
     p.partials = (float*)(ws + L.partials);
+    p.proto_sums = proto_sums;
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
     p.S = d.space; p.B = d.n_lab + d.n_unlab; p.C = d.classes; p.D = d.feat;
     p.tpi = L.tiles_per_image; p.NT = L.n_tiles; p.NDB = (d.feat + T32_ROWS - 1) / T32_ROWS;

@@ -7,6 +7,7 @@
 // to decide: valid_classes, valid_seg, which LOOP-2 positions run, and the FIFO bookkeeping of
 // dequeue_and_enqueue (loss_helper_3d.py:12-32) for a device-resident ring buffer.
 #include "arco_common.cuh"
+#include "plan_common.cuh"
 
 namespace arco {
 
@@ -16,10 +17,7 @@ struct ScanParams {
     uint32_t* off_anchor;
     uint32_t* off_key;
     arco_plan* plan;
-    int32_t* bank_head;
-    int32_t* bank_len;
-    int64_t* bank_ptr;
-    int32_t cap[ARCO_MAX_CLASSES];
+    PlanBank bank;
     int32_t C, NT, Q;
 };
 
@@ -32,86 +30,22 @@ __global__ void __launch_bounds__(1024) scan_plan_kernel(ScanParams p) {
     const bool is_key = row >= p.C;
     const uint32_t* cnt = (is_key ? p.cnt_key : p.cnt_anchor) + (int64_t)c * p.NT;
     uint32_t* off = (is_key ? p.off_key : p.off_anchor) + (int64_t)c * (p.NT + 1);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < p.NT; base += 1024) {
-        const int i = base + tid;
-        const uint32_t v = i < p.NT ? cnt[i] : 0u;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = s_warp[lane], ws = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
-                if (lane >= o) ws += y;
-            }
-            s_warp[lane] = ws - w;              // exclusive warp offsets
-        }
-        __syncthreads();
-        const uint32_t excl = s_carry + s_warp[warp] + x - v;
-        if (i < p.NT) off[i] = excl;
-        __syncthreads();
-        if (tid == 1023) s_carry = excl + v;
-        __syncthreads();
-    }
+    const int tid = threadIdx.x;
+    const uint32_t total = scan_row_block<1024>(cnt, off, p.NT, s_warp, &s_carry);
     if (tid == 0) {
-        off[p.NT] = s_carry;
-        if (is_key) p.plan->n_key[c] = s_carry; else p.plan->n_anchor[c] = s_carry;
+        if (is_key) p.plan->n_key[c] = total; else p.plan->n_anchor[c] = total;
         __threadfence();
         const uint32_t ticket = atomicAdd(&p.plan->scan_done, 1u);
         s_last = ticket == gridDim.x - 1;
     }
     __syncthreads();
-    if (!s_last || tid != 0) return;
+    if (!s_last || tid >= 32) return;
     __threadfence();
-
-    // ---- plan (single thread; C <= 32) ----
-    arco_plan* pl = p.plan;
-    volatile arco_plan* vpl = pl;
-    const int C = p.C;
-    int nv = 0;
-    for (int k = 0; k < C; ++k) {
-        // dequeue_and_enqueue (loss_helper_3d.py:19-30) on a ring buffer
-        const int cap = p.cap[k];
-        const int len = p.bank_len[k], head = p.bank_head[k];
-        const long long nk = vpl->n_key[k];
-        const long long merged = (long long)len + nk;
-        const long long overflow = merged > cap ? merged - cap : 0;      // rows dropped from the front
-        pl->bank_write_base[k] = cap > 0 ? (int)(((long long)head + len) % cap) : 0;
-        pl->bank_skip[k] = nk > cap ? (int)(nk - cap) : 0;                // this call's keys that never land
-        const int new_len = (int)(merged > cap ? cap : merged);
-        const int new_head = cap > 0 ? (int)(((long long)head + overflow) % cap) : 0;
-        long long ptr = p.bank_ptr[k];
-        ptr = (merged >= cap) ? cap : (ptr + nk) % cap;                  // reference pointer rule (:24-28)
-        pl->bank_len[k] = new_len;
-        pl->bank_head[k] = new_head;
-        pl->queue_ptr[k] = ptr;
-        p.bank_len[k] = new_len;
-        p.bank_head[k] = new_head;
-        p.bank_ptr[k] = ptr;
-        if (vpl->lv_count[k] > 0) pl->valid_class[nv++] = k;             // (:413-415)
-    }
-    for (int k = nv; k < ARCO_MAX_CLASSES; ++k) pl->valid_class[k] = -1;
-    pl->n_valid = nv;
-    for (int pos = 0; pos < ARCO_MAX_CLASSES; ++pos) {
-        int active = 0;
-        if (nv > 1 && pos < nv) {
-            // trap 1: anchors by POSITION, bank by CLASS ID (:437-438)
-            const int bank_cls = pl->valid_class[pos];
-            active = (vpl->n_anchor[pos] > 0 && pl->bank_len[bank_cls] > 0) ? 1 : 0;
-        }
-        pl->slot_active[pos] = active;
-    }
-    pl->inv_scale = nv > 1 ? 1.0f / ((float)p.Q * (float)nv) : 0.f;      // mean over Q, / valid_seg (:507-511)
-    pl->replanned = 0;
+    // ---- plan: one warp, lane <-> class ----
+    volatile arco_plan* vpl = p.plan;
+    const bool on = tid < p.C;
+    derive_plan_warp(p.plan, p.bank, p.C, p.Q, on ? vpl->lv_count[tid] : 0u, on ? vpl->n_anchor[tid] : 0u,
+                     on ? vpl->n_key[tid] : 0u, vpl->status);
 }
 
 // Multi-GPU: after the per-class (feature sum, count) buffer has been all-reduced, the set of valid
@@ -162,10 +96,10 @@ extern "C" int arco_scan_plan(const arco_dims* dims, const arco_bank* bank, void
     p.off_anchor = (uint32_t*)(ws + L.off_anchor);
     p.off_key = (uint32_t*)(ws + L.off_key);
     p.plan = (arco_plan*)(ws + L.plan);
-    p.bank_head = bank->head;
-    p.bank_len = bank->len;
-    p.bank_ptr = bank->queue_ptr;
-    for (int c = 0; c < ARCO_MAX_CLASSES; ++c) p.cap[c] = c < d.classes ? bank->cap[c] : 0;
+    p.bank.head = bank->head;
+    p.bank.len = bank->len;
+    p.bank.ptr = bank->queue_ptr;
+    for (int c = 0; c < ARCO_MAX_CLASSES; ++c) p.bank.cap[c] = c < d.classes ? bank->cap[c] : 0;
     for (int c = 0; c < d.classes; ++c) ARCO_REQUIRE(bank->cap[c] > 0, "queue_size must be positive");
     p.C = d.classes; p.NT = L.n_tiles; p.Q = d.queries;
     arco::scan_plan_kernel<<<2 * d.classes, 1024, 0, (cudaStream_t)stream>>>(p);

@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "contrastive_loss_fwd_bwd_throughput"
 UNIT = "Mpixels/s"
-KERNELS_PER_STEP = 9        # classify, scan_plan, proto_enqueue, proto_finalize, sample_scan, sample_emit, infonce, fill_zero, grad_scatter
+KERNELS_PER_STEP = 7        # classify(+scan+plan), proto_enqueue(+finalize), sample_scan, sample_emit, infonce, fill_zero, grad_scatter
 
 
 COLD_BANK = False
@@ -465,9 +465,8 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
     lm, hm = fl(x["low_mask"]), fl(x["high_mask"])
     rt, rs = x["rep_teacher"].contiguous(), x["rep"].detach().contiguous()
     calls = [
-        ("classify_count", lambda: lib.arco_classify_count(d, ll.data_ptr(), lu.data_ptr(), pl.data_ptr(), pu.data_ptr(),
-                                                           lm.data_ptr(), hm.data_ptr(), 0.3, 0.97, 3, 20, ws.data_ptr(), sp)),
-        ("scan_plan", lambda: lib.arco_scan_plan(d, b, ws.data_ptr(), sp)),
+        ("classify_plan", lambda: lib.arco_classify_plan(d, ll.data_ptr(), lu.data_ptr(), pl.data_ptr(), pu.data_ptr(),
+                                                         lm.data_ptr(), hm.data_ptr(), 0.3, 0.97, 3, 20, b, ws.data_ptr(), sp)),
         ("proto_enqueue", lambda: lib.arco_proto_enqueue(d, rt.data_ptr(), b, proto.data_ptr(), ws.data_ptr(), sp)),
         ("sample", lambda: lib.arco_sample(d, _cabi.FUNC_SMC, 1337, 7, idx_a.data_ptr(), idx_n.data_ptr(), ws.data_ptr(), sp)),
         ("infonce", lambda: lib.arco_infonce(d, rs.data_ptr(), b, proto.data_ptr(), idx_a.data_ptr(), idx_n.data_ptr(), 0.5,
@@ -496,8 +495,7 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
     K = sum(min(int(plan.n_key[c]), caps[c]) for c in range(Cn))
     Cv = sum(1 for j in range(Cn) if plan.slot_active[j])
     alg = {
-        "classify_count": P * (8 * Cn + 4 * Cn + 8) + P,
-        "scan_plan": 2 * Cn * L.n_tiles * 8,
+        "classify_plan": P * (8 * Cn + 4 * Cn + 8) + P + 2 * Cn * L.n_tiles * 8,
         "proto_enqueue": P_lv * D * e_t + K * D * (e_t + e_bank) + P,
         "sample": Cv * (Q + Q * N) * 4,
         "infonce": Cv * Q * D * e_t + Cv * Q * N * D * e_bank + Cv * Q * D * 4,
@@ -521,7 +519,7 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
              else "arco::proto_tc32_kernel (tcgen05 kind::tf32, hi + lo passes, TMA)"
              if spec.dtype != "bf16" and spec.feat > 128 and os.environ.get("ARCO_PROTO_TC32", "1") != "0"
              else "arco::proto_pipe_kernel")
-    roof = {"kernel": kname + " + proto_finalize_kernel (<2% of the call)", "bound": "hbm",
+    roof = {"kernel": kname + " (fp64 finalize in its tail)", "bound": "hbm",
             "achieved": stages[k]["gbs"], "peak": peak, "unit": "GB/s", "frac": stages[k]["frac_hbm"],
             "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg[k], "ms_per_launch": ms[k],
             "bytes_formula": "P_lv*D*e_t + K*D*(e_t+e_bank) + P  (SURVEY.md section 8(d) teacher-read and key terms + 1 code byte per pixel)",

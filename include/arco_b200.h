@@ -110,6 +110,8 @@ typedef struct arco_plan {
     uint32_t scan_done;                      /* internal tickets                                      */
     uint32_t loss_done;
     uint32_t replanned;                      /* arco_replan_global changed valid_class / slot_active  */
+    uint32_t proto_done;                     /* internal tickets of the prototype kernel's in-kernel finalize */
+    uint32_t proto_done2;
     uint32_t reserved;
 } arco_plan;
 
@@ -132,7 +134,12 @@ typedef struct arco_bank {
     void*    host_mirror;
     uint64_t mirror_seq;
     int64_t* host_queue_ptr;                  /* NULL, or device-accessible pinned int64[C]: the live queue_prtlis values */
+    /* Device scratch of ARCO_COUNTER_WORDS uint32, ZERO when the bank is created and left zero by every step
+       (self-cleaning tickets and accumulators of arco_classify_plan: no per-step memset).  Required by
+       arco_classify_plan / arco_forward; the arco_classify_count + arco_scan_plan pair does not use it. */
+    uint32_t* counters;
 } arco_bank;
+#define ARCO_COUNTER_WORDS 64
 
 ARCO_API const char* arco_version(void);
 ARCO_API const char* arco_last_error_string(void);
@@ -156,6 +163,16 @@ ARCO_API int arco_classify_count(const arco_dims* dims,
                         float delta_p, float delta_n, int32_t low_rank, int32_t high_rank,
                         void* workspace, void* stream);
 
+/* (a1-a4,a6) arco_classify_count + arco_scan_plan in ONE launch and without the memset of the plan: the CTAs that finish
+ * last scan the per-tile counts (one class row each) and the very last one derives the plan with one warp; tickets and
+ * the per-class low-valid accumulators live in bank->counters and are left zero for the next step. */
+ARCO_API int arco_classify_plan(const arco_dims* dims,
+                       const int64_t* label_l, const int64_t* label_u,
+                       const float* prob_l, const float* prob_u,
+                       const float* low_mask, const float* high_mask,
+                       float delta_p, float delta_n, int32_t low_rank, int32_t high_rank,
+                       const arco_bank* bank, void* workspace, void* stream);
+
 /* (a4,a6) exclusive scans of the tile counts (ordered compaction offsets), valid-class list,
  * slot activity, ring-buffer bookkeeping (dequeue_and_enqueue, loss_helper_3d.py:12-32). */
 ARCO_API int arco_scan_plan(const arco_dims* dims, const arco_bank* bank, void* workspace, void* stream);
@@ -166,7 +183,8 @@ ARCO_API int arco_replan_global(const arco_dims* dims, const double* proto_sums,
 
 /* (a5,a6) one pass over rep_teacher: per-class feature sums of low-valid pixels (prototype numerators,
  * :380-384) and ordered tail-only enqueue of the negative keys into the ring (:403-411).
- * proto_sums: float64 [C, D+1] = (sum over pixels, count) -- the buffer a multi-GPU caller all-reduces. */
+ * proto_sums: float64 [C, D+1] = (sum over pixels, count) -- the buffer a multi-GPU caller all-reduces.  One launch: the
+ * per-CTA partial rows are folded in fp64, in a fixed order, by the CTAs that finish last. */
 ARCO_API int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher, const arco_bank* bank,
                        double* proto_sums, void* workspace, void* stream);
 

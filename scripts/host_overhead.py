@@ -20,7 +20,16 @@ for _ in range(300): step()
 t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
-print("host ms/step %.3f   with drain %.3f" % ((t1 - t0) / 300 * 1e3, (t2 - t0) / 300 * 1e3))
+print("300 steps: issue ms/step %.3f   with drain %.3f (issue == drain: the launch queue filled, i.e. the GPU is the limit)" % ((t1 - t0) / 300 * 1e3, (t2 - t0) / 300 * 1e3))
+# host cost alone: few enough steps that the launch queue never fills
+hs = []
+for _ in range(5):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20): step()
+    hs.append((time.perf_counter() - t0) / 20 * 1e3)
+    torch.cuda.synchronize()
+print("20-step bursts: host issue ms/step %s" % ["%.3f" % h for h in hs])
 pr = cProfile.Profile(); pr.enable()
 for _ in range(300): step()
 pr.disable(); torch.cuda.synchronize()

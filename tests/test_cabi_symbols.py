@@ -19,7 +19,7 @@ def _declared():
 
 def test_header_declares_the_path():
     names = _declared()
-    for must in ("arco_classify_count", "arco_scan_plan", "arco_proto_enqueue", "arco_sample", "arco_infonce",
+    for must in ("arco_classify_count", "arco_classify_plan", "arco_scan_plan", "arco_proto_enqueue", "arco_sample", "arco_infonce",
                  "arco_grad_scatter", "arco_workspace_layout", "arco_last_error_string", "arco_label_onehot"):
         assert must in names
 

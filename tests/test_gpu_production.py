@@ -270,3 +270,49 @@ def test_sparse_grad_contract_matches_the_dense_gradient(workload, batch):
         assert torch.equal(l0, l1)
         assert torch.equal(g0, g1)
         assert float(g0.float().abs().sum()) > 0
+
+
+@pytest.mark.parametrize("workload,batch", [("acdc2d_loss", None), ("cityscapes", (1, 1)), ("la3d", (1, 1))])
+def test_one_launch_classify_plan_equals_the_two_launch_form(workload, batch):
+    """arco_classify_plan (scan + plan in the classify kernel's tail, self-cleaning counters, warp-parallel plan) against
+    the stand-alone arco_classify_count + arco_scan_plan pair: identical plan words, tile offsets, bank bookkeeping and
+    loss, for three consecutive steps on the same bank (the counters must come back to zero every step)."""
+    import ctypes as C
+
+    import arco_b200
+    from arco_b200 import _cabi
+    dev = torch.device("cuda", 0)
+    n_lab, n_unlab = batch if batch else (None, None)
+    outs = []
+    for legacy in (False, True):
+        spec, x = bench_inputs(workload, dev, seed=19, n_lab=n_lab, n_unlab=n_unlab)
+        bank, ptr, caps = bench_bank(spec, seed=5)
+        res = []
+        for step in range(3):
+            dbg = {"legacy_scan": legacy}
+            _, loss = arco_b200.compute_contra_memobank_loss(
+                x["rep"], x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"], bank, ptr, caps,
+                x["rep_teacher"], delta_n=0.97, func="smc", num_queries=64, num_negatives=32, seed=7, _debug=dbg)
+            torch.cuda.synchronize()
+            L = dbg["layout"]
+            ws = dbg["ws"]
+            plan = _cabi.Plan.from_buffer_copy(ws[L.plan: L.plan + C.sizeof(_cabi.Plan)].cpu().numpy().tobytes())
+            fields = {}
+            for name, _t in _cabi.Plan._fields_:
+                if name in ("scan_done", "loss_done", "proto_done", "proto_done2", "reserved"):
+                    continue
+                v = getattr(plan, name)
+                fields[name] = list(v) if hasattr(v, "__len__") else v
+            n_off = spec.classes * (L.n_tiles + 1) * 4
+            res.append(dict(plan=fields, loss=loss.detach().clone(),
+                            off_a=ws[L.off_anchor: L.off_anchor + n_off].clone(), off_k=ws[L.off_key: L.off_key + n_off].clone(),
+                            counters=bank[0].bank._counters.clone(), ptr=[int(q) for q in ptr]))
+        outs.append(res)
+        del x, bank
+        gc.collect()
+        torch.cuda.empty_cache()
+    for step, (a, b) in enumerate(zip(*outs)):
+        assert a["plan"] == b["plan"], step
+        assert torch.equal(a["off_a"], b["off_a"]) and torch.equal(a["off_k"], b["off_k"]), step
+        assert torch.equal(a["loss"], b["loss"]) and a["ptr"] == b["ptr"], step
+        assert int(a["counters"].abs().sum()) == 0, "arco_classify_plan must leave the persistent counters zero"
