@@ -11,6 +11,8 @@ import os
 
 MAX_CLASSES = 32
 COUNTER_WORDS = 64
+CTR_STEP = 40
+MIRROR_SLOTS, MIRROR_STRIDE = 8, 1536
 TILE = 1024
 F32, BF16 = 0, 1
 LABEL_ONEHOT_I64, LABEL_INDEX_I64 = 0, 1
@@ -53,7 +55,7 @@ class Plan(C.Structure):
         ("bank_len", _I32x), ("bank_head", _I32x),
         ("queue_ptr", _I64x),
         ("inv_scale", C.c_float), ("status", C.c_uint32), ("scan_done", C.c_uint32), ("loss_done", C.c_uint32),
-        ("replanned", C.c_uint32), ("proto_done", C.c_uint32), ("proto_done2", C.c_uint32), ("reserved", C.c_uint32),
+        ("replanned", C.c_uint32), ("proto_done", C.c_uint32), ("proto_done2", C.c_uint32), ("step_ctr", C.c_uint32),
     ]
 
 

@@ -136,6 +136,7 @@ class DeviceMemoryBank:
         self.c_struct.len = self.len.data_ptr()
         self.c_struct.queue_ptr = self.ptr.data_ptr()
         self.c_struct.host_queue_ptr = self._ptr_alias.data_ptr()
+        self.c_struct.host_mirror = self._mirror.data_ptr()
         self._counters = torch.zeros(_cabi.COUNTER_WORDS, dtype=torch.int32, device=self.device)   # self-cleaning tickets
         self.c_struct.counters = self._counters.data_ptr()
         for c in range(self.classes):
@@ -175,8 +176,8 @@ class DeviceMemoryBank:
         self.c_struct.row_dtype = _cabi.F32
 
     # ------------------------------------------------------------------ host mirror
-    _MIRROR_SLOTS = 8          # ring of pinned plan copies: the host may run this many steps ahead of the device
-    _MIRROR_STRIDE = 1536      # bytes per slot: arco_plan (1440 B) + u64 sequence number at offset sizeof(arco_plan)
+    _MIRROR_SLOTS = _cabi.MIRROR_SLOTS      # ring of pinned plan copies the device writes (ARCO_MIRROR_SLOTS)
+    _MIRROR_STRIDE = _cabi.MIRROR_STRIDE    # bytes per slot: arco_plan + u64 sequence number at offset sizeof(arco_plan)
 
     def _bind_pointers(self, queue_ptrlis: list) -> None:
         """Rebind the caller's ``queue_prtlis[c]`` to 1-element views of the pinned live-pointer array (like
@@ -193,13 +194,11 @@ class DeviceMemoryBank:
                 queue_ptrlis[c] = views[c]
 
     def begin_step(self) -> None:
-        """Point the step about to be launched at its slot of the pinned mirror ring.  The LAST CTA of the step's
-        InfoNCE kernel stores the final ``arco_plan`` there through the PCIe-mapped address, then the live queue pointers
-        and the step number (zero-copy: no memcpy, no event, nothing on the stream), which is how ``queue_prtlis``, the
-        bank lengths and the label-error status reach the host without the step ever synchronising (see :meth:`poll`)."""
-        seq = self.step + 1
-        self.c_struct.host_mirror = self._mirror.data_ptr() + (seq % self._MIRROR_SLOTS) * self._MIRROR_STRIDE
-        self.c_struct.mirror_seq = seq
+        """Nothing changes in the launch parameters from step to step (so a step can be captured in a CUDA graph and
+        replayed): the LAST CTA of every step's InfoNCE kernel stores the final ``arco_plan`` into slot ``seq % 8`` of the
+        pinned mirror ring through its PCIe-mapped address, then the live queue pointers, then ``seq`` -- the bank's
+        DEVICE step counter -- which is how ``queue_prtlis``, the bank lengths and the label-error status reach the host
+        without the step ever synchronising (see :meth:`poll`)."""
 
     def post_step(self, plan_view: torch.Tensor) -> None:
         """Remember the step's device-resident ``arco_plan`` (a view into its workspace); nothing is copied."""
@@ -210,28 +209,28 @@ class DeviceMemoryBank:
         self.step += 1
 
     def poll(self, block: bool = False) -> Optional[_cabi.Plan]:
-        """Non-blocking look at the host mirror: for every step that has FINISHED on the device since the last call, the
-        status word is checked (invalid labels / indices raise ``ValueError`` here, i.e. at the start of the first step
-        after the offending one has completed) and the newest landed plan is remembered for :attr:`host_len` /
-        :attr:`last_plan`.  Two 8-byte reads per finished step; never waits for the device unless ``block``."""
+        """Non-blocking look at the host mirror: for every step that has FINISHED on the device since the last call
+        (device sequence numbers 1, 2, 3, ... -- replays of a captured CUDA graph count too), the status word is checked
+        (invalid labels / indices raise ``ValueError`` here, i.e. at the start of the first call after the offending
+        step has completed) and the newest landed plan is remembered for :attr:`host_len` / :attr:`last_plan`.  A handful
+        of 8-byte reads; never waits for the device unless ``block``."""
         if block:
             return self.settle()
         slots = self._MIRROR_SLOTS
-        while self._applied < self.step:
-            s_no = self._applied + 1
+        newest = int(self._seq_np.max())
+        if newest <= self._applied:
+            return None
+        first = max(self._applied + 1, newest - slots + 1)            # older ones were overwritten in the ring
+        bad = 0
+        for s_no in range(first, newest + 1):
             slot = s_no % slots
-            seq = int(self._seq_np[slot])
-            if seq < s_no:
-                break                                             # that step has not finished yet
-            self._applied = s_no
-            if seq > s_no:
-                continue                                          # slot already reused by step s_no + k*slots: skip
-            status = int(self._status_np[slot])
+            if int(self._seq_np[slot]) != s_no:
+                continue                                          # not landed yet / already reused
+            bad |= int(self._status_np[slot])
             self._latest = (slot, s_no)
-            if s_no == self.step and not self._edited:
-                self._dirty = False
-            if status:
-                self.check_status(status)
+        self._applied = newest
+        if bad:
+            self.check_status(bad)
         return None
 
     def _landed_plan(self) -> Optional[_cabi.Plan]:
@@ -290,7 +289,7 @@ class DeviceMemoryBank:
         self._edited = False
         lens = self.len.cpu().tolist()
         ptrs = self.ptr.cpu().tolist()                            # (stream-ordered copy: every launched step has finished)
-        self._applied = self.step
+        self._applied = int(self._seq_np.max())
         self._latest = None
         self._host_len0 = [int(v) for v in lens[: self.classes]]
         self._ptr_alias[: self.classes] = torch.tensor(ptrs[: self.classes], dtype=torch.int64)

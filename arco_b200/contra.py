@@ -161,14 +161,16 @@ def _p2p_exchange(group, dev: torch.device, n: int):
 def _sampler_stream(seed, bank: DeviceMemoryBank, dev: torch.device):
     """(Philox seed, per-step stream id) of the in-kernel sampler.
 
-    Explicit ``seed=``: deterministic replay -- stream id = number of steps this bank has seen (tests, benchmarks).
+    The kernels add the bank's DEVICE step counter to the stream id returned here, so even a CUDA-graph replay of
+    identical launch parameters draws a fresh stream every step.
+    Explicit ``seed=``: deterministic replay -- stream id = number of steps this bank has completed (tests, benchmarks).
     Default: behave like the reference, which CONSUMES global RNG state (Python ``random`` + torch's CPU generator,
     loss_helper_3d.py:157-177): the seed is torch's CUDA seed mixed with the process's distributed rank (DDP ranks seeded
     alike must not draw identical index streams), and the stream id is taken from -- and advances -- the device's
     default CUDA generator offset, so a resumed run that restores (or re-seeds) torch's RNG state continues (or
     replays) exactly like the reference would, instead of restarting at stream 0 whenever a bank is re-adopted."""
     if seed is not None:
-        return int(seed) & (2 ** 64 - 1), bank.step
+        return int(seed) & (2 ** 64 - 1), 0              # the device adds the bank's own step counter (arco_plan.step_ctr)
     rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
     gen = torch.cuda.default_generators[dev.index]
     off = int(gen.get_offset())

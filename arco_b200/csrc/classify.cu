@@ -92,7 +92,7 @@ __device__ __forceinline__ void classify_tail(const ClassifyParams& p) {
     const bool on = tid < p.C;
     const uint32_t lv = on ? vc[tid] : 0u;
     const uint32_t status = vc[CTR_STATUS];
-    derive_plan_warp(p.plan, p.bank, p.C, p.Q, lv, on ? vpl->n_anchor[tid] : 0u, on ? vpl->n_key[tid] : 0u, status);
+    derive_plan_warp(p.plan, p.bank, p.C, p.Q, lv, on ? vpl->n_anchor[tid] : 0u, on ? vpl->n_key[tid] : 0u, status, vc[ARCO_CTR_STEP]);
     // leave the persistent counters zero for the next step
     __syncwarp();
     vc[tid] = 0u;

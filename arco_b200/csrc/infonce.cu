@@ -35,9 +35,9 @@ struct InfoParams {
     const float* momentum;       // [C][Q][D] or NULL
     const int32_t* momentum_on;  // device flag: momentum tensor has a non-zero entry (:489)
     float* proto_out;            // [C][Q][D] positive_feat written per (bank class, query) (:497), or NULL
-    void* host_mirror;           // arco_bank.host_mirror / mirror_seq / host_queue_ptr
+    void* host_mirror;           // arco_bank.host_mirror (ring base) / host_queue_ptr
     int64_t* host_queue_ptr;
-    uint64_t mirror_seq;
+    uint32_t* step_ctr;          // bank->counters + ARCO_CTR_STEP or NULL
     float ema_decay, ema_keep;   // ema_keep = float32(1 - ema_decay) formed in DOUBLE by the caller, as the reference's Python scalar is (:491-495)
     int64_t row_off[ARCO_MAX_CLASSES];
     int32_t cap[ARCO_MAX_CLASSES];
@@ -255,19 +255,22 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
         p.loss[0] = s;
         p.plan->loss_done = 0;                               // re-arm: the entry point may run again on the same plan
     }
+    // ---- end of the step: zero-copy host mirror of the summary, then advance the bank's device step counter ----
+    const uint32_t seq = p.plan->step_ctr + 1u;
     if (p.host_mirror) {
-        // zero-copy host mirror of the step summary (arco_bank.host_mirror): plan words, system fence, sequence number
+        // (arco_bank.host_mirror) plan words -> slot seq % SLOTS, live queue pointers, system fence, sequence number
+        char* slot = reinterpret_cast<char*>(p.host_mirror) + (size_t)(seq % ARCO_MIRROR_SLOTS) * ARCO_MIRROR_STRIDE;
         const volatile uint32_t* src = reinterpret_cast<const volatile uint32_t*>(p.plan);
-        volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(p.host_mirror);
+        volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(slot);
         for (int i = tid; i < (int)(sizeof(arco_plan) / 4); i += 128) dst[i] = src[i];
         if (p.host_queue_ptr && tid < p.C) reinterpret_cast<volatile long long*>(p.host_queue_ptr)[tid] = p.plan->queue_ptr[tid];
         __threadfence_system();
         __syncthreads();
         if (tid == 0) {
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<char*>(p.host_mirror) + sizeof(arco_plan)),
-                         "l"((unsigned long long)p.mirror_seq) : "memory");
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + sizeof(arco_plan)), "l"((unsigned long long)seq) : "memory");
         }
     }
+    if (p.step_ctr && tid == 0) *p.step_ctr = seq;
 }
 
 // MAXIT: 16-byte chunks per lane in pass 2 (ceil(chunks per row / 32)); BF16BANK: the ring stores bf16 rows
@@ -723,7 +726,8 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     p.loss = loss; p.g_anchor = grad_anchor; p.anchor_pix = anchor_pix; p.logits = logits;
     p.loss_parts = (float*)(ws + L.loss_parts);
     p.momentum = momentum; p.momentum_on = momentum_on; p.proto_out = proto_out; p.ema_decay = ema_decay; p.ema_keep = ema_keep;
-    p.host_mirror = bank->host_mirror; p.mirror_seq = bank->mirror_seq; p.host_queue_ptr = bank->host_queue_ptr;
+    p.host_mirror = bank->host_mirror; p.host_queue_ptr = bank->host_queue_ptr;
+    p.step_ctr = bank->counters ? bank->counters + ARCO_CTR_STEP : nullptr;
     ARCO_REQUIRE(momentum == nullptr || momentum_on != nullptr, "momentum needs the device flag momentum_on");
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) { p.row_off[c] = bank->row_off[c]; p.cap[c] = bank->cap[c] > 0 ? bank->cap[c] : 1; }
     p.S = d.space; p.C = d.classes; p.D = d.feat; p.Q = d.queries; p.N = d.negatives;

@@ -21,7 +21,7 @@ struct PlanBank {
 // Reference: dequeue_and_enqueue (loss_helper_3d.py:19-30) on a ring buffer; valid_classes (:413-415); LOOP-2 activity
 // (:436-438, trap 1: anchors by POSITION, bank by CLASS ID); mean over Q and / valid_seg (:507-511).
 __device__ __forceinline__ void derive_plan_warp(arco_plan* pl, const PlanBank& bank, int C, int Q, uint32_t lv, uint32_t na,
-                                                 uint32_t nk, uint32_t status) {
+                                                 uint32_t nk, uint32_t status, uint32_t step_ctr) {
     const int k = threadIdx.x & 31;
     const bool on = k < C;
     int new_len = 0;
@@ -57,7 +57,7 @@ __device__ __forceinline__ void derive_plan_warp(arco_plan* pl, const PlanBank& 
         pl->n_valid = nv;
         pl->inv_scale = nv > 1 ? 1.0f / ((float)Q * (float)nv) : 0.f;
         pl->status = status;
-        pl->scan_done = 0; pl->loss_done = 0; pl->replanned = 0; pl->proto_done = 0; pl->proto_done2 = 0; pl->reserved = 0;
+        pl->scan_done = 0; pl->loss_done = 0; pl->replanned = 0; pl->proto_done = 0; pl->proto_done2 = 0; pl->step_ctr = step_ctr;
     }
 }
 

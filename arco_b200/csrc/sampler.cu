@@ -81,7 +81,7 @@ __device__ __forceinline__ Call decode_call(const SampleParams& p, int call) {
             c.shape = p.Q;
             c.out = p.idx_anchor + (int64_t)j * p.Q;
         }
-        c.stream = p.stream * 64ull + (uint64_t)call;
+        c.stream = (p.stream + (uint64_t)p.plan->step_ctr) * 64ull + (uint64_t)call;   // fresh stream every device step
     } else {
         c.high = p.high; c.shape = p.shape; c.out = p.out;
     }

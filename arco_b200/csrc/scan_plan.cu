@@ -18,6 +18,7 @@ struct ScanParams {
     uint32_t* off_key;
     arco_plan* plan;
     PlanBank bank;
+    const uint32_t* step_ctr;     // bank->counters + ARCO_CTR_STEP, or NULL
     int32_t C, NT, Q;
 };
 
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(1024) scan_plan_kernel(ScanParams p) {
     volatile arco_plan* vpl = p.plan;
     const bool on = tid < p.C;
     derive_plan_warp(p.plan, p.bank, p.C, p.Q, on ? vpl->lv_count[tid] : 0u, on ? vpl->n_anchor[tid] : 0u,
-                     on ? vpl->n_key[tid] : 0u, vpl->status);
+                     on ? vpl->n_key[tid] : 0u, vpl->status, p.step_ctr ? *(volatile const uint32_t*)p.step_ctr : 0u);
 }
 
 // Multi-GPU: after the per-class (feature sum, count) buffer has been all-reduced, the set of valid
@@ -102,6 +103,7 @@ extern "C" int arco_scan_plan(const arco_dims* dims, const arco_bank* bank, void
     for (int c = 0; c < ARCO_MAX_CLASSES; ++c) p.bank.cap[c] = c < d.classes ? bank->cap[c] : 0;
     for (int c = 0; c < d.classes; ++c) ARCO_REQUIRE(bank->cap[c] > 0, "queue_size must be positive");
     p.C = d.classes; p.NT = L.n_tiles; p.Q = d.queries;
+    p.step_ctr = bank->counters ? bank->counters + ARCO_CTR_STEP : nullptr;
     arco::scan_plan_kernel<<<2 * d.classes, 1024, 0, (cudaStream_t)stream>>>(p);
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;

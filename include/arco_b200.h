@@ -112,7 +112,7 @@ typedef struct arco_plan {
     uint32_t replanned;                      /* arco_replan_global changed valid_class / slot_active  */
     uint32_t proto_done;                     /* internal tickets of the prototype kernel's in-kernel finalize */
     uint32_t proto_done2;
-    uint32_t reserved;
+    uint32_t step_ctr;                       /* value of the bank's device step counter when this step was planned   */
 } arco_plan;
 
 /* Device-resident ring-buffer memory bank (replaces the CPU list memobank[c] = [tensor[n,D]],
@@ -127,10 +127,13 @@ typedef struct arco_bank {
     int64_t  row_off[ARCO_MAX_CLASSES];
     int32_t  row_dtype;                       /* ARCO_F32 | ARCO_BF16                  */
     int32_t  reserved;
-    /* Optional zero-copy host mirror of the step summary: NULL, or a DEVICE-ACCESSIBLE address of pinned host memory with
-       room for sizeof(arco_plan) + 8 bytes.  The last CTA of arco_infonce stores the final arco_plan there and then
-       mirror_seq as a uint64 at offset sizeof(arco_plan) (system-scope release), so the host can follow new_keys,
-       queue_prtlis and the status bits by polling memory -- no memcpy, no event, no synchronisation. */
+    /* Optional zero-copy host mirror of the step summaries: NULL, or a DEVICE-ACCESSIBLE address of pinned host memory
+       holding a ring of ARCO_MIRROR_SLOTS slots of ARCO_MIRROR_STRIDE bytes.  The last CTA of arco_infonce stores the final
+       arco_plan into slot (seq % ARCO_MIRROR_SLOTS) and then seq as a uint64 at offset sizeof(arco_plan) of that slot
+       (system-scope release), seq = 1, 2, 3, ... being the bank's DEVICE step counter (counters[ARCO_CTR_STEP], advanced by
+       that same CTA).  The host follows new_keys, queue_prtlis and the status bits by polling memory: no memcpy, no event, no
+       synchronisation -- and nothing in the launch parameters changes from step to step, so a whole step can be
+       captured in a CUDA graph and replayed.  mirror_seq is unused (kept for layout stability). */
     void*    host_mirror;
     uint64_t mirror_seq;
     int64_t* host_queue_ptr;                  /* NULL, or device-accessible pinned int64[C]: the live queue_prtlis values */
@@ -140,6 +143,9 @@ typedef struct arco_bank {
     uint32_t* counters;
 } arco_bank;
 #define ARCO_COUNTER_WORDS 64
+#define ARCO_CTR_STEP 40           /* counters[ARCO_CTR_STEP]: number of steps this bank has completed on the device */
+#define ARCO_MIRROR_SLOTS 8
+#define ARCO_MIRROR_STRIDE 1536
 
 ARCO_API const char* arco_version(void);
 ARCO_API const char* arco_last_error_string(void);
@@ -190,7 +196,8 @@ ARCO_API int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher, 
 
 /* (a7) in-kernel Philox restatement of grid_monte_carlo_sample / grid_as_monte_carlo_sample and their
  * fallbacks (loss_helper_3d.py:35-268): idx_anchor int32 [C,Q], idx_neg int32 [C,Q*N], for every
- * active LOOP-2 position. */
+ * active LOOP-2 position.  The Philox stream of a step is `step` + arco_plan.step_ctr (the bank's device step counter),
+ * so replaying identical launch parameters (CUDA graph) still draws a fresh stream every step. */
 ARCO_API int arco_sample(const arco_dims* dims, int32_t func, uint64_t seed, uint64_t step,
                 int32_t* idx_anchor, int32_t* idx_neg, void* workspace, void* stream);
 

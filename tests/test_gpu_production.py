@@ -315,4 +315,60 @@ def test_one_launch_classify_plan_equals_the_two_launch_form(workload, batch):
         assert a["plan"] == b["plan"], step
         assert torch.equal(a["off_a"], b["off_a"]) and torch.equal(a["off_k"], b["off_k"]), step
         assert torch.equal(a["loss"], b["loss"]) and a["ptr"] == b["ptr"], step
-        assert int(a["counters"].abs().sum()) == 0, "arco_classify_plan must leave the persistent counters zero"
+        ctr = a["counters"].clone()
+        assert int(ctr[40]) == step + 1                            # ARCO_CTR_STEP: the device step counter
+        ctr[40] = 0
+        assert int(ctr.abs().sum()) == 0, "arco_classify_plan must leave its tickets / accumulators zero"
+
+
+def test_whole_step_replays_as_a_cuda_graph():
+    """Nothing in the launch parameters changes from step to step (Philox stream and host-mirror slot come from the
+    bank's device step counter), so forward + backward can be captured once with ``torch.cuda.graph`` and replayed:
+    every replay must equal the eager step with the same bank history -- loss, gradient, bank rows -- and the host
+    mirror must keep following (queue pointers, sequence numbers)."""
+    import arco_b200
+    dev = torch.device("cuda", 0)
+    runs = {}
+    for mode in ("eager", "graph"):
+        spec, x = bench_inputs("acdc2d_loss", dev, seed=23, n_lab=2, n_unlab=2)
+        bank, ptr, caps = bench_bank(spec, seed=5)
+        rep = x["rep"].clone().requires_grad_(True)
+
+        def step():
+            rep.grad = None
+            _, loss = arco_b200.compute_contra_memobank_loss(
+                rep, x["label_l"], x["label_u"], x["prob_l"], x["prob_u"], x["low_mask"], x["high_mask"], bank, ptr, caps,
+                x["rep_teacher"], delta_n=0.97, func="smc", num_queries=64, num_negatives=32, seed=77)
+            loss.backward()
+            return loss
+
+        out = []
+        step()                                                     # step 1 eager in both modes (adoption, lazy init)
+        torch.cuda.synchronize()
+        if mode == "eager":
+            for _ in range(3):
+                loss = step()
+                torch.cuda.synchronize()
+                out.append((loss.detach().clone(), rep.grad.clone(), [int(q) for q in ptr]))
+        else:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    loss = step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for _ in range(3):
+                g.replay()
+                torch.cuda.synchronize()
+                bank[0].bank.poll()
+                out.append((loss.detach().clone(), rep.grad.clone(), [int(q) for q in ptr]))
+            assert bank[0].bank._applied == 4                      # device sequence numbers 1..4 landed on the host
+        arco_b200.synchronize_bank(bank)
+        runs[mode] = (out, [bank[c][0].clone() for c in range(spec.classes)])
+    for (l0, g0, p0), (l1, g1, p1) in zip(runs["eager"][0], runs["graph"][0]):
+        assert torch.equal(l0, l1) and torch.equal(g0, g1) and p0 == p1
+    for a, b in zip(runs["eager"][1], runs["graph"][1]):
+        assert torch.equal(a, b)
+    assert not torch.equal(runs["graph"][0][0][1], runs["graph"][0][1][1])     # replays draw fresh sample streams
