@@ -11,6 +11,8 @@
 // One CTA per 1024-pixel tile (a tile never straddles an image); 256 threads x 4 consecutive pixels
 // so every global access is a 16-byte vector (int64 labels: two per pixel pair).  HBM-bound:
 // algorithmic bytes = P * (8C + 4C + 8) read + P written.
+#include <stdlib.h>
+
 #include "arco_common.cuh"
 #include "plan_common.cuh"
 
@@ -48,27 +50,27 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     return v;
 }
 
-// Tail of arco_classify_plan, entered by every CTA after its tile's counts are written.  The min(NT, 2C) CTAs that finish
+// Tail of arco_classify_plan, entered by every CTA after its tiles' counts are written.  The min(grid, 2C) CTAs that finish
 // LAST wait until every tile is done (they took their ticket after their own stores, so everything they wait for is
 // already running or finished -- at most 2C <= 64 CTAs ever spin), scan one row of tile counts each (row = anchor or key
 // counts of one class), and the last scanner derives the plan with one warp and re-zeroes the persistent counters.
-__device__ __forceinline__ void classify_tail(const ClassifyParams& p) {
+__device__ __forceinline__ void classify_tail(const ClassifyParams& p, int n_cta) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     __shared__ int s_role;
     __shared__ bool s_last;
     const int tid = threadIdx.x;
-    const int n_scan = min(p.NT, 2 * p.C);
+    const int n_scan = min(n_cta, 2 * p.C);
     if (tid == 0) {
         __threadfence();
         const uint32_t t = atomicAdd(&p.ctr[CTR_TILES], 1u);
-        s_role = (int)t >= p.NT - n_scan ? (int)t - (p.NT - n_scan) : -1;
+        s_role = (int)t >= n_cta - n_scan ? (int)t - (n_cta - n_scan) : -1;
     }
     __syncthreads();
     const int role = s_role;
     if (role < 0) return;
     if (tid == 0) {
-        while (ld_acquire_gpu(&p.ctr[CTR_TILES]) < (uint32_t)p.NT) __nanosleep(40);
+        while (ld_acquire_gpu(&p.ctr[CTR_TILES]) < (uint32_t)n_cta) __nanosleep(40);
     }
     __syncthreads();
     for (int row = role; row < 2 * p.C; row += n_scan) {
@@ -122,15 +124,46 @@ struct PixVec<1> {
 
 // NV = pixels per thread per pass (4: vector path, 1: scalar path for unaligned / odd S)
 template <int NV, bool TAIL>
-__global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p) {
+__global__ void __launch_bounds__(256, 4) classify_kernel(ClassifyParams p) {
     __shared__ uint32_t s_anchor[ARCO_MAX_CLASSES], s_key[ARCO_MAX_CLASSES], s_lv[ARCO_MAX_CLASSES];
     __shared__ uint32_t s_flagged, s_status;
     const int tid = threadIdx.x;
+    // Persistent CTAs: tile, tile + grid, ...  Before a tile is processed, the NEXT tile's input lines are requested into
+    // L2 (prefetch.global.L2, no registers held), so its three dependent load phases (labels -> own-class probability ->
+    // rank pass) hit L2 instead of paying the HBM latency three times.
+  for (int tile = blockIdx.x; tile < p.NT; tile += gridDim.x) {
     if (tid < ARCO_MAX_CLASSES) { s_anchor[tid] = 0; s_key[tid] = 0; s_lv[tid] = 0; }
     if (tid == 0) { s_flagged = 0; s_status = 0; }
     __syncthreads();
-
-    const int tile = blockIdx.x;
+    {
+        const int nt = tile + gridDim.x;
+        if (nt < p.NT) {
+            const int nb = nt / p.tpi;
+            const int64_t ns0 = (int64_t)(nt % p.tpi) * ARCO_TILE;
+            const int64_t npx = min((int64_t)ARCO_TILE, p.S - ns0);
+            const bool nlab = nb < p.n_lab;
+            const int nbx = nlab ? nb : nb - p.n_lab;
+            const int C_ = p.C;
+            const char* lab0 = reinterpret_cast<const char*>(nlab ? p.label_l : p.label_u);
+            const char* prob0 = reinterpret_cast<const char*>(nlab ? p.prob_l : p.prob_u);
+            const int lab_rows = p.label_kind == ARCO_LABEL_ONEHOT_I64 ? C_ : 1;
+            const int lab_lines = (int)((npx * 8 + 127) >> 7), f_lines = (int)((npx * 4 + 127) >> 7);
+            const int total = lab_rows * lab_lines + (C_ + 2) * f_lines;
+            for (int i = tid; i < total; i += 256) {
+                const char* a;
+                if (i < lab_rows * lab_lines) {
+                    const int r = i / lab_lines, l = i - r * lab_lines;
+                    a = lab0 + (((int64_t)nbx * lab_rows + r) * p.S + ns0) * 8 + (int64_t)l * 128;
+                } else {
+                    const int k = i - lab_rows * lab_lines;
+                    const int r = k / f_lines, l = k - r * f_lines;
+                    if (r < C_) a = prob0 + (((int64_t)nbx * C_ + r) * p.S + ns0) * 4 + (int64_t)l * 128;
+                    else a = reinterpret_cast<const char*>(r == C_ ? p.low_mask : p.high_mask) + ((int64_t)nb * p.S + ns0) * 4 + (int64_t)l * 128;
+                }
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+        }
+    }
     const int b = tile / p.tpi;
     const int64_t s0 = (int64_t)(tile % p.tpi) * ARCO_TILE;
     const bool labelled = b < p.n_lab;
@@ -251,10 +284,9 @@ __global__ void __launch_bounds__(256) classify_kernel(ClassifyParams p) {
         p.tile_flagged[tile] = s_flagged;
         if (s_status) atomicOr(TAIL ? &p.ctr[CTR_STATUS] : &p.plan->status, s_status);
     }
-    if (TAIL) {
-        __syncthreads();
-        classify_tail(p);
-    }
+    __syncthreads();                                         // shared counters are reset for the next tile
+  }
+    if (TAIL) classify_tail(p, (int)gridDim.x);
 }
 
 // (a1) stand-alone drop-in for the trainers' label_onehot
@@ -329,12 +361,16 @@ static int classify_launch(const arco_dims* dims, const int64_t* label_l, const 
     auto aligned16 = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
     const bool vec = (d.space % 4 == 0) && aligned16(label_l) && aligned16(label_u) && aligned16(prob_l) &&
                      aligned16(prob_u) && aligned16(low_mask) && aligned16(high_mask);
+    // persistent grid: one resident wave (the tail's waiting CTAs must never keep a pending CTA off the machine)
+    static const int per_sm = [] { const char* e = getenv("ARCO_CLASSIFY_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
+    int grid = arco::sm_count() * per_sm;
+    if (grid > L.n_tiles) grid = L.n_tiles;
     if (tail) {
-        if (vec) arco::classify_kernel<4, true><<<L.n_tiles, 256, 0, st>>>(p);
-        else arco::classify_kernel<1, true><<<L.n_tiles, 256, 0, st>>>(p);
+        if (vec) arco::classify_kernel<4, true><<<grid, 256, 0, st>>>(p);
+        else arco::classify_kernel<1, true><<<grid, 256, 0, st>>>(p);
     } else {
-        if (vec) arco::classify_kernel<4, false><<<L.n_tiles, 256, 0, st>>>(p);
-        else arco::classify_kernel<1, false><<<L.n_tiles, 256, 0, st>>>(p);
+        if (vec) arco::classify_kernel<4, false><<<grid, 256, 0, st>>>(p);
+        else arco::classify_kernel<1, false><<<grid, 256, 0, st>>>(p);
     }
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;

@@ -1,10 +1,11 @@
 // In-kernel finalize of the prototype pass: the per-CTA partial rows [rows][C][D] (fp32) are folded into
 // proto_sums[C][D+1] (fp64: feature sums, low-valid count) by the CTAs that finish LAST, instead of a second launch.
 //
-// Every CTA calls proto_finalize_tail() once, with all its threads, after its partial row is written.  The min(grid, 16)
+// Every CTA calls proto_finalize_tail() once, with all its threads, after its partial row is written.  The min(grid, 32)
 // CTAs with the highest tickets wait until every CTA has arrived (a CTA takes its ticket after its own stores, so whoever
-// it waits for is already running or done) and then fold a slice of the outputs each: one warp per output, lanes stride
-// over the rows, fixed-order shuffle tree in fp64 -- the same deterministic reduction the separate kernel used.
+// it waits for is already running or done) and then fold blocks of 32 consecutive outputs each: lane <-> output (feature
+// index fastest, so every load is a coalesced 128-byte line), the CTA's warps split the partial rows, fp64 partial sums per
+// warp, combined in a fixed order -- deterministic run to run.
 // The tickets live in the step's arco_plan (written fresh, as zero, by the plan derivation).
 #pragma once
 #include "arco_common.cuh"
@@ -20,9 +21,13 @@ __device__ __forceinline__ uint32_t tail_ld_acquire(const uint32_t* p) {
 __device__ __forceinline__ void proto_finalize_tail(const float* __restrict__ partials, int rows, int C, int D,
                                                     arco_plan* plan, double* __restrict__ proto_sums) {
     __shared__ int s_tail_role;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    __shared__ double s_tail_red[16][33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;   // nwarp <= 16
     const int grid = gridDim.x;
-    const int K = grid < 16 ? grid : 16;
+    const int n = C * (D + 1);
+    const int nblk = (n + 31) >> 5;                              // blocks of 32 consecutive outputs (d fastest: coalesced)
+    int K = grid < 32 ? grid : 32;
+    if (K > nblk) K = nblk;
     __syncthreads();                                             // this CTA's partial row is complete
     if (tid == 0) {
         __threadfence();
@@ -36,21 +41,33 @@ __device__ __forceinline__ void proto_finalize_tail(const float* __restrict__ pa
         while (tail_ld_acquire(&plan->proto_done) < (uint32_t)grid) __nanosleep(40);
     }
     __syncthreads();
-    const int n = C * (D + 1);
-    for (int i = role * nwarp + warp; i < n; i += K * nwarp) {
-        const int c = i / (D + 1), d = i % (D + 1);
-        if (d == D) {
-            if (lane == 0) proto_sums[i] = (double)plan->lv_count[c];
-            continue;
-        }
+    // lane <-> output, the CTA's warps split the rows (fixed partition), fp64 partial per warp, fixed-order combine
+    for (int blk = role; blk < nblk; blk += K) {
+        const int i = blk * 32 + lane;
+        const bool valid = i < n;
+        const int c = valid ? i / (D + 1) : 0, d = valid ? i % (D + 1) : 0;
         double s = 0.0;
-        for (int r = lane; r < rows; r += 32) s += (double)__ldcg(partials + ((int64_t)r * C + c) * D + d);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) proto_sums[i] = s;
+        if (valid && d < D) {
+            const float* src = partials + (int64_t)c * D + d;
+            const int64_t rstride = (int64_t)C * D;
+            int r = warp;
+            for (; r + 3 * nwarp < rows; r += 4 * nwarp) {       // four independent loads in flight
+                const float a0 = __ldcg(src + (int64_t)r * rstride), a1 = __ldcg(src + (int64_t)(r + nwarp) * rstride);
+                const float a2 = __ldcg(src + (int64_t)(r + 2 * nwarp) * rstride), a3 = __ldcg(src + (int64_t)(r + 3 * nwarp) * rstride);
+                s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
+            }
+            for (; r < rows; r += nwarp) s += (double)__ldcg(src + (int64_t)r * rstride);
+        }
+        s_tail_red[warp][lane] = s;
+        __syncthreads();
+        if (warp == 0 && valid) {
+            double t = 0.0;
+            for (int w = 0; w < nwarp; ++w) t += s_tail_red[w][lane];
+            proto_sums[i] = d == D ? (double)plan->lv_count[c] : t;
+        }
+        __syncthreads();
     }
     // re-arm the tickets (the entry point may be called again on the same plan, e.g. when a stage is timed on its own)
-    __syncthreads();
     if (tid == 0 && atomicAdd(&plan->proto_done2, 1u) == (uint32_t)K - 1) {
         plan->proto_done = 0;
         plan->proto_done2 = 0;
