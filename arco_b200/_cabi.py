@@ -52,7 +52,7 @@ class Plan(C.Structure):
         ("lv_count", _U32x), ("n_anchor", _U32x), ("n_key", _U32x),
         ("n_valid", C.c_int32),
         ("valid_class", _I32x), ("slot_active", _I32x), ("bank_write_base", _I32x), ("bank_skip", _I32x),
-        ("bank_len", _I32x), ("bank_head", _I32x),
+        ("bank_len", _I32x), ("bank_head", _I32x), ("reserved0", C.c_int32),
         ("queue_ptr", _I64x),
         ("inv_scale", C.c_float), ("status", C.c_uint32), ("scan_done", C.c_uint32), ("loss_done", C.c_uint32),
         ("replanned", C.c_uint32), ("proto_done", C.c_uint32), ("proto_done2", C.c_uint32), ("step_ctr", C.c_uint32),

@@ -289,6 +289,145 @@ __global__ void __launch_bounds__(256, 4) classify_kernel(ClassifyParams p) {
     if (TAIL) classify_tail(p, (int)gridDim.x);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// C <= 8 (ACDC C=4, LA C=2, ...): every input of a 4-pixel group -- C probability vectors, the label vectors, both masks --
+// is requested up front (no load depends on another); the own-class probability and the teacher rank are then selected
+// from registers.  The generic kernel above needs three dependent round trips per tile (labels -> prob[label] -> rank
+// pass), which kept it at 0.2-0.3 of the HBM roofline on the small shapes.  Per-class counts are packed 8 bits per class
+// (<= 4 per thread, <= 128 per warp), reduced with redux.sync, and added to the tile counters by one lane per warp.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int C, int KIND, bool TAIL>
+__global__ void __launch_bounds__(256) classify_small_kernel(ClassifyParams p) {
+    constexpr int NLAB = KIND == ARCO_LABEL_ONEHOT_I64 ? C : 1;
+    __shared__ uint32_t s_anchor[8], s_key[8], s_lv[8];
+    __shared__ uint32_t s_flagged, s_status;
+    const int tid = threadIdx.x;
+    if (tid < 8) { s_anchor[tid] = 0; s_key[tid] = 0; s_lv[tid] = 0; }
+    if (tid == 0) { s_flagged = 0; s_status = 0; }
+    __syncthreads();
+    const int tile = blockIdx.x;
+    const int b = tile / p.tpi;
+    const int64_t s0 = (int64_t)(tile % p.tpi) * ARCO_TILE;
+    const bool labelled = b < p.n_lab;
+    const int bx = labelled ? b : b - p.n_lab;
+    const int64_t S = p.S;
+    const int64_t s = s0 + 4 * tid;
+    const bool in_range = s < S;                             // S % 4 == 0: the group is all-in or all-out
+
+    float4 pr[C];
+    longlong2 la[NLAB][2];
+    float4 lm4 = make_float4(0.f, 0.f, 0.f, 0.f), hm4 = lm4;
+#pragma unroll
+    for (int c = 0; c < C; ++c) pr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < NLAB; ++c) la[c][0] = la[c][1] = make_longlong2(0, 0);
+    if (in_range) {
+        const float* pp = (labelled ? p.prob_l : p.prob_u) + (int64_t)bx * C * S + s;
+#pragma unroll
+        for (int c = 0; c < C; ++c) pr[c] = __ldg(reinterpret_cast<const float4*>(pp + (int64_t)c * S));
+        const int64_t* lp = (labelled ? p.label_l : p.label_u) + (int64_t)bx * NLAB * S + s;
+#pragma unroll
+        for (int c = 0; c < NLAB; ++c) {
+            la[c][0] = __ldg(reinterpret_cast<const longlong2*>(lp + (int64_t)c * S));
+            la[c][1] = __ldg(reinterpret_cast<const longlong2*>(lp + (int64_t)c * S + 2));
+        }
+        lm4 = __ldg(reinterpret_cast<const float4*>(p.low_mask + (int64_t)b * S + s));
+        hm4 = __ldg(reinterpret_cast<const float4*>(p.high_mask + (int64_t)b * S + s));
+    }
+    const float lm[4] = {lm4.x, lm4.y, lm4.z, lm4.w}, hm[4] = {hm4.x, hm4.y, hm4.z, hm4.w};
+    uint32_t packed = 0, status = 0;
+    unsigned long long n_lv = 0ull, n_an = 0ull, n_key = 0ull;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        int istar = -1;
+        if (KIND == ARCO_LABEL_ONEHOT_I64) {
+#pragma unroll
+            for (int c = 0; c < NLAB; ++c) {
+                const long long x = v == 0 ? la[c][0].x : v == 1 ? la[c][0].y : v == 2 ? la[c][1].x : la[c][1].y;
+                if (x != 0) { if (istar < 0) istar = c; else status |= ARCO_ST_MULTI_HOT; }
+            }
+        } else if (in_range) {
+            long long l = v == 0 ? la[0][0].x : v == 1 ? la[0][0].y : v == 2 ? la[0][1].x : la[0][1].y;
+            l = l < 0 ? 0 : l;                               // relu: ignore label -1 -> class 0 (trap 4)
+            if (l >= C) status |= ARCO_ST_LABEL_RANGE; else istar = (int)l;
+        }
+        float pstar = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float q = v == 0 ? pr[c].x : v == 1 ? pr[c].y : v == 2 ? pr[c].z : pr[c].w;
+            pstar = (c == istar) ? q : pstar;
+        }
+        const bool has = istar >= 0;
+        const bool lv = has && (lm[v] != 0.f);
+        const bool anchor = lv && (pstar > p.delta_p);
+        // labelled images can never yield a key (trap 3, loss_helper_3d.py:372-374,397-399)
+        const bool hard = has && !labelled && (hm[v] != 0.f) && (pstar < p.delta_n);
+        int rank = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float q = v == 0 ? pr[c].x : v == 1 ? pr[c].y : v == 2 ? pr[c].z : pr[c].w;
+            rank += (q > pstar) || (q == pstar && c < istar);
+        }
+        const bool key = hard && rank >= p.low_rank && rank < p.high_rank;
+        uint32_t code = 0;
+        if (has) code = (uint32_t)istar | (lv ? CODE_LV : 0u) | (anchor ? CODE_ANCHOR : 0u) | (key ? CODE_KEY : 0u);
+        packed |= code << (8 * v);
+        const unsigned long long one = has ? 1ull << (8 * istar) : 0ull;
+        n_lv += lv ? one : 0ull;
+        n_an += anchor ? one : 0ull;
+        n_key += key ? one : 0ull;
+    }
+    if (in_range) *reinterpret_cast<uint32_t*>(p.codes + (int64_t)b * S + s) = packed;
+    {
+        uint32_t w[6];
+        w[0] = __reduce_add_sync(0xffffffffu, (uint32_t)n_lv);
+        w[1] = __reduce_add_sync(0xffffffffu, (uint32_t)n_an);
+        w[2] = __reduce_add_sync(0xffffffffu, (uint32_t)n_key);
+        w[3] = C > 4 ? __reduce_add_sync(0xffffffffu, (uint32_t)(n_lv >> 32)) : 0u;
+        w[4] = C > 4 ? __reduce_add_sync(0xffffffffu, (uint32_t)(n_an >> 32)) : 0u;
+        w[5] = C > 4 ? __reduce_add_sync(0xffffffffu, (uint32_t)(n_key >> 32)) : 0u;
+        const uint32_t st = __reduce_or_sync(0xffffffffu, status);
+        if ((tid & 31) == 0) {
+            uint32_t flagged = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int sh = 8 * (c & 3), hi = c >> 2;
+                const uint32_t a = (w[3 * hi + 0] >> sh) & 0xffu, bq = (w[3 * hi + 1] >> sh) & 0xffu, k = (w[3 * hi + 2] >> sh) & 0xffu;
+                if (a) atomicAdd(&s_lv[c], a);
+                if (bq) atomicAdd(&s_anchor[c], bq);
+                if (k) atomicAdd(&s_key[c], k);
+                flagged += a + k;
+            }
+            if (flagged) atomicAdd(&s_flagged, flagged);
+            if (st) atomicOr(&s_status, st);
+        }
+    }
+    __syncthreads();
+    if (tid < C) {
+        p.cnt_anchor[(int64_t)tid * p.NT + tile] = s_anchor[tid];
+        p.cnt_key[(int64_t)tid * p.NT + tile] = s_key[tid];
+        if (s_lv[tid]) atomicAdd(TAIL ? &p.ctr[tid] : &p.plan->lv_count[tid], s_lv[tid]);
+    }
+    if (tid == 0) {
+        p.tile_flagged[tile] = s_flagged;
+        if (s_status) atomicOr(TAIL ? &p.ctr[CTR_STATUS] : &p.plan->status, s_status);
+    }
+    if (TAIL) {
+        __syncthreads();
+        classify_tail(p, (int)gridDim.x);
+    }
+}
+
+template <int KIND, bool TAIL>
+static bool launch_classify_small(const ClassifyParams& p, int grid, cudaStream_t st) {
+    switch (p.C) {
+#define ARCO_CS(CC) case CC: classify_small_kernel<CC, KIND, TAIL><<<grid, 256, 0, st>>>(p); return true;
+        ARCO_CS(2) ARCO_CS(3) ARCO_CS(4) ARCO_CS(5) ARCO_CS(6) ARCO_CS(7) ARCO_CS(8)
+#undef ARCO_CS
+        default: return false;
+    }
+}
+
 // (a1) stand-alone drop-in for the trainers' label_onehot
 __global__ void label_onehot_kernel(const int64_t* __restrict__ labels, float* __restrict__ out, int64_t batch,
                                     int classes, int64_t space) {
@@ -361,10 +500,23 @@ static int classify_launch(const arco_dims* dims, const int64_t* label_l, const 
     auto aligned16 = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
     const bool vec = (d.space % 4 == 0) && aligned16(label_l) && aligned16(label_u) && aligned16(prob_l) &&
                      aligned16(prob_u) && aligned16(low_mask) && aligned16(high_mask);
-    // persistent grid: one resident wave (the tail's waiting CTAs must never keep a pending CTA off the machine)
-    static const int per_sm = [] { const char* e = getenv("ARCO_CLASSIFY_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
+    // ARCO_CLASSIFY_CTAS CTAs per SM; above ~28 that is one CTA per tile for every shape here (the default).  Measured on
+    // B200: persistent CTAs (4 per SM) with an L2 prefetch of their next tile are no faster at C <= 4 and slower at C = 19
+    // (0.285 vs 0.199 ms: 140 MB of prefetched lines thrash the 126 MB L2), so tiles are left to the block scheduler.
+    static const int per_sm = [] { const char* e = getenv("ARCO_CLASSIFY_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 32; }();
     int grid = arco::sm_count() * per_sm;
     if (grid > L.n_tiles) grid = L.n_tiles;
+    static const bool small_ok = [] { const char* e = getenv("ARCO_CLASSIFY_SMALL"); return !(e && e[0] == '0'); }();
+    if (vec && small_ok && d.classes >= 2 && d.classes <= 8) {
+        // one tile per CTA, every load independent (see classify_small_kernel)
+        const int g = L.n_tiles;
+        bool done;
+        if (d.label_kind == ARCO_LABEL_ONEHOT_I64)
+            done = tail ? arco::launch_classify_small<ARCO_LABEL_ONEHOT_I64, true>(p, g, st) : arco::launch_classify_small<ARCO_LABEL_ONEHOT_I64, false>(p, g, st);
+        else
+            done = tail ? arco::launch_classify_small<ARCO_LABEL_INDEX_I64, true>(p, g, st) : arco::launch_classify_small<ARCO_LABEL_INDEX_I64, false>(p, g, st);
+        if (done) { ARCO_LAUNCH_CHECK(); return ARCO_OK; }
+    }
     if (tail) {
         if (vec) arco::classify_kernel<4, true><<<grid, 256, 0, st>>>(p);
         else arco::classify_kernel<1, true><<<grid, 256, 0, st>>>(p);

@@ -55,6 +55,7 @@ __device__ __forceinline__ void derive_plan_warp(arco_plan* pl, const PlanBank& 
     pl->slot_active[k] = (nv > 1 && k < nv && na > 0 && len_of_bank > 0) ? 1 : 0;
     if (k == 0) {
         pl->n_valid = nv;
+        pl->reserved0 = 0;
         pl->inv_scale = nv > 1 ? 1.0f / ((float)Q * (float)nv) : 0.f;
         pl->status = status;
         pl->scan_done = 0; pl->loss_done = 0; pl->replanned = 0; pl->proto_done = 0; pl->proto_done2 = 0; pl->step_ctr = step_ctr;

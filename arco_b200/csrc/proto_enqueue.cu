@@ -656,6 +656,24 @@ __global__ void __launch_bounds__(256) proto_small_kernel(ProtoParams p) {
     proto_finalize_tail(p.partials, p.rows, CC, DD, const_cast<arco_plan*>(p.plan), p.proto_sums);
 }
 
+__global__ void __launch_bounds__(128) proto_finalize_kernel(const float* __restrict__ partials, int rows, int C, int D,
+                                                            const arco_plan* __restrict__ plan,
+                                                            double* __restrict__ proto_sums) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= C * (D + 1)) return;
+    const int c = i / (D + 1), d = i % (D + 1);
+    if (d == D) {
+        if (lane == 0) proto_sums[i] = (double)plan->lv_count[c];
+        return;
+    }
+    double s = 0.0;
+    for (int r = lane; r < rows; r += 32) s += (double)partials[((int64_t)r * C + c) * D + d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) proto_sums[i] = s;
+}
+
 // Kernel variant for a problem: the 8-dims-per-lane kernel needs 16-byte vector loads and its 8 KB * C
 // stream accumulators to fit beside the tile; otherwise the 4-dims-per-lane kernel (4 KB * C) runs.
 bool proto_tc_supported(const arco_dims& d);
@@ -801,13 +819,21 @@ extern "C" int arco_proto_enqueue(const arco_dims* dims, const void* rep_teacher
     int ndc, groups;
     arco::proto_grid(d, &ndc, &groups);
     p.NDC = ndc;
-    p.proto_sums = proto_sums; p.rows = groups;
+    static const bool in_kernel_tail = [] { const char* e = getenv("ARCO_PROTO_TAIL"); return !(e && e[0] == '0'); }();
+    double* tail_out = in_kernel_tail ? proto_sums : nullptr;
+    p.proto_sums = tail_out; p.rows = groups;
     ARCO_REQUIRE(((uintptr_t)rep_teacher & 15) == 0, "rep_teacher must be 16-byte aligned");
     p.vec_ok = arco::proto_vec_ok(d);
     int rc;
-    if (arco::proto_cfg(d).kind == 3) rc = arco::launch_proto_tc(d, rep_teacher, bank, L, ws, groups, proto_sums, st);
-    else if (arco::proto_cfg(d).kind == 4) rc = arco::launch_proto_tc32(d, rep_teacher, bank, L, ws, groups, proto_sums, st);
+    if (arco::proto_cfg(d).kind == 3) rc = arco::launch_proto_tc(d, rep_teacher, bank, L, ws, groups, tail_out, st);
+    else if (arco::proto_cfg(d).kind == 4) rc = arco::launch_proto_tc32(d, rep_teacher, bank, L, ws, groups, tail_out, st);
     else rc = d.rep_dtype == ARCO_BF16 ? arco::launch_proto<__nv_bfloat16>(d, p, groups, st)
                                        : arco::launch_proto<float>(d, p, groups, st);
-    return rc;
+    if (rc != ARCO_OK) return rc;
+    if (!in_kernel_tail) {
+        const int n = d.classes * (d.feat + 1);
+        arco::proto_finalize_kernel<<<(n + 3) / 4, 128, 0, st>>>(p.partials, groups, d.classes, d.feat, p.plan, proto_sums);
+        ARCO_LAUNCH_CHECK();
+    }
+    return ARCO_OK;
 }

@@ -20,6 +20,8 @@ __device__ __forceinline__ uint32_t tail_ld_acquire(const uint32_t* p) {
 
 __device__ __forceinline__ void proto_finalize_tail(const float* __restrict__ partials, int rows, int C, int D,
                                                     arco_plan* plan, double* __restrict__ proto_sums) {
+    if (proto_sums == nullptr) return;                           // A/B switch: the host launches proto_finalize_kernel instead
+    if (proto_sums == nullptr) return;                           // A/B switch (ARCO_PROTO_TAIL=0): the host launches proto_finalize_kernel
     __shared__ int s_tail_role;
     __shared__ double s_tail_red[16][33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;   // nwarp <= 16
@@ -73,5 +75,10 @@ __device__ __forceinline__ void proto_finalize_tail(const float* __restrict__ pa
         plan->proto_done2 = 0;
     }
 }
+
+// Stand-alone form of the same fold (ARCO_PROTO_TAIL=0: A/B measurements): one warp per output element.
+__global__ void __launch_bounds__(128) proto_finalize_kernel(const float* __restrict__ partials, int rows, int C, int D,
+                                                            const arco_plan* __restrict__ plan,
+                                                            double* __restrict__ proto_sums);
 
 }  // namespace arco

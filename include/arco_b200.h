@@ -104,6 +104,7 @@ typedef struct arco_plan {
     int32_t  bank_skip[ARCO_MAX_CLASSES];    /* leading keys dropped because n_key > capacity         */
     int32_t  bank_len[ARCO_MAX_CLASSES];     /* bank rows after this call                             */
     int32_t  bank_head[ARCO_MAX_CLASSES];    /* ring position of logical row 0 after this call        */
+    int32_t  reserved0;                      /* explicit padding (8-byte alignment of queue_ptr), written as 0 */
     int64_t  queue_ptr[ARCO_MAX_CLASSES];    /* reference pointer bookkeeping (:24-30)                */
     float    inv_scale;                      /* 1 / (Q * valid_seg), 0 when valid_seg <= 1            */
     uint32_t status;                         /* ARCO_ST_* bits                                        */
