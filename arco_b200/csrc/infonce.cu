@@ -264,9 +264,8 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
         volatile uint32_t* dst = reinterpret_cast<volatile uint32_t*>(slot);
         for (int i = tid; i < (int)(sizeof(arco_plan) / 4); i += 128) dst[i] = src[i];
         if (p.host_queue_ptr && tid < p.C) reinterpret_cast<volatile long long*>(p.host_queue_ptr)[tid] = p.plan->queue_ptr[tid];
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
+        __syncthreads();                                     // the release below is cumulative over the CTA's stores (one
+        if (tid == 0) {                                      // system fence by one thread instead of one per thread)
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + sizeof(arco_plan)), "l"((unsigned long long)seq) : "memory");
         }
     }
@@ -458,25 +457,23 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
 
 
 // ======================================================================================================================
-// Short rows (row = CPR 16-byte chunks, CPR in {4, 8, 16, 32}: D = 16..128 fp32, 32..256 bf16; ACDC D=64, LA D=16):
-// no shared-memory staging and no per-row bulk copy -- a 64..512-byte row is too small for a TMA descriptor issue per row
-// (Q*N*C_v = 524 288 of them per step made the staged kernel issue-bound: 0.40 of the HBM roofline at D=64, 0.07 at D=16).
-// A warp reads 32/CPR rows per instruction with plain 16-byte loads straight into registers (lane = (row, chunk)), U of
-// them in flight; dot and norm are reduced over the CPR lanes of a row with shuffles, and because the row is still in
-// registers the gradient term  G += e_k/|k_k| * k_k  is accumulated in the same pass.  cos <= 1, so every exponential is
-// taken at the fixed offset 1/temp (no running maximum; needs temp >= 0.03 like the mma.sync kernel).
+// Short rows (D <= 64: ACDC D=64, LA D=16): one LANE per key.  The staged kernel above issues one TMA bulk copy per row and
+// then spends ~26 warp instructions per key on cross-lane reductions (ncu at D=64: issue slots 61 % busy, DRAM 10 %: it
+// is instruction-bound, 0.40 of the HBM roofline; 0.07 at D=16).  Here a lane loads its OWN row with 16-byte loads (NCH of
+// them in flight per lane, the row's two 128-byte lines stay in L1 between them), so the dot product, the norm and the
+// gradient term  G += e_k/|k_k| * k_k  are plain per-lane FMA chains with no shuffle at all; the 32 lanes' G vectors meet
+// once per warp at the end.  ~7 warp instructions per key.  cos <= 1, so every exponential is taken at the fixed offset
+// 1/temp (no running maximum; needs temp >= 0.03 like the mma.sync kernel).
 // ======================================================================================================================
-template <int CPR, bool BF16BANK>
-__global__ void __launch_bounds__(128) infonce_reg_kernel(InfoParams p) {
+template <int NCH, bool BF16BANK>
+__global__ void __launch_bounds__(128, 3) infonce_lane_kernel(InfoParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CHD = BF16BANK ? 8 : 4;                         // feature dims per 16-byte chunk
-    constexpr int KPW = 32 / CPR;                                 // rows per warp-wide load
-    constexpr int U = CPR >= 16 ? 8 : 4;                          // loads in flight per lane
-    const int D = p.D;                                            // == CPR * CHD
+    constexpr int DD = NCH * CHD;                                 // == p.D
     float* a_hat = reinterpret_cast<float*>(smem_raw);            // [D]
-    float* k0hat = a_hat + D;                                     // [D]
-    float* gbuf = k0hat + D;                                      // [4][D]
-    int32_t* s_idx = reinterpret_cast<int32_t*>(gbuf + 4 * D);    // [N] this query's negative indices
+    float* k0hat = a_hat + DD;                                    // [D]
+    float* gbuf = k0hat + DD;                                     // [4][D]
+    int32_t* s_idx = reinterpret_cast<int32_t*>(gbuf + 4 * DD);   // [N] this query's negatives as physical ring rows
     __shared__ float s_red[4][2];
     __shared__ float s_stats[4][2];
     __shared__ int s_pix;
@@ -490,10 +487,9 @@ __global__ void __launch_bounds__(128) infonce_reg_kernel(InfoParams p) {
     if (active) {
         const int bank_cls = pl->valid_class[j];                  // trap 1: bank by CLASS ID
         const int blen = pl->bank_len[bank_cls], bhead = pl->bank_head[bank_cls], cap = p.cap[bank_cls];
-        constexpr uint32_t row_bytes = CPR * 16;
+        constexpr uint32_t row_bytes = NCH * 16;
         const unsigned char* bank = reinterpret_cast<const unsigned char*>(p.bank_rows) + p.row_off[bank_cls] * (int64_t)row_bytes;
         const float inv_scale = pl->inv_scale;
-        // this query's indices -> physical ring rows, once, coalesced (the prologue's latency hides the loads)
         {
             const int32_t* src = p.idx_n + ((int64_t)j * p.Q + q) * p.N;
             bool bad = false;
@@ -510,61 +506,52 @@ __global__ void __launch_bounds__(128) infonce_reg_kernel(InfoParams p) {
         const float inv_temp = 1.f / p.temp;
         const float z0 = ai.cos0 * inv_temp;
 
-        const int ksel = lane / CPR, ch = lane % CPR;
-        float av[CHD];
-#pragma unroll
-        for (int e = 0; e < CHD; ++e) av[e] = a_hat[ch * CHD + e];
         const int npw = (p.N + 3) / 4;
         const int n_begin = min(p.N, warp * npw), n_end = min(p.N, n_begin + npw);
         float S = 0.f, S2 = 0.f;
-        float G[CHD];
+        float G[DD];
 #pragma unroll
-        for (int e = 0; e < CHD; ++e) G[e] = 0.f;
+        for (int d = 0; d < DD; ++d) G[d] = 0.f;
 
-        for (int base = n_begin; base < n_end; base += KPW * U) {
-            uint4 raw[U];
-            bool val[U];
+        for (int base = n_begin; base < n_end; base += 32) {      // warp-uniform trip count
+            const int n = base + lane;
+            const bool val = n < n_end;
+            uint4 raw[NCH];
+            const uint4* row = reinterpret_cast<const uint4*>(bank + (int64_t)(val ? s_idx[n] : 0) * row_bytes);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int n = base + u * KPW + ksel;
-                val[u] = n < n_end;
-                raw[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (val[u]) raw[u] = ldg_nc_u4(bank + (int64_t)s_idx[n] * row_bytes + ch * 16);
-            }
+            for (int c = 0; c < NCH; ++c) raw[c] = val ? __ldg(row + c) : make_uint4(0u, 0u, 0u, 0u);
+            float kv[DD];
+            float dacc[4] = {0.f, 0.f, 0.f, 0.f}, nacc[4] = {0.f, 0.f, 0.f, 0.f};      // independent FMA chains
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                float kv[CHD];
-                unpack_chunk<BF16BANK>(raw[u], kv);
-                float dot = 0.f, n2 = 0.f;
+            for (int c = 0; c < NCH; ++c) {
+                unpack_chunk<BF16BANK>(raw[c], kv + c * CHD);
 #pragma unroll
-                for (int e = 0; e < CHD; ++e) { dot += kv[e] * av[e]; n2 += kv[e] * kv[e]; }
-#pragma unroll
-                for (int o = 1; o < CPR; o <<= 1) {
-                    dot += __shfl_xor_sync(0xffffffffu, dot, o);
-                    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+                for (int e4 = 0; e4 < CHD; e4 += 4) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(a_hat + c * CHD + e4);   // broadcast read
+                    const float* kk = kv + c * CHD + e4;
+                    dacc[0] += kk[0] * a4.x; dacc[1] += kk[1] * a4.y; dacc[2] += kk[2] * a4.z; dacc[3] += kk[3] * a4.w;
+                    nacc[0] += kk[0] * kk[0]; nacc[1] += kk[1] * kk[1]; nacc[2] += kk[2] * kk[2]; nacc[3] += kk[3] * kk[3];
                 }
-                const float inv_nk = 1.f / fmaxf(sqrtf(n2), kEps);
-                const float cosv = dot * inv_nk;
-                const float e = val[u] ? __expf((cosv - 1.f) * inv_temp) : 0.f;
-                if (ch == 0) {
-                    S += e;
-                    S2 += e * cosv;
-                    if (p.logits && val[u]) p.logits[((int64_t)j * p.Q + q) * (1 + p.N) + 1 + base + u * KPW + ksel] = cosv;
-                }
-                const float coef = e * inv_nk;
-#pragma unroll
-                for (int e2 = 0; e2 < CHD; ++e2) G[e2] += coef * kv[e2];
             }
+            const float dot = (dacc[0] + dacc[1]) + (dacc[2] + dacc[3]);
+            const float n2 = (nacc[0] + nacc[1]) + (nacc[2] + nacc[3]);
+            const float inv_nk = 1.f / fmaxf(sqrtf(n2), kEps);
+            const float cosv = dot * inv_nk;
+            const float e = val ? __expf((cosv - 1.f) * inv_temp) : 0.f;
+            S += e;
+            S2 += e * cosv;
+            if (p.logits && val) p.logits[((int64_t)j * p.Q + q) * (1 + p.N) + 1 + n] = cosv;
+            const float coef = e * inv_nk;
+#pragma unroll
+            for (int d = 0; d < DD; ++d) G[d] += coef * kv[d];
         }
-        // rows of different ksel hit the same chunk: fold them, then one partial vector per warp
+        // the 32 lanes' partial G vectors meet once per warp
 #pragma unroll
-        for (int o = CPR; o < 32; o <<= 1) {
+        for (int d = 0; d < DD; ++d) {
+            float g = G[d];
 #pragma unroll
-            for (int e2 = 0; e2 < CHD; ++e2) G[e2] += __shfl_xor_sync(0xffffffffu, G[e2], o);
-        }
-        if (ksel == 0) {
-#pragma unroll
-            for (int e2 = 0; e2 < CHD; ++e2) gbuf[(size_t)warp * D + ch * CHD + e2] = G[e2];
+            for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+            if (lane == (d & 31)) gbuf[(size_t)warp * DD + d] = g;
         }
         S = warp_sum(S);
         S2 = warp_sum(S2);
@@ -575,7 +562,7 @@ __global__ void __launch_bounds__(128) infonce_reg_kernel(InfoParams p) {
         const float S_all = e0 + s_stats[0][0] + s_stats[1][0] + s_stats[2][0] + s_stats[3][0];
         const float S2_all = e0 * ai.cos0 + s_stats[0][1] + s_stats[1][1] + s_stats[2][1] + s_stats[3][1];
         info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, S_all, S2_all, a_hat, k0hat,
-                      [&](int d) { return gbuf[d] + gbuf[D + d] + gbuf[2 * D + d] + gbuf[3 * D + d]; });
+                      [&](int d) { return gbuf[d] + gbuf[DD + d] + gbuf[2 * DD + d] + gbuf[3 * DD + d]; });
     } else if (tid == 0) {
         p.loss_parts[bid] = 0.f;
         p.anchor_pix[bid] = -1;
@@ -891,21 +878,22 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
         ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_kernel<MI, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         arco::infonce_kernel<MI, BF><<<grid, 128, smem, st>>>(p);                                                           \
     } while (0)
-    static const bool reg_ok = [] { const char* e = getenv("ARCO_INFONCE_REG"); return !(e && e[0] == '0'); }();
-    if (reg_ok && temp >= 0.03f && (cpl == 4 || cpl == 8 || cpl == 16 || cpl == 32)) {
-        // short rows: register gather (see infonce_reg_kernel)
+    static const bool lane_ok = [] { const char* e = getenv("ARCO_INFONCE_LANE"); return !(e && e[0] == '0'); }();
+    if (lane_ok && temp >= 0.03f && d.feat <= 64 && (cpl == 2 || cpl == 4 || cpl == 8 || cpl == 16)) {
+        // short rows: one lane per key (see infonce_lane_kernel)
         const size_t sm = (size_t)6 * d.feat * 4 + (size_t)(d.negatives > 0 ? d.negatives : 1) * 4;
-#define ARCO_INFONCE_REG(CP, BF)                                                                                         \
+#define ARCO_INFONCE_LANE(NC, BF)                                                                                        \
         do {                                                                                                             \
-            ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_reg_kernel<CP, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-            arco::infonce_reg_kernel<CP, BF><<<grid, 128, sm, st>>>(p);                                                   \
+            ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_lane_kernel<NC, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            arco::infonce_lane_kernel<NC, BF><<<grid, 128, sm, st>>>(p);                                                  \
         } while (0)
-        if (bf16bank) { if (cpl == 4) ARCO_INFONCE_REG(4, true); else if (cpl == 8) ARCO_INFONCE_REG(8, true); else if (cpl == 16) ARCO_INFONCE_REG(16, true); else ARCO_INFONCE_REG(32, true); }
-        else { if (cpl == 4) ARCO_INFONCE_REG(4, false); else if (cpl == 8) ARCO_INFONCE_REG(8, false); else if (cpl == 16) ARCO_INFONCE_REG(16, false); else ARCO_INFONCE_REG(32, false); }
-#undef ARCO_INFONCE_REG
+        if (bf16bank) { if (cpl == 2) ARCO_INFONCE_LANE(2, true); else if (cpl == 4) ARCO_INFONCE_LANE(4, true); else if (cpl == 8) ARCO_INFONCE_LANE(8, true); else goto staged; }
+        else { if (cpl == 2) ARCO_INFONCE_LANE(2, false); else if (cpl == 4) ARCO_INFONCE_LANE(4, false); else if (cpl == 8) ARCO_INFONCE_LANE(8, false); else ARCO_INFONCE_LANE(16, false); }
+#undef ARCO_INFONCE_LANE
         ARCO_LAUNCH_CHECK();
         return ARCO_OK;
     }
+staged:
     static const int mma_env = [] { const char* e = getenv("ARCO_INFONCE_MMA"); return e ? atoi(e) : 1; }();   // 0 = off, else stages (1 | 2)
     // Measured (profiles/r01_config5_sweep.md): the mma.sync kernel's per-chunk cost is flat in D, so it wins for long rows
     // (D = 496: 0.142 vs 0.190 ms) and loses to the FFMA kernel on the same bf16 ring at D <= 256 (0.114 vs 0.090 ms).
