@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
 
 
 // ======================================================================================================================
-// Short rows (D <= 64: ACDC D=64, LA D=16): one LANE per key.  The staged kernel above issues one TMA bulk copy per row and
+// Short rows (<= 128 bytes: LA D=16, D=32 fp32, D<=64 bf16): one LANE per key.  The staged kernel above issues one TMA bulk copy per row and
 // then spends ~26 warp instructions per key on cross-lane reductions (ncu at D=64: issue slots 61 % busy, DRAM 10 %: it
 // is instruction-bound, 0.40 of the HBM roofline; 0.07 at D=16).  Here a lane loads its OWN row with 16-byte loads (NCH of
 // them in flight per lane, the row's two 128-byte lines stay in L1 between them), so the dot product, the norm and the
@@ -879,7 +879,9 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
         arco::infonce_kernel<MI, BF><<<grid, 128, smem, st>>>(p);                                                           \
     } while (0)
     static const bool lane_ok = [] { const char* e = getenv("ARCO_INFONCE_LANE"); return !(e && e[0] == '0'); }();
-    if (lane_ok && temp >= 0.03f && d.feat <= 64 && (cpl == 2 || cpl == 4 || cpl == 8 || cpl == 16)) {
+    // Measured on B200 (cold bank, Q=256, N=512): 128-byte rows and shorter gain (LA D=16: 0.027 vs 0.036 ms staged), a 256-byte
+    // row does not (ACDC D=64: 0.086 vs 0.051 ms -- 32 lanes x 2 lines per load instruction thrash L1), so longer rows stay staged.
+    if (lane_ok && temp >= 0.03f && cpl <= 8 && (cpl == 2 || cpl == 4 || cpl == 8)) {
         // short rows: one lane per key (see infonce_lane_kernel)
         const size_t sm = (size_t)6 * d.feat * 4 + (size_t)(d.negatives > 0 ? d.negatives : 1) * 4;
 #define ARCO_INFONCE_LANE(NC, BF)                                                                                        \
@@ -888,7 +890,7 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
             arco::infonce_lane_kernel<NC, BF><<<grid, 128, sm, st>>>(p);                                                  \
         } while (0)
         if (bf16bank) { if (cpl == 2) ARCO_INFONCE_LANE(2, true); else if (cpl == 4) ARCO_INFONCE_LANE(4, true); else if (cpl == 8) ARCO_INFONCE_LANE(8, true); else goto staged; }
-        else { if (cpl == 2) ARCO_INFONCE_LANE(2, false); else if (cpl == 4) ARCO_INFONCE_LANE(4, false); else if (cpl == 8) ARCO_INFONCE_LANE(8, false); else ARCO_INFONCE_LANE(16, false); }
+        else { if (cpl == 2) ARCO_INFONCE_LANE(2, false); else if (cpl == 4) ARCO_INFONCE_LANE(4, false); else ARCO_INFONCE_LANE(8, false); }
 #undef ARCO_INFONCE_LANE
         ARCO_LAUNCH_CHECK();
         return ARCO_OK;

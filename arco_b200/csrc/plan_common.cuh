@@ -63,17 +63,25 @@ __device__ __forceinline__ void derive_plan_warp(arco_plan* pl, const PlanBank& 
 }
 
 // Exclusive scan of cnt[0..NT) into off[0..NT], off[NT] = total, by one CTA of NTHR threads (NTHR a multiple of 32, <= 1024).
-// s_warp: 32 words of shared memory, s_carry: 1 word.  Returns the total (valid in every thread after the call).
+// A thread owns ITEMS consecutive entries per round: all its loads are issued together (one L2 round trip), scanned in
+// registers, one block-wide scan of the thread totals, one round of stores -- instead of a load / 4 barriers / store
+// round per NTHR entries.  s_warp: 32 words of shared memory, s_carry: 1 word.  Returns the total (valid in every thread).
 template <int NTHR>
 __device__ __forceinline__ uint32_t scan_row_block(const uint32_t* cnt, uint32_t* off, int NT, uint32_t* s_warp, uint32_t* s_carry) {
     constexpr int NW = NTHR / 32;
+    constexpr int ITEMS = 8;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) *s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < NT; base += NTHR) {
-        const int i = base + tid;
-        const uint32_t v = i < NT ? __ldcg(cnt + i) : 0u;                    // written by other CTAs of this launch: L2
-        uint32_t x = v;
+    for (int base = 0; base < NT; base += NTHR * ITEMS) {
+        const int i0 = base + tid * ITEMS;
+        uint32_t v[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) v[k] = (i0 + k) < NT ? __ldcg(cnt + i0 + k) : 0u;   // written by other CTAs of this launch: L2
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) mine += v[k];
+        uint32_t x = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -92,10 +100,14 @@ __device__ __forceinline__ uint32_t scan_row_block(const uint32_t* cnt, uint32_t
             if (lane < NW) s_warp[lane] = ws - w;                            // exclusive warp offsets
         }
         __syncthreads();
-        const uint32_t excl = *s_carry + s_warp[warp] + x - v;
-        if (i < NT) off[i] = excl;
+        uint32_t run = *s_carry + s_warp[warp] + x - mine;                   // exclusive prefix of this thread's first entry
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (i0 + k < NT) off[i0 + k] = run;
+            run += v[k];
+        }
         __syncthreads();
-        if (tid == NTHR - 1) *s_carry = excl + v;
+        if (tid == NTHR - 1) *s_carry = run;
         __syncthreads();
     }
     const uint32_t total = *s_carry;
