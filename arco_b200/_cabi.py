@@ -114,6 +114,9 @@ def _load():
         "arco_entropy_masks_scratch": (C.c_int64, []),
         "arco_entropy_masks": (C.c_int, [vp, vp, vp, i64, i64, f32, f32, vp, vp, vp, vp, vp]),
         "arco_prepare_contrast": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32, i64, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "arco_revisit_scratch_bytes": (C.c_int64, [i32, i32]),
+        "arco_revisit_loss": (C.c_int, [vp, vp, vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp]),
+        "arco_revisit_enqueue": (C.c_int, [vp, vp, vp, i64, i32, i32, i64, i32, vp]),
         "arco_similarity_dense_scratch": (C.c_int64, [i32, i32, i32, bp, vp]),
         "arco_similarity_dense": (C.c_int, [i32, i32, i32, i32, vp, vp, bp, vp, vp, vp, vp]),
     }

@@ -1,0 +1,299 @@
+// the nearest-neighbour "revisiting" loss and its random-pool queue.
+//
+// Reference (train_arco_2d.py:126-136, :156-159, :400-402, :109-120):
+//   rep_u, rep_u_teacher [bs, D, H, W] are flattened to [bs, L] (L = D*H*W = 32.5 M at D=496, 256x256) and L2-normalised
+//   (two full read+write passes each), dist = 2 - 2 * rep_n @ pool^T against the K = 36 unit rows of random_pool
+//   [K, L] fp32 (4.7 GB), once for the student (-> top-k smallest: the neighbours) and once for the teacher (-> the
+//   distances that are averaged), then the normalised teacher rows overwrite pool[ptr : ptr+bs].
+//
+// Here: ONE streaming pass reads every element of rep_u, rep_u_teacher and random_pool exactly once and produces all
+// 2*bs*K dot products plus the 2*bs squared norms (the normalised copies are never materialised: x_n . p = (x . p)/|x|);
+// a one-CTA kernel turns them into distances, top-k, gather and the loss; the enqueue is one scale-and-copy pass.
+//
+// The pass is a [2bs x L] x [L x K] contraction with M = 24, N = 36 -- 864 FMAs per 60 loaded values, i.e. FMA- and
+// HBM-time are about equal (0.8 vs 0.95 ms at the reference shape), so it runs on the CUDA cores in exact fp32 (a
+// single-pass TF32 MMA would truncate both operands: 1e-3 relative on a dot, the loss needs 1e-5): a warp owns a
+// 6-row x 9-column tile of the output, its lanes stride over L (conflict-free shared-memory reads, 3.6 FMAs per read),
+// chunks of L are double-buffered in shared memory with cp.async, CTAs are persistent and the 54 accumulators per lane
+// meet in shuffles once, at the end.  Per-CTA partials are folded in fp64 in a fixed order (deterministic).
+#include "arco_common.cuh"
+
+namespace arco {
+
+constexpr int RV_TM = 6, RV_TN = 9;          // output tile of a warp: rows (reps) x columns (pool rows)
+constexpr int RV_TC = 256;                   // elements of L per staged chunk
+constexpr int RV_MAX_WARPS = 16;             // 512 threads: 128 registers per thread for the 54 + 6 accumulators
+
+struct RevisitParams {
+    const void* rep_s;       // [bs][L]
+    const void* rep_t;       // [bs][L]
+    const float* pool;       // [K][L]
+    float* partials;         // [grid][MP*NP + MP]
+    int64_t L;
+    int32_t bs, K, MT, NT_, MP, NP;   // tiles and padded sizes: MP = MT*6 >= 2bs, NP = NT_*9 >= K
+    int64_t nchunks;
+};
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ float rv_load(const T* p);
+template <> __device__ __forceinline__ float rv_load<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float rv_load<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(p));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512, 1) revisit_dots_kernel(RevisitParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthr = blockDim.x;
+    const int MP = p.MP, NP = p.NP;
+    const size_t rep_bytes = (size_t)MP * RV_TC * sizeof(T), pool_bytes = (size_t)NP * RV_TC * 4;
+    const size_t buf_bytes = rep_bytes + pool_bytes;
+    auto rep_buf = [&](int b) { return reinterpret_cast<T*>(smem_raw + (size_t)b * buf_bytes); };
+    auto pool_buf = [&](int b) { return reinterpret_cast<float*>(smem_raw + (size_t)b * buf_bytes + rep_bytes); };
+
+    // padding rows (>= 2bs, >= K) are zero and never reloaded
+    for (size_t i = tid; i < 2 * buf_bytes / 16; i += nthr) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+
+    constexpr int PER16 = 16 / (int)sizeof(T);
+    const int rep_pieces = RV_TC / PER16;                    // 16-byte pieces per rep row per chunk
+    const int pool_pieces = RV_TC / 4;
+    auto issue = [&](int64_t ch, int b) {
+        const int64_t c0 = ch * RV_TC;
+        const int n_rep = 2 * p.bs * rep_pieces, n_pool = p.K * pool_pieces;
+        for (int i = tid; i < n_rep + n_pool; i += nthr) {
+            if (i < n_rep) {
+                const int row = i / rep_pieces, pc = i - row * rep_pieces;
+                const int64_t c = c0 + (int64_t)pc * PER16;
+                const T* src = reinterpret_cast<const T*>(row < p.bs ? p.rep_s : p.rep_t) + (int64_t)(row < p.bs ? row : row - p.bs) * p.L + c;
+                int64_t left = (p.L - c) * (int64_t)sizeof(T);
+                const int nb = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+                cp_async16(rep_buf(b) + (size_t)row * RV_TC + pc * PER16, nb > 0 ? (const void*)src : (const void*)p.pool, nb);
+            } else {
+                const int k = i - n_rep;
+                const int row = k / pool_pieces, pc = k - row * pool_pieces;
+                const int64_t c = c0 + (int64_t)pc * 4;
+                const float* src = p.pool + (int64_t)row * p.L + c;
+                int64_t left = (p.L - c) * 4;
+                const int nb = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+                cp_async16(pool_buf(b) + (size_t)row * RV_TC + pc * 4, nb > 0 ? (const void*)src : (const void*)p.pool, nb);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int mt = warp / p.NT_, nt = warp % p.NT_;
+    const bool has_tile = warp < p.MT * p.NT_;
+    float acc[RV_TM][RV_TN], sq[RV_TM];
+#pragma unroll
+    for (int r = 0; r < RV_TM; ++r) {
+        sq[r] = 0.f;
+#pragma unroll
+        for (int k = 0; k < RV_TN; ++k) acc[r][k] = 0.f;
+    }
+
+    int64_t ch = blockIdx.x;
+    int b = 0;
+    if (ch < p.nchunks) issue(ch, 0);
+    for (; ch < p.nchunks; ch += gridDim.x, b ^= 1) {
+        const int64_t nxt = ch + gridDim.x;
+        if (nxt < p.nchunks) {
+            issue(nxt, b ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (has_tile) {
+            const T* ar = rep_buf(b) + (size_t)(mt * RV_TM) * RV_TC;
+            const float* br = pool_buf(b) + (size_t)(nt * RV_TN) * RV_TC;
+#pragma unroll 2
+            for (int c = lane; c < RV_TC; c += 32) {
+                float a[RV_TM], bb[RV_TN];
+#pragma unroll
+                for (int r = 0; r < RV_TM; ++r) a[r] = rv_load<T>(ar + (size_t)r * RV_TC + c);
+#pragma unroll
+                for (int k = 0; k < RV_TN; ++k) bb[k] = br[(size_t)k * RV_TC + c];
+#pragma unroll
+                for (int r = 0; r < RV_TM; ++r) {
+#pragma unroll
+                    for (int k = 0; k < RV_TN; ++k) acc[r][k] += a[r] * bb[k];
+                }
+                if (nt == 0) {
+#pragma unroll
+                    for (int r = 0; r < RV_TM; ++r) sq[r] += a[r] * a[r];
+                }
+            }
+        }
+        __syncthreads();                                     // buffer b may be refilled by the next iteration's issue
+    }
+    if (has_tile) {
+        float* out = p.partials + (size_t)blockIdx.x * (MP * NP + MP);
+#pragma unroll
+        for (int r = 0; r < RV_TM; ++r) {
+#pragma unroll
+            for (int k = 0; k < RV_TN; ++k) {
+                float v = acc[r][k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) out[(mt * RV_TM + r) * NP + nt * RV_TN + k] = v;
+            }
+            if (nt == 0) {
+                float v = sq[r];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) out[MP * NP + mt * RV_TM + r] = v;
+            }
+        }
+    }
+}
+
+// One CTA: fold the per-CTA partials in fp64 (fixed order), distances, top-k smallest student distances per row
+// (train_arco_2d.py:133; ties: lower pool index first), gather of the teacher distances, mean (:134-135).
+// Outputs: loss[1]; nn_index int32 [bs][topk]; stats float [2*bs*K dots (student rows first) | 2*bs squared norms].
+__global__ void __launch_bounds__(256) revisit_finish_kernel(const float* __restrict__ partials, int rows, int bs, int K, int MP, int NP,
+                                                            int topk, float* __restrict__ loss, int32_t* __restrict__ nn_index,
+                                                            float* __restrict__ stats) {
+    extern __shared__ double s_tot[];                         // [2bs*K + 2bs]
+    const int tid = threadIdx.x;
+    const int n_dot = 2 * bs * K, n_all = n_dot + 2 * bs;
+    for (int i = tid; i < n_all; i += blockDim.x) {
+        int src;
+        if (i < n_dot) { const int m = i / K, k = i - m * K; src = m * NP + k; } else src = MP * NP + (i - n_dot);
+        double s = 0.0;
+        for (int r = 0; r < rows; ++r) s += (double)partials[(size_t)r * (MP * NP + MP) + src];
+        s_tot[i] = s;
+        stats[i] = (float)s;
+    }
+    __syncthreads();
+    __shared__ float s_row[64];
+    if (tid < bs) {
+        // F.normalize: x / max(|x|, 1e-12)  (:128,:130)
+        const float inv_s = 1.f / fmaxf(sqrtf((float)s_tot[n_dot + tid]), 1e-12f);
+        const float inv_t = 1.f / fmaxf(sqrtf((float)s_tot[n_dot + bs + tid]), 1e-12f);
+        unsigned long long taken = 0ull;
+        float sum = 0.f;
+        for (int j = 0; j < topk; ++j) {
+            int best = -1;
+            float bd = 0.f;
+            for (int k = 0; k < K; ++k) {
+                if (k < 64 && ((taken >> k) & 1ull)) continue;
+                const float dt = 2.f - 2.f * ((float)s_tot[tid * K + k] * inv_s);          // dist_t, from the STUDENT rows (:131)
+                if (best < 0 || dt < bd) { best = k; bd = dt; }
+            }
+            if (best >= 0) {
+                if (best < 64) taken |= 1ull << best;
+                nn_index[tid * topk + j] = best;
+                sum += 2.f - 2.f * ((float)s_tot[(bs + tid) * K + best] * inv_t);          // dist_q, from the TEACHER rows (:132,:134)
+            }
+        }
+        s_row[tid] = sum / (float)topk;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int i = 0; i < bs; ++i) s += s_row[i];
+        loss[0] = s / (float)bs;
+    }
+}
+
+// pool[(ptr + b) % K] = rep_t[b] / max(|rep_t[b]|, 1e-12)   (train_arco_2d.py:400-402 + :109-120); the pointer is host
+// bookkeeping (it advances by bs per call whatever the data, :117), so it is a plain argument.
+template <typename T>
+__global__ void __launch_bounds__(256) revisit_enqueue_kernel(const T* __restrict__ rep_t, const float* __restrict__ stats, float* __restrict__ pool,
+                                                             int64_t ptr, int bs, int K, int64_t L) {
+    const int b = blockIdx.y;
+    const float n2 = stats[2 * bs * K + bs + b];
+    const float inv = 1.f / fmaxf(sqrtf(n2), 1e-12f);
+    const int64_t row = (ptr + b) % K;
+    const T* src = rep_t + (int64_t)b * L;
+    float* dst = pool + row * L;
+    constexpr int PER16 = 16 / (int)sizeof(T);
+    const int64_t groups = L / PER16;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 raw = ldg_nc_u4(src + g * PER16);
+        if (PER16 == 4) {
+            float4 o;
+            o.x = __uint_as_float(raw.x) * inv; o.y = __uint_as_float(raw.y) * inv; o.z = __uint_as_float(raw.z) * inv; o.w = __uint_as_float(raw.w) * inv;
+            reinterpret_cast<float4*>(dst)[g] = o;
+        } else {
+            float4 o0, o1;
+            o0.x = __uint_as_float(raw.x << 16) * inv; o0.y = __uint_as_float(raw.x & 0xffff0000u) * inv;
+            o0.z = __uint_as_float(raw.y << 16) * inv; o0.w = __uint_as_float(raw.y & 0xffff0000u) * inv;
+            o1.x = __uint_as_float(raw.z << 16) * inv; o1.y = __uint_as_float(raw.z & 0xffff0000u) * inv;
+            o1.z = __uint_as_float(raw.w << 16) * inv; o1.w = __uint_as_float(raw.w & 0xffff0000u) * inv;
+            reinterpret_cast<float4*>(dst)[2 * g] = o0;
+            reinterpret_cast<float4*>(dst)[2 * g + 1] = o1;
+        }
+    }
+}
+
+static int revisit_geometry(int bs, int K, int* MT, int* NT_) {
+    *MT = (2 * bs + RV_TM - 1) / RV_TM;
+    *NT_ = (K + RV_TN - 1) / RV_TN;
+    return (*MT) * (*NT_);
+}
+
+}  // namespace arco
+
+extern "C" int64_t arco_revisit_scratch_bytes(int32_t bs, int32_t pool_rows) {
+    int MT, NT_;
+    arco::revisit_geometry(bs, pool_rows, &MT, &NT_);
+    const int64_t per = (int64_t)(MT * arco::RV_TM) * (NT_ * arco::RV_TN) + MT * arco::RV_TM;
+    return (int64_t)arco::sm_count() * per * 4 + 256;
+}
+
+extern "C" int arco_revisit_loss(const void* rep_u, const void* rep_u_teacher, const float* pool, int32_t bs, int32_t pool_rows,
+                                 int64_t length, int32_t rep_dtype, int32_t topk, float* loss, int32_t* nn_index, float* stats,
+                                 void* scratch, void* stream) {
+    ARCO_REQUIRE(rep_u && rep_u_teacher && pool && loss && nn_index && stats && scratch, "arco_revisit_loss: NULL argument");
+    ARCO_REQUIRE(bs >= 1 && bs <= 64 && pool_rows >= 1 && topk >= 1 && topk <= pool_rows && length > 0, "arco_revisit_loss: bad sizes");
+    const int esz = rep_dtype == ARCO_BF16 ? 2 : 4;
+    ARCO_REQUIRE((length * esz) % 16 == 0 && (length * 4) % 16 == 0, "arco_revisit_loss: D*H*W must make 16-byte aligned rows");
+    ARCO_REQUIRE((((uintptr_t)rep_u | (uintptr_t)rep_u_teacher | (uintptr_t)pool) & 15) == 0, "arco_revisit_loss: tensors must be 16-byte aligned");
+    int MT, NT_;
+    const int warps = arco::revisit_geometry(bs, pool_rows, &MT, &NT_);
+    ARCO_REQUIRE(warps <= arco::RV_MAX_WARPS, "arco_revisit_loss: ceil(2*bs/6) * ceil(K/9) must be <= 16 (the trainers: bs 12, K 36)");
+    arco::RevisitParams p;
+    p.rep_s = rep_u; p.rep_t = rep_u_teacher; p.pool = pool; p.partials = (float*)scratch;
+    p.L = length; p.bs = bs; p.K = pool_rows; p.MT = MT; p.NT_ = NT_; p.MP = MT * arco::RV_TM; p.NP = NT_ * arco::RV_TN;
+    p.nchunks = (length + arco::RV_TC - 1) / arco::RV_TC;
+    int grid = arco::sm_count();
+    if ((int64_t)grid > p.nchunks) grid = (int)p.nchunks;
+    const int threads = ((warps + 3) / 4) * 4 * 32;
+    const size_t smem = 2 * ((size_t)p.MP * arco::RV_TC * esz + (size_t)p.NP * arco::RV_TC * 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rep_dtype == ARCO_BF16) {
+        ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::revisit_dots_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        arco::revisit_dots_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p);
+    } else {
+        ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::revisit_dots_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        arco::revisit_dots_kernel<float><<<grid, threads, smem, st>>>(p);
+    }
+    ARCO_LAUNCH_CHECK();
+    const int n_all = 2 * bs * pool_rows + 2 * bs;
+    arco::revisit_finish_kernel<<<1, 256, (size_t)n_all * 8, st>>>(p.partials, grid, bs, pool_rows, p.MP, p.NP, topk, loss, nn_index, stats);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}
+
+extern "C" int arco_revisit_enqueue(const void* rep_u_teacher, const float* stats, float* pool, int64_t pool_ptr, int32_t bs,
+                                    int32_t pool_rows, int64_t length, int32_t rep_dtype, void* stream) {
+    ARCO_REQUIRE(rep_u_teacher && stats && pool && pool_ptr >= 0, "arco_revisit_enqueue: bad argument");
+    ARCO_REQUIRE(bs >= 1 && pool_rows >= bs && pool_rows % bs == 0, "arco_revisit_enqueue: K must be a multiple of the batch (train_arco_2d.py:113)");
+    const int esz = rep_dtype == ARCO_BF16 ? 2 : 4;
+    ARCO_REQUIRE((length * esz) % 16 == 0, "arco_revisit_enqueue: rows must be 16-byte multiples");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)(arco::sm_count() * 8 / bs + 1), (unsigned)bs);
+    if (rep_dtype == ARCO_BF16)
+        arco::revisit_enqueue_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)rep_u_teacher, stats, pool, pool_ptr, bs, pool_rows, length);
+    else
+        arco::revisit_enqueue_kernel<float><<<grid, 256, 0, st>>>((const float*)rep_u_teacher, stats, pool, pool_ptr, bs, pool_rows, length);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}

@@ -347,6 +347,22 @@ ARCO_API int arco_prepare_contrast(const float* pred_u, const float* pred_l_teac
                                    float* prob_u_teacher, float* entropy, float* low_mask, float* high_mask,
                                    float* thresholds, void* scratch, void* stream);
 
+/* ---- nearest-neighbour "revisiting" loss + random-pool queue ----------------------------
+   Replaces get_revisiting_loss (train_arco_2d.py:126-136) and the pool enqueue (:400-402 with _dequeue_and_enqueue :109-120).
+   rep_u / rep_u_teacher: [bs, length] (the [bs, D, H, W] tensors flattened; f32 or bf16 per rep_dtype), pool: f32
+   [pool_rows, length] unit rows.  ONE streaming pass yields every dot product and squared norm; the normalised copies the
+   reference materialises are never written.
+   loss f32[1]; nn_index int32 [bs, topk] (the top-k smallest STUDENT distances, ties: lower row first);
+   stats f32 [2*bs*pool_rows dots (student rows, then teacher rows) | 2*bs squared norms] -- input of arco_revisit_enqueue.
+   Limits: ceil(2*bs/6) * ceil(pool_rows/9) <= 16 (the trainers: bs 12, K 36), 16-byte aligned rows. */
+ARCO_API int64_t arco_revisit_scratch_bytes(int32_t bs, int32_t pool_rows);
+ARCO_API int arco_revisit_loss(const void* rep_u, const void* rep_u_teacher, const float* pool, int32_t bs, int32_t pool_rows,
+                               int64_t length, int32_t rep_dtype, int32_t topk, float* loss, int32_t* nn_index, float* stats,
+                               void* scratch, void* stream);
+/* pool[(pool_ptr + b) % pool_rows] = rep_u_teacher[b] / max(|rep_u_teacher[b]|, 1e-12) with the norms of `stats`. */
+ARCO_API int arco_revisit_enqueue(const void* rep_u_teacher, const float* stats, float* pool, int64_t pool_ptr, int32_t bs,
+                                  int32_t pool_rows, int64_t length, int32_t rep_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

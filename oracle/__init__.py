@@ -25,3 +25,4 @@ from .samplers_oracle import (  # noqa: F401
     sampler_plan,
     strata_sample,
 )
+from .revisit_oracle import pool_enqueue, revisiting_loss  # noqa: F401,E402

@@ -105,3 +105,82 @@ def prepare_inputs(case):
 
     return dict(pred_l=logits(n_lab), pred_u=logits(n_unlab), pred_l_teacher=logits(n_lab), pred_u_teacher=logits(n_unlab),
                 train_l_label=labels(n_lab), train_u_aug_label=labels(n_unlab), alpha_t=float(alpha_t), num_classes=C)
+
+
+# SURVEY.md section 8(f) rank 3 -- revisiting loss + random-pool queue (train_arco_2d.py:126-136, :109-120, :400-402)
+REVISIT_CASES = [
+    dict(name="revisit_small", bs=4, K=8, shape=(8, 8, 8), topk=3, steps=3, seed=201, dtype="f32"),
+    dict(name="revisit_ref_tiles", bs=12, K=36, shape=(6, 8, 10), topk=5, steps=2, seed=202, dtype="f32"),     # the trainers' bs / K / topk
+    dict(name="revisit_ragged", bs=3, K=9, shape=(5, 4, 12), topk=5, steps=4, seed=203, dtype="f32"),          # L = 240: one partial chunk
+    dict(name="revisit_bf16", bs=6, K=12, shape=(16, 8, 8), topk=4, steps=2, seed=204, dtype="bf16"),
+]
+
+
+def revisit_inputs(case):
+    """Inputs of a REVISIT case: per-step student / teacher tensors [bs, D, H, W] and the initial unit-row pool [K, L]."""
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(case["seed"])
+    bs, K = case["bs"], case["K"]
+    D, H, W = case["shape"]
+    L = D * H * W
+    pool = rs.randint(-512, 513, size=(K, L)).astype(np.float64)
+    pool[:, 0] += 0.5                                             # never an all-zero row
+    pool = (pool / np.sqrt((pool * pool).sum(axis=1, keepdims=True))).astype(np.float32)
+    tdt = torch.bfloat16 if case["dtype"] == "bf16" else torch.float32
+
+    def rep():
+        base = rs.randint(-256, 257, size=(bs, D, H, W)).astype(np.float32) / np.float32(64.0)
+        return torch.from_numpy(base).to(tdt).float()            # bf16 cases: bf16-representable values, handed over as fp32
+
+    reps_s, reps_t = [], []
+    for _ in range(case["steps"]):
+        s = rep()
+        # teacher = student + a perturbation, plus a pull towards one pool row so that neighbours are not arbitrary
+        t = (s * 0.75 + rep() * 0.25)
+        pull = torch.from_numpy(pool[rs.randint(0, K, size=bs)]).view(bs, D, H, W) * float(np.sqrt(L)) * 0.5
+        reps_s.append((s + pull).to(tdt).float())
+        reps_t.append((t + pull).to(tdt).float())
+    return dict(pool=torch.from_numpy(pool), rep_u=reps_s, rep_u_teacher=reps_t)
+
+
+# SURVEY.md section 8(f) rank 4 -- compute_unsupervised_loss (train_arco_2d.py:482-489)
+UNSUP_CASES = [
+    dict(name="unsup_small", B=2, C=4, spatial=(12, 12), strong_threshold=0.97, ignore_frac=0.1, seed=301),
+    dict(name="unsup_c19", B=3, C=19, spatial=(9, 14), strong_threshold=0.9, ignore_frac=0.3, seed=302),
+    dict(name="unsup_noignore", B=1, C=2, spatial=(16, 16), strong_threshold=0.5, ignore_frac=0.0, seed=303),
+]
+
+
+def unsup_inputs(case):
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(case["seed"])
+    B, C, sp = case["B"], case["C"], tuple(case["spatial"])
+    predict = torch.from_numpy(rs.randint(-4096, 4096, size=(B, C) + sp).astype(np.float32) / np.float32(1024.0))
+    target = rs.randint(0, C, size=(B,) + sp).astype(np.int64)
+    if case["ignore_frac"]:
+        target[rs.rand(*target.shape) < case["ignore_frac"]] = -1
+    logits = torch.from_numpy(rs.randint(0, 1025, size=(B,) + sp).astype(np.float32) / np.float32(1024.0))
+    return dict(predict=predict, target=torch.from_numpy(target), logits=logits)
+
+
+# SURVEY.md section 8(f) rank 4 -- TPS equivariance loss (train_arco_2d.py:404-423, tps/rand_tps.py:82-153)
+EQV_CASES = [
+    dict(name="eqv_small", B=4, C=4, H=32, W=32, sigma=0.05, weak_threshold=0.7, seed=401),
+    dict(name="eqv_rect", B=2, C=3, H=24, W=40, sigma=0.1, weak_threshold=0.5, seed=402),
+    dict(name="eqv_c19", B=2, C=19, H=16, W=16, sigma=0.05, weak_threshold=0.7, seed=403),
+]
+
+
+def eqv_inputs(case):
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(case["seed"] + 7)
+    B, C, H, W = case["B"], case["C"], case["H"], case["W"]
+
+    def f(*shape, lo=-4096, hi=4096, div=1024.0):
+        return torch.from_numpy(rs.randint(lo, hi, size=shape).astype(np.float32) / np.float32(div))
+
+    return dict(images=f(B, 1, H, W, lo=0, hi=1025), pred_all=f(B, C, H, W), pred_tps=f(B, C, H, W),
+                labels=torch.from_numpy(rs.randint(0, C, size=(B, H, W)).astype(np.int64)), logits=f(B, H, W, lo=0, hi=1025))
