@@ -19,6 +19,7 @@ _EXPORTS = {
     "compute_contra_memobank_loss": "contra",
     "prepare_contrast_inputs": "prepare", "softmax_entropy": "prepare", "entropy_masks": "prepare",
     "dense_similarity": "similarity",
+    "compute_unsupervised_loss": "stepterms", "RandTPS": "stepterms", "tps_equivariance_loss": "stepterms",
     "get_revisiting_loss": "revisit", "revisit_enqueue": "revisit", "_dequeue_and_enqueue": "revisit",
     "as_monte_carlo_sample": "samplers", "dequeue_and_enqueue": "samplers", "grid_as_monte_carlo_sample": "samplers",
     "grid_monte_carlo_sample": "samplers", "label_onehot": "samplers", "monte_carlo_sample": "samplers",

@@ -117,6 +117,13 @@ def _load():
         "arco_revisit_scratch_bytes": (C.c_int64, [i32, i32]),
         "arco_revisit_loss": (C.c_int, [vp, vp, vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp]),
         "arco_revisit_enqueue": (C.c_int, [vp, vp, vp, i64, i32, i32, i64, i32, vp]),
+        "arco_step_scratch_bytes": (C.c_int64, [i32, i64]),
+        "arco_unsup_loss": (C.c_int, [vp, vp, vp, f32, i32, i32, i64, vp, vp, vp]),
+        "arco_unsup_loss_backward": (C.c_int, [vp, vp, vp, vp, i32, i32, i64, vp, vp]),
+        "arco_tps_grid": (C.c_int, [vp, vp, i32, i32, i32, i32, vp, vp]),
+        "arco_grid_sample": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+        "arco_eqv_loss": (C.c_int, [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "arco_scale_rows": (C.c_int, [vp, vp, vp, i32, i64, vp, vp]),
         "arco_similarity_dense_scratch": (C.c_int64, [i32, i32, i32, bp, vp]),
         "arco_similarity_dense": (C.c_int, [i32, i32, i32, i32, vp, vp, bp, vp, vp, vp, vp]),
     }

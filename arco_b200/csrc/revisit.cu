@@ -45,6 +45,16 @@ template <> __device__ __forceinline__ float rv_load<__nv_bfloat16>(const __nv_b
     return bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(p));
 }
 
+template <typename T> __device__ __forceinline__ void rv_load2(const T* p, float& x, float& y);
+template <> __device__ __forceinline__ void rv_load2<float>(const float* p, float& x, float& y) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    x = v.x; y = v.y;
+}
+template <> __device__ __forceinline__ void rv_load2<__nv_bfloat16>(const __nv_bfloat16* p, float& x, float& y) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+    x = __uint_as_float(v << 16); y = __uint_as_float(v & 0xffff0000u);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(512, 1) revisit_dots_kernel(RevisitParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -112,21 +122,26 @@ __global__ void __launch_bounds__(512, 1) revisit_dots_kernel(RevisitParams p) {
         if (has_tile) {
             const T* ar = rep_buf(b) + (size_t)(mt * RV_TM) * RV_TC;
             const float* br = pool_buf(b) + (size_t)(nt * RV_TN) * RV_TC;
+            // a lane takes PAIRS of consecutive elements: one 8-byte (fp32) / 4-byte (bf16) shared load feeds two FMAs per
+            // output, 7.2 FMAs per load instruction instead of 3.6 (the loop is issue- and shared-memory-bound)
 #pragma unroll 2
-            for (int c = lane; c < RV_TC; c += 32) {
-                float a[RV_TM], bb[RV_TN];
+            for (int c = 2 * lane; c < RV_TC; c += 64) {
+                float a0[RV_TM], a1[RV_TM], b0[RV_TN], b1[RV_TN];
 #pragma unroll
-                for (int r = 0; r < RV_TM; ++r) a[r] = rv_load<T>(ar + (size_t)r * RV_TC + c);
+                for (int r = 0; r < RV_TM; ++r) rv_load2<T>(ar + (size_t)r * RV_TC + c, a0[r], a1[r]);
 #pragma unroll
-                for (int k = 0; k < RV_TN; ++k) bb[k] = br[(size_t)k * RV_TC + c];
+                for (int k = 0; k < RV_TN; ++k) {
+                    const float2 v = *reinterpret_cast<const float2*>(br + (size_t)k * RV_TC + c);
+                    b0[k] = v.x; b1[k] = v.y;
+                }
 #pragma unroll
                 for (int r = 0; r < RV_TM; ++r) {
 #pragma unroll
-                    for (int k = 0; k < RV_TN; ++k) acc[r][k] += a[r] * bb[k];
+                    for (int k = 0; k < RV_TN; ++k) { acc[r][k] += a0[r] * b0[k]; acc[r][k] += a1[r] * b1[k]; }
                 }
                 if (nt == 0) {
 #pragma unroll
-                    for (int r = 0; r < RV_TM; ++r) sq[r] += a[r] * a[r];
+                    for (int r = 0; r < RV_TM; ++r) { sq[r] += a0[r] * a0[r]; sq[r] += a1[r] * a1[r]; }
                 }
             }
         }

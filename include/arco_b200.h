@@ -363,6 +363,33 @@ ARCO_API int arco_revisit_loss(const void* rep_u, const void* rep_u_teacher, con
 ARCO_API int arco_revisit_enqueue(const void* rep_u_teacher, const float* stats, float* pool, int64_t pool_ptr, int32_t bs,
                                   int32_t pool_rows, int64_t length, int32_t rep_dtype, void* stream);
 
+/* ---- the other per-pixel loss terms of the 2-D trainer's step ---------------------------
+   All tensors f32 unless noted; [B, C, S] channel-first like the trainer's predictions; scratch: arco_step_scratch_bytes(). */
+ARCO_API int64_t arco_step_scratch_bytes(int32_t batch, int64_t space);
+/* compute_unsupervised_loss (train_arco_2d.py:482-489): target int64 [B,S] (ignore -1), logits [B,S] confidences.
+   stats out: [B] weighting (= #{logits >= thr} / #{valid}), [1] 1/N (N = #{loss > 0}), [1] the loss. */
+ARCO_API int arco_unsup_loss(const float* predict, const int64_t* target, const float* logits, float strong_threshold, int32_t batch,
+                             int32_t classes, int64_t space, float* stats, void* scratch, void* stream);
+ARCO_API int arco_unsup_loss_backward(const float* predict, const int64_t* target, const float* stats, const float* grad_out,
+                                      int32_t batch, int32_t classes, int64_t space, float* grad_predict, void* stream);
+/* TPSGridGen.forward (tps_stn_pytorch/tps_grid_gen.py:54-75) for RandTPS (tps/rand_tps.py:82-153): grid f32 [B,H,W,2] from
+   mapping [B, n_points+3, 2] (= inverse_kernel @ [source control points; 0], 28 x 28, host side) and the n_points target
+   control points [n_points, 2]. */
+ARCO_API int arco_tps_grid(const float* mapping, const float* control_points, int32_t n_points, int32_t batch, int32_t height,
+                           int32_t width, float* grid, void* stream);
+/* tps(x) = F.grid_sample(x, grid, bilinear, align_corners=True, zeros | border padding) (tps/grid_sample.py:11-12); forward only. */
+ARCO_API int arco_grid_sample(const float* input, const float* grid, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                              int32_t border_padding, float* out, void* stream);
+/* Equivariance loss (train_arco_2d.py:404-423) in one pass: mask from labels int64 [B,H,W] / logits [B,H,W], its warp, the warp of
+   pred_detached [B,C,H,W], both softmaxes, the masked KL.  stats out: [B] 1/(B*(sum mask_tps + 1e-7)), [1] the loss.
+   grad_unscaled: NULL, or [B,C,H,W] receiving mask_tps * (softmax(pred_tps) - softmax(warped)); the gradient w.r.t. pred_tps is
+   arco_scale_rows(grad_unscaled, stats, grad_out). */
+ARCO_API int arco_eqv_loss(const float* pred_tps, const float* pred_detached, const float* grid, const int64_t* labels,
+                           const float* logits, float weak_threshold, int32_t batch, int32_t classes, int32_t height, int32_t width,
+                           float* stats, float* grad_unscaled, void* scratch, void* stream);
+ARCO_API int arco_scale_rows(const float* g, const float* scale, const float* grad_out, int32_t batch, int64_t per_image, float* out,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

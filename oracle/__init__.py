@@ -26,3 +26,4 @@ from .samplers_oracle import (  # noqa: F401
     strata_sample,
 )
 from .revisit_oracle import pool_enqueue, revisiting_loss  # noqa: F401,E402
+from .stepterms_oracle import equivariance_loss, tps_grid, unsupervised_loss, warp  # noqa: F401,E402

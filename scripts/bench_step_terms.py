@@ -8,13 +8,14 @@ import time
 import torch
 
 sys.path.insert(0, ".")
+sys.path.insert(0, "..")
 import arco_b200
 import oracle
 
 dev = torch.device("cuda", 0)
 PEAK = 6539.2
 try:
-    PEAK = float(json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"])
+    PEAK = float(json.load(open(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
 

@@ -72,7 +72,7 @@ def test_trainer_size_against_oracle_ops(dtype):
     torch.cuda.synchronize()
     assert int(ptr) == bs
     want = torch.nn.functional.normalize(rep_t.reshape(bs, -1).float(), dim=-1)
-    assert float((pool[:bs] - want).abs().max()) <= 1e-9 + 2e-7 * float(want.abs().max())
+    assert float((pool[:bs] - want).abs().max()) <= 1e-5 * float(want.abs().max())
     assert not torch.equal(before, pool[:bs])
     del pool, rep_s, rep_t, want, before
     gc.collect()
