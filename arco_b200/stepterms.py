@@ -158,7 +158,7 @@ class RandTPS(torch.nn.Module):
         fk[:n, -2:].copy_(self.target_control_points)
         fk[-2:, :n].copy_(self.target_control_points.transpose(0, 1))
         self._inverse_kernel = torch.inverse(fk)
-        dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.grid = torch.nn.Parameter(torch.zeros(self.batch_size, self.height, self.width, 2, device=dev), requires_grad=False)
         self._ctrl_dev = self.target_control_points.to(dev).contiguous()
         self.reset_control_points()

@@ -43,7 +43,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="acdc2d_trainstep",
-                    choices=["acdc2d_loss", "acdc2d_trainstep", "la3d", "cityscapes"])
+                    choices=["acdc2d_loss", "acdc2d_trainstep", "la3d", "cityscapes", "acdc2d_fullstep"])
+    ap.add_argument("--no-fullstep", action="store_true",
+                    help="skip the BASELINE config-2 block (full ARCO 2-D training step, PyTorch U-Net + this repo's loss ops vs the "
+                         "reference's op mix; N=1 only)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--func", default="smc")
     ap.add_argument("--blocky", action="store_true", help="labels constant on 16-pixel tiles instead of iid")
@@ -358,6 +361,18 @@ def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, grou
     return out, ctx
 
 
+def main_fullstep(args):
+    import torch
+    assert torch.cuda.is_available(), "bench.py needs a GPU; there is no CPU fallback"
+    blk = run_fullstep(max(3, args.steps))
+    o = blk.get("arco_b200", {})
+    print(json.dumps({
+        "metric": "arco_2d_train_step_throughput", "value": o.get("value_mpixels_per_s"), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": 2, "ms_per_step": o.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": {"workload": "acdc2d_fullstep", "batch_per_gpu": 24, "classes": 4,
+                                                            "spatial": [256, 256], "feat": 496}, "acdc2d_fullstep": blk}))
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -438,6 +453,10 @@ def main_ours(args):
             gc.collect()
             torch.cuda.empty_cache()
 
+    fullstep = None
+    if rank == 0 and world == 1 and not args.no_fullstep and not args.no_configs:
+        fullstep = run_fullstep(max(3, args.steps // 4))
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = run_cpu(args.workload, 2, 1, args.func, budget_s=25.0)
@@ -460,10 +479,29 @@ def main_ours(args):
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "aten_gpu_baseline": aten, "stages": stages,
             "step_alg_bytes": head.get("step_alg_bytes"), "step_frac_hbm": head.get("step_frac_hbm"),
             "multi_gpu_check": head.get("multi_gpu_check"), "cuda_graph_replay": head.get("cuda_graph_replay"), "configs": configs,
+            "acdc2d_fullstep": fullstep,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_fullstep(steps):
+    """BASELINE.json config 2 as stated: one synthetic ARCO 2-D training step (U-Net student + EMA teacher, FeatureExtractor,
+    q_representation, CE + Dice, and all semi-supervised terms), bf16 autocast, batch 24, with the loss terms (a) as the
+    reference composes them from ATen ops on the same GPU and (b) through this repository's CUDA ops (scripts/fullstep.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    try:
+        import fullstep
+        ours = fullstep.run("arco_b200", steps=steps, warmup=2)
+        ref = fullstep.run("reference_ops", steps=max(2, steps // 2), warmup=1)
+        return {"what": "train_arco_2d.py:284-431 on synthetic tensors: batch 12+12, 256x256, 4 classes, D=496, Q=256, N=512, K=36, "
+                        "bf16 autocast backbones in PyTorch in both arms; wall clock with synchronize",
+                "arco_b200": ours, "reference_ops_on_gpu": ref, "step_speedup": ref["ms_per_step"] / ours["ms_per_step"],
+                "loss_terms_speedup": ref["ms_semi_supervised_terms"] / ours["ms_semi_supervised_terms"]}
+    except Exception as e:                                      # noqa: BLE001 -- reported, never fatal for the bench line
+        import traceback
+        return {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
 
 
 def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush, iters=10):
@@ -625,7 +663,9 @@ def run_e2e(torch, arco_b200, spec, x, memobank, ptrs, caps, dev, kw, world, ste
 if __name__ == "__main__":
     a = parse()
     COLD_BANK = a.bank == "cold"
-    if a.impl == "reference":
+    if a.workload == "acdc2d_fullstep":
+        main_fullstep(a)
+    elif a.impl == "reference":
         main_reference(a)
     else:
         main_ours(a)
