@@ -228,7 +228,7 @@ def main_reference(args):
 # our arm
 # --------------------------------------------------------------------------------------------------
 def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, group, steps, warmup, func, blocky, cold,
-                     with_stages=True, check_ranks=False, sparse_grad=False, graph=True):
+                     with_stages=True, check_ranks=False, sparse_grad=False, graph=True, index_labels=False):
     """One workload, device-timed: W warm-up steps, then `steps` forward+backward passes, each bracketed by CUDA events on
     the launching stream; max over ranks.  Returns the block that goes into the JSON line (headline or `configs`)."""
     from arco_b200.synth import bench_bank, bench_inputs
@@ -236,6 +236,10 @@ def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, grou
     memobank, ptrs, caps = bench_bank(spec, seed=1337 + rank, cold=cold)
     rep = x["rep"].requires_grad_(True)
     P = spec.pixels
+    if index_labels:
+        # the op's cheaper label input: int64 class maps [B,*S] (8 B/pixel) instead of the trainers' int64 one-hot (8*C B/pixel)
+        x["label_l"] = x["labels"][: spec.n_lab].clamp_min(0).contiguous()
+        x["label_u"] = x["labels"][spec.n_lab:].clamp_min(0).contiguous()
     kw = dict(delta_n=0.97, func=func, num_queries=spec.queries, num_negatives=spec.negatives, temp=0.5,
               process_group=group, seed=1337)
     if sparse_grad:
@@ -297,7 +301,7 @@ def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, grou
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     out = {
-        "workload": name + ("+cold_bank" if cold else "") + ("+blocky" if blocky else "") + ("+sparse_grad" if sparse_grad else ""),
+        "workload": name + ("+cold_bank" if cold else "") + ("+blocky" if blocky else "") + ("+sparse_grad" if sparse_grad else "") + ("+index_labels" if index_labels else ""),
         "ms_per_step": total_ms / steps, "value": world * P * steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "steps": steps,
         "pixels_per_gpu": P, "rep_storage": spec.dtype, "l2": l2_note,
     }
@@ -440,14 +444,15 @@ def main_ours(args):
     configs = None
     if not args.no_configs:
         configs = {}
-        todo = [("acdc2d_loss", False, False), ("la3d", False, False), ("la3d", True, False), ("cityscapes", False, False),
-                (args.workload, COLD_BANK, True)]
-        for name, cold, sparse in todo:
-            if name == args.workload and cold == COLD_BANK and not sparse:
+        todo = [("acdc2d_loss", False, False, False), ("la3d", False, False, False), ("la3d", True, False, False),
+                ("cityscapes", False, False, False), (args.workload, COLD_BANK, True, False), (args.workload, COLD_BANK, False, True)]
+        for name, cold, sparse, idxlab in todo:
+            if name == args.workload and cold == COLD_BANK and not sparse and not idxlab:
                 continue
             blk, c2 = measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, group, max(5, args.steps // 2),
                                        args.warmup, "asmc" if name == "la3d" else args.func, args.blocky, cold,
-                                       check_ranks=(name == "cityscapes"), sparse_grad=sparse)
+                                       check_ranks=(name == "cityscapes"), sparse_grad=sparse, index_labels=idxlab,
+                                       with_stages=not idxlab)
             configs[blk["workload"]] = blk
             del c2
             gc.collect()

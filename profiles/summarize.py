@@ -73,9 +73,9 @@ def main():
             f.write("\n")
     # bench lines
     out = [f"# {tag}: bench.py lines brought back from the B200 box\n"]
-    for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "bench_*.json"))):
+    for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "bench_*.json" if tag == "r01" else f"{tag}_final_bench*.json"))):
         try:
-            j = json.load(open(path))
+            j = json.loads(open(path).read().strip().splitlines()[-1])
         except Exception:
             continue
         out.append(f"\n## {os.path.basename(path)}: {j['config']['workload']} x{j['n_gpus']} -> {j['value']:.1f} {j['unit']}, "
@@ -86,7 +86,15 @@ def main():
                 continue
             out.append(f"| {k} | {v['ms']:.4f} | {v['alg_bytes']/1e6:.1f} | {v['gbs']:.0f} | {v['frac_hbm']:.3f} |")
         out.append(f"\nmeasured counts: {j.get('stages', {}).get('_measured')}\n")
-        out.append("```json\n" + json.dumps({k: j[k] for k in j if k != "stages"}) + "\n```")
+        for cname, cv in (j.get("configs") or {}).items():
+            out.append(f"\n### configs[{cname}] x{j['n_gpus']}: {cv['ms_per_step']:.4f} ms/step, {cv['value']:.1f} {cv['unit']}"
+                       f" (CUDA-graph replay: {(cv.get('cuda_graph_replay') or {}).get('ms_per_step')})\n")
+            if cv.get("stages"):
+                out.append("| stage | ms | algorithmic MB | GB/s | frac of measured HBM peak |\n|---|---|---|---|---|")
+                for k, v in cv["stages"].items():
+                    if not k.startswith("_"):
+                        out.append(f"| {k} | {v['ms']:.4f} | {v['alg_bytes']/1e6:.1f} | {v['gbs']:.0f} | {v['frac_hbm']:.3f} |")
+        out.append("```json\n" + json.dumps({k: j[k] for k in j if k not in ("stages", "configs")}) + "\n```")
     with open(os.path.join(ROOT, "profiles", f"{tag}_bench_lines.md"), "w") as f:
         f.write("\n".join(out) + "\n")
 
