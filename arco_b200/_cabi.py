@@ -124,6 +124,11 @@ def _load():
         "arco_grid_sample": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "arco_eqv_loss": (C.c_int, [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "arco_scale_rows": (C.c_int, [vp, vp, vp, i32, i64, vp, vp]),
+        "arco_keys_transform_scratch_bytes": (C.c_int64, [i32, i32]),
+        "arco_keys_transform": (C.c_int, [dp, bp, vp, vp, vp, vp]),
+        "arco_proto_transform": (C.c_int, [i32, i32, vp, i32, vp, vp, vp]),
+        "arco_anchor_gather": (C.c_int, [dp, vp, vp, vp, vp, vp, vp]),
+        "arco_infonce_rows": (C.c_int, [dp, vp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
         "arco_similarity_dense_scratch": (C.c_int64, [i32, i32, i32, bp, vp]),
         "arco_similarity_dense": (C.c_int, [i32, i32, i32, i32, vp, vp, bp, vp, vp, vp, vp]),
     }

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libarco_b200.so")
-SOURCES = ["cabi.cu", "classify.cu", "scan_plan.cu", "proto_enqueue.cu", "proto_tc.cu", "proto_tc32.cu", "sampler.cu", "infonce.cu", "sim_dense.cu", "prepare.cu", "revisit.cu", "stepterms.cu", "allreduce.cu", "grad.cu", "forward.cu"]
+SOURCES = ["cabi.cu", "classify.cu", "scan_plan.cu", "proto_enqueue.cu", "proto_tc.cu", "proto_tc32.cu", "sampler.cu", "infonce.cu", "sim_dense.cu", "prepare.cu", "revisit.cu", "stepterms.cu", "producers.cu", "allreduce.cu", "grad.cu", "forward.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -46,6 +46,10 @@ struct InfoParams {
     int32_t KC, RS16;        // keys per staged chunk, padded row stride in 16-byte chunks
     int32_t rep_dtype;
     float temp;
+    // "rows mode" (arco_infonce_rows): the anchors were selected and produced upstream -- row j*Q+q of a dense
+    // fp32 [C*Q][D] array and its pixel id -- instead of being rank-selected and gathered from a [B,D,S] tensor here
+    const float* anchor_rows;
+    const int32_t* anchor_pix_in;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,6 +107,57 @@ __device__ __forceinline__ void unpack_chunk(const uint4& u, float* v) {
 
 struct AnchorInfo { int pix; float na, cos0; };
 
+// Rank-select of one anchor: the idx-th anchor candidate (raster order) of LOOP-2 position j -> its pixel id in *s_pix.
+// Called by ONE full warp.  No compacted list exists: 32-ary search over the per-tile exclusive counts, then an in-tile
+// select on the code bytes (replaces seg_feat_low_entropy_list[i][idx], loss_helper_3d.py:455-457).
+__device__ __forceinline__ void anchor_select_warp(const InfoParams& p, int j, int q, int* s_pix) {
+    const int lane = threadIdx.x & 31;
+    const arco_plan* pl = p.plan;
+    const uint32_t n_anchor = pl->n_anchor[j];
+    uint32_t idx = (uint32_t)p.idx_a[(int64_t)j * p.Q + q];
+    if (idx >= n_anchor) {                                   // injected / foreign index out of range: flag it (the host raises), then stay in bounds
+        if (lane == 0) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE);
+        idx = n_anchor - 1;
+    }
+    const uint32_t* off = p.off_anchor + (int64_t)j * (p.NT + 1);
+    // largest tile lo with off[lo] <= idx: 32 probes per round instead of a dependent load per halving
+    int lo = 0, hi = p.NT;
+    while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        const int pos = lo + lane * step;
+        const bool le = pos < hi && off[pos] <= idx;
+        const int k = __popc(__ballot_sync(0xffffffffu, le));         // >= 1: off[lo] <= idx holds throughout
+        lo += (k - 1) * step;
+        hi = min(hi, lo + step);
+    }
+    const uint32_t r = idx - off[lo];
+    const int b = lo / p.tpi;
+    const int64_t s0 = (int64_t)(lo % p.tpi) * ARCO_TILE;
+    const int64_t n = min((int64_t)ARCO_TILE, p.S - s0);
+    const uint8_t* cp = p.codes + (int64_t)b * p.S + s0;
+    const uint32_t want = CODE_ANCHOR | (uint32_t)j;
+    uint32_t mask = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const int i = lane * 32 + k;
+        const uint32_t cd = i < n ? cp[i] : 0u;
+        mask |= (uint32_t)((cd & (CODE_ANCHOR | CODE_CLS_MASK)) == want) << k;
+    }
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const uint32_t excl = incl - cnt;
+    if (r >= excl && r < incl) {
+        uint32_t m = mask;
+        for (uint32_t i = 0; i < r - excl; ++i) m &= m - 1;
+        *s_pix = (int)((int64_t)b * p.S + s0 + lane * 32 + (__ffs(m) - 1));
+    }
+}
+
 // Anchor rank-select, anchor and prototype rows -> a_hat / k0hat (unit vectors in shared memory), |a| and cos(a, k0).
 // Called by all 128 threads of the CTA.
 __device__ __forceinline__ AnchorInfo info_prologue(const InfoParams& p, int j, int q, int bank_cls, float* a_hat,
@@ -111,53 +166,9 @@ __device__ __forceinline__ AnchorInfo info_prologue(const InfoParams& p, int j, 
     const int D = p.D;
     const arco_plan* pl = p.plan;
     // ---- anchor rank-select: idx-th anchor candidate of class j (... anchors by POSITION j) ----
-    if (warp == 0) {
-        const uint32_t n_anchor = pl->n_anchor[j];
-        uint32_t idx = (uint32_t)p.idx_a[(int64_t)j * p.Q + q];
-        if (idx >= n_anchor) {                                   // injected / foreign index out of range: flag it (the host raises), then stay in bounds
-            if (lane == 0) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE);
-            idx = n_anchor - 1;
-        }
-        const uint32_t* off = p.off_anchor + (int64_t)j * (p.NT + 1);
-        // largest tile lo with off[lo] <= idx: 32 probes per round instead of a dependent load per halving
-        int lo = 0, hi = p.NT;
-        while (hi - lo > 1) {
-            const int step = (hi - lo + 31) >> 5;
-            const int pos = lo + lane * step;
-            const bool le = pos < hi && off[pos] <= idx;
-            const int k = __popc(__ballot_sync(0xffffffffu, le));         // >= 1: off[lo] <= idx holds throughout
-            lo += (k - 1) * step;
-            hi = min(hi, lo + step);
-        }
-        const uint32_t r = idx - off[lo];
-        const int b = lo / p.tpi;
-        const int64_t s0 = (int64_t)(lo % p.tpi) * ARCO_TILE;
-        const int64_t n = min((int64_t)ARCO_TILE, p.S - s0);
-        const uint8_t* cp = p.codes + (int64_t)b * p.S + s0;
-        const uint32_t want = CODE_ANCHOR | (uint32_t)j;
-        uint32_t mask = 0;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const int i = lane * 32 + k;
-            const uint32_t cd = i < n ? cp[i] : 0u;
-            mask |= (uint32_t)((cd & (CODE_ANCHOR | CODE_CLS_MASK)) == want) << k;
-        }
-        const uint32_t cnt = __popc(mask);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        const uint32_t excl = incl - cnt;
-        if (r >= excl && r < incl) {
-            uint32_t m = mask;
-            for (uint32_t i = 0; i < r - excl; ++i) m &= m - 1;
-            *s_pix = (int)((int64_t)b * p.S + s0 + lane * 32 + (__ffs(m) - 1));
-        }
-    }
+    if (warp == 0 && p.anchor_rows == nullptr) anchor_select_warp(p, j, q, s_pix);
     __syncthreads();
-    const int pix = *s_pix;
+    const int pix = p.anchor_rows ? p.anchor_pix_in[(int64_t)j * p.Q + q] : *s_pix;
     const int ab = (int)(pix / p.S);
     const int64_t as = pix - (int64_t)ab * p.S;
 
@@ -166,7 +177,9 @@ __device__ __forceinline__ AnchorInfo info_prologue(const InfoParams& p, int j, 
     const double cntj = p.proto_sums[(int64_t)j * (D + 1) + D];
     for (int d = tid; d < D; d += 128) {
         float v;
-        if (p.rep_dtype == ARCO_BF16)
+        if (p.anchor_rows)
+            v = p.anchor_rows[((int64_t)j * p.Q + q) * D + d];
+        else if (p.rep_dtype == ARCO_BF16)
             v = bf16_bits_to_float(reinterpret_cast<const unsigned short*>(p.rep)[((int64_t)ab * D + d) * p.S + as]);
         else
             v = reinterpret_cast<const float*>(p.rep)[((int64_t)ab * D + d) * p.S + as];
@@ -816,13 +829,46 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
     info_fold_loss(p);
 }
 
+
+// SURVEY 8(f) rank 2 (sampled producers): the step's C*Q anchors as ROWS of the tensor the student's 1x1 convolutions read.
+// One CTA per (LOOP-2 position, query): warp 0 rank-selects the pixel, all threads gather its D channel values (one strided
+// element per channel, the same access the InfoNCE prologue makes) into rows[j*Q+q][0..D) in fp32.  Inactive positions get
+// pixel -1 and a zero row, so whatever is computed from the rows downstream stays finite and their gradient is dropped.
+__global__ void __launch_bounds__(128) anchor_gather_kernel(InfoParams p, float* __restrict__ rows, int32_t* __restrict__ pix_out) {
+    __shared__ int s_pix;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int bid = blockIdx.x;
+    const int j = bid / p.Q, q = bid % p.Q;
+    const bool active = p.plan->slot_active[j] != 0;
+    if (!active) {
+        for (int d = tid; d < p.D; d += 128) rows[(int64_t)bid * p.D + d] = 0.f;
+        if (tid == 0) pix_out[bid] = -1;
+        return;
+    }
+    if (warp == 0) anchor_select_warp(p, j, q, &s_pix);
+    __syncthreads();
+    const int pix = s_pix;
+    const int ab = (int)(pix / p.S);
+    const int64_t as = pix - (int64_t)ab * p.S;
+    for (int d = tid; d < p.D; d += 128) {
+        float v;
+        if (p.rep_dtype == ARCO_BF16)
+            v = bf16_bits_to_float(reinterpret_cast<const unsigned short*>(p.rep)[((int64_t)ab * p.D + d) * p.S + as]);
+        else
+            v = reinterpret_cast<const float*>(p.rep)[((int64_t)ab * p.D + d) * p.S + as];
+        rows[(int64_t)bid * p.D + d] = v;
+    }
+    if (tid == 0) pix_out[bid] = pix;
+}
+
 }  // namespace arco
 
 static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank* bank, const double* proto_sums,
                         const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
                         float* grad_anchor, int32_t* anchor_pix, float* logits, const float* momentum,
-                        const int32_t* momentum_on, float ema_decay, float ema_keep, float* proto_out, void* workspace, void* stream) {
-    ARCO_REQUIRE(dims && rep && bank && proto_sums && idx_anchor && idx_neg && loss && grad_anchor && anchor_pix &&
+                        const int32_t* momentum_on, float ema_decay, float ema_keep, float* proto_out, void* workspace, void* stream,
+                        const float* anchor_rows = nullptr, const int32_t* anchor_pix_in = nullptr) {
+    ARCO_REQUIRE(dims && (rep || anchor_rows) && bank && proto_sums && idx_anchor && idx_neg && loss && grad_anchor && anchor_pix &&
                      workspace, "arco_infonce: NULL argument");
     const arco_dims& d = *dims;
     ARCO_REQUIRE(d.feat % 4 == 0 && d.feat >= 4 && d.feat <= 512, "feat (D) must be a multiple of 4 in [4, 512]");
@@ -837,6 +883,7 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     p.off_anchor = (const uint32_t*)(ws + L.off_anchor);
     p.plan = (arco_plan*)(ws + L.plan);
     p.loss = loss; p.g_anchor = grad_anchor; p.anchor_pix = anchor_pix; p.logits = logits;
+    p.anchor_rows = anchor_rows; p.anchor_pix_in = anchor_pix_in;
     p.loss_parts = (float*)(ws + L.loss_parts);
     p.momentum = momentum; p.momentum_on = momentum_on; p.proto_out = proto_out; p.ema_decay = ema_decay; p.ema_keep = ema_keep;
     p.host_mirror = bank->host_mirror; p.host_queue_ptr = bank->host_queue_ptr;
@@ -941,4 +988,34 @@ extern "C" int arco_infonce_ema(const arco_dims* dims, const void* rep, const ar
     ARCO_REQUIRE(momentum && momentum_on && proto_out, "arco_infonce_ema: NULL momentum argument");
     return infonce_impl(dims, rep, bank, proto_sums, idx_anchor, idx_neg, temp, loss, grad_anchor, anchor_pix, logits,
                         momentum, momentum_on, ema_decay, ema_keep, proto_out, workspace, stream);
+}
+
+// ---- sampled producers ------------------------------------------------------------------------------
+extern "C" int arco_anchor_gather(const arco_dims* dims, const void* x, const int32_t* idx_anchor, float* rows,
+                                  int32_t* anchor_pix, void* workspace, void* stream) {
+    ARCO_REQUIRE(dims && x && idx_anchor && rows && anchor_pix && workspace, "arco_anchor_gather: NULL argument");
+    const arco_dims& d = *dims;
+    arco_ws_layout L;
+    arco::compute_layout(d, &L);
+    char* ws = (char*)workspace;
+    arco::InfoParams p;
+    memset(&p, 0, sizeof(p));
+    p.rep = x; p.idx_a = idx_anchor;
+    p.codes = (const uint8_t*)(ws + L.codes);
+    p.off_anchor = (const uint32_t*)(ws + L.off_anchor);
+    p.plan = (arco_plan*)(ws + L.plan);
+    p.S = d.space; p.C = d.classes; p.D = d.feat; p.Q = d.queries; p.N = d.negatives;
+    p.tpi = L.tiles_per_image; p.NT = L.n_tiles; p.rep_dtype = d.rep_dtype;
+    arco::anchor_gather_kernel<<<d.classes * d.queries, 128, 0, (cudaStream_t)stream>>>(p, rows, anchor_pix);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}
+
+extern "C" int arco_infonce_rows(const arco_dims* dims, const float* anchor_rows, const int32_t* anchor_pix_in, const arco_bank* bank,
+                                 const double* proto_sums, const int32_t* idx_anchor, const int32_t* idx_neg, float temp,
+                                 float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits, void* workspace,
+                                 void* stream) {
+    ARCO_REQUIRE(anchor_rows && anchor_pix_in, "arco_infonce_rows: NULL anchor rows");
+    return infonce_impl(dims, nullptr, bank, proto_sums, idx_anchor, idx_neg, temp, loss, grad_anchor, anchor_pix, logits,
+                        nullptr, nullptr, 0.f, 1.f, nullptr, workspace, stream, anchor_rows, anchor_pix_in);
 }

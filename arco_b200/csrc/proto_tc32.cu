@@ -56,14 +56,6 @@ struct ProtoTc32Params {
     int32_t B, C, D, tpi, NT, NDB, NST, NCLS, NLO;       // NCLS = MMA N: 16 or 32; NLO = lo slots in TMEM
 };
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
 // same with the A operand in tensor memory (lane = row m, column = k; 8 columns per K = 8 step)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -72,10 +64,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
-}
-// instruction descriptor of kind::tf32: D fp32, A/B TF32 (format 2), both K-major, M x N
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // byte offset of (row r, pixel kp) inside a SWIZZLE_128B box of rows x 32 fp32
 __device__ __forceinline__ uint32_t box_off32(uint32_t r, uint32_t kp) {

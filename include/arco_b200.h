@@ -390,6 +390,34 @@ ARCO_API int arco_eqv_loss(const float* pred_tps, const float* pred_detached, co
 ARCO_API int arco_scale_rows(const float* g, const float* scale, const float* grad_out, int32_t batch, int64_t per_image, float* out,
                              void* stream);
 
+/* ---- the representation producers, folded into the loss -------------------------------
+   Replaces the bias-free 1x1 convolutions that PRODUCE the loss's two big operands (model_2D.py:49-53 `fea4` of the teacher's and
+   the student's FeatureExtractor, train_arco_2d.py:231-234 `q_representation`, applied at train_arco_2d.py:317-329) by
+   applying their weights only where the loss consumes a value: a 1x1 convolution is linear and per-pixel, so
+   sum_px(W x) = W sum_px(x) and (W x)[pixel] = W (x[pixel]).  The caller runs arco_classify_plan and arco_proto_enqueue on
+   the convolutions' INPUT tensors (same [B, D, S] layout, square weights [D_out = D][D_in = D] row-major as
+   nn.Conv2d.weight[:, :, 0, 0]) and then: */
+/* The ring rows enqueued by this step (found from the device plan in `workspace`) <- weight . row, in place, on tcgen05
+   (bf16 ring: kind::f16; fp32 ring: kind::tf32, three-term split, needs arco_keys_transform_scratch_bytes() of scratch).
+   `weight` must have the ring's row dtype. */
+ARCO_API int64_t arco_keys_transform_scratch_bytes(int32_t feat, int32_t row_dtype);
+ARCO_API int arco_keys_transform(const arco_dims* dims, const arco_bank* bank, const void* weight, void* scratch,
+                                 void* workspace, void* stream);
+/* sums_out[c][0..D) = weight . sums_in[c][0..D) in fp64, sums_out[c][D] = sums_in[c][D] (the prototype buffer of
+   arco_proto_enqueue; multi-GPU: apply after the exchange).  weight_dtype ARCO_F32 | ARCO_BF16. */
+ARCO_API int arco_proto_transform(int32_t classes, int32_t feat, const void* weight, int32_t weight_dtype,
+                                  const double* sums_in, double* sums_out, void* stream);
+/* The step's anchors as rows: rows[j*Q+q][0..D) = x[:, :, pixel of the idx_anchor[j][q]-th anchor candidate of position j]
+   (fp32), anchor_pix[j*Q+q] = that pixel (-1 and a zero row for inactive positions).  x is [B, D, S] in dims->rep_dtype. */
+ARCO_API int arco_anchor_gather(const arco_dims* dims, const void* x, const int32_t* idx_anchor, float* rows,
+                                int32_t* anchor_pix, void* workspace, void* stream);
+/* arco_infonce with the anchors given as dense fp32 rows [C*Q][D] (what the student's convolutions made of the gathered rows)
+   and their pixels, instead of being gathered from a [B, D, S] tensor.  grad_anchor is d loss / d anchor_rows. */
+ARCO_API int arco_infonce_rows(const arco_dims* dims, const float* anchor_rows, const int32_t* anchor_pix_in, const arco_bank* bank,
+                               const double* proto_sums, const int32_t* idx_anchor, const int32_t* idx_neg, float temp,
+                               float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits, void* workspace,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,3 +27,4 @@ from .samplers_oracle import (  # noqa: F401
 )
 from .revisit_oracle import pool_enqueue, revisiting_loss  # noqa: F401,E402
 from .stepterms_oracle import equivariance_loss, tps_grid, unsupervised_loss, warp  # noqa: F401,E402
+from . import producers_oracle  # noqa: F401,E402

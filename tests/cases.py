@@ -184,3 +184,52 @@ def eqv_inputs(case):
 
     return dict(images=f(B, 1, H, W, lo=0, hi=1025), pred_all=f(B, C, H, W), pred_tps=f(B, C, H, W),
                 labels=torch.from_numpy(rs.randint(0, C, size=(B, H, W)).astype(np.int64)), logits=f(B, H, W, lo=0, hi=1025))
+
+
+# SURVEY.md section 8(f) rank 2 -- representation producers (model_2D.py:20-55, train_arco_2d.py:231-236, :313-333)
+# The trainers' own channel plan [256,128,64,32,16] -> D = 496 on a small pyramid (1x1 ... 16x16 = 256 pixels per image).
+PRODUCER_CASES = [
+    # two steps: the second one wraps the class rings (fill 40 of 60/50 rows, ~32 keys per class and step)
+    dict(name="producers_d496", fea_dim=(256, 128, 64, 32, 16), top=16, spec=CaseSpec(
+        "producers_d496", 2, 2, 4, (16, 16), 496, queries=16, negatives=8, func="smc", bank_init="fill:40",
+        caps=[60, 50, 50, 50], steps=2, seed=601)),
+]
+
+
+def producer_inputs(case, step=0):
+    """Machine-independent inputs of a PRODUCER case: the five decoder feature maps of the labelled / unlabelled batch for the
+    student and the teacher network (coarsest first, like the reference's ``fea_list``), and the weights of the two
+    FeatureExtractors (``fea0..fea4``) and of ``q_representation``; labels / probabilities / masks come from
+    ``exact_case(case['spec'], step)``.  Integer RNG + exact IEEE scaling only."""
+    import numpy as np
+    import torch
+    spec = case["spec"]
+    rs = np.random.RandomState(spec.seed * 31 + 17)               # weights: the same at every step
+    fea = list(case["fea_dim"])
+
+    def tri(shape, scale):
+        a = rs.randint(-256, 257, size=shape).astype(np.int32) + rs.randint(-256, 257, size=shape).astype(np.int32)
+        return torch.from_numpy((a.astype(np.float32) * np.float32(scale)).astype(np.float32))
+
+    def extractor_weights():
+        ws, cnt = [], 0
+        for i in range(5):
+            cnt += fea[i]
+            # ~ N(0, 1/cin): keeps the activations O(1) through the residual chain
+            ws.append(tri((cnt, cnt), 2.0 ** -9 / 2 ** int(np.log2(cnt) / 2 - 3)))
+        return ws
+
+    w_q_fe, w_k_fe = extractor_weights(), extractor_weights()
+    D = sum(fea)
+    w_q_rep = [tri((D, D), 2.0 ** -10), tri((D, D), 2.0 ** -10)]
+    rs2 = np.random.RandomState(spec.seed * 31 + 18 + 101 * step)
+    top = case["top"]
+    sizes = [max(1, top >> (4 - i)) for i in range(5)]
+
+    def maps(batch):
+        return [torch.from_numpy((rs2.randint(-256, 257, size=(batch, fea[i], sizes[i], sizes[i])).astype(np.float32)
+                                  / np.float32(128.0)).astype(np.float32)) for i in range(5)]
+
+    return dict(w_q_fe=w_q_fe, w_k_fe=w_k_fe, w_q_rep=w_q_rep,
+                maps_l=maps(spec.n_lab), maps_u=maps(spec.n_unlab),
+                maps_l_teacher=maps(spec.n_lab), maps_u_teacher=maps(spec.n_unlab))
