@@ -88,7 +88,7 @@ def test_fused_producers_match_reference(case):
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
 
 
-def _trainer_like(dtype, dev, seed=77, n_lab=2, n_unlab=2, spatial=(64, 64), D=496, C=4, Q=64, N=128, fill=600, caps=(700, 650, 650, 650)):
+def _trainer_like(dtype, dev, seed=77, n_lab=2, n_unlab=2, spatial=(128, 128), D=496, C=4, Q=64, N=128, fill=600, caps=(700, 650, 650, 650)):
     spec = CaseSpec("producers_big", n_lab, n_unlab, C, spatial, D, queries=Q, negatives=N, func="smc", bank_init=f"fill:{fill}",
                     caps=list(caps), seed=seed, dtype="bf16" if dtype == torch.bfloat16 else "f32")
     x = {k: v.to(dev) for k, v in exact_case(spec, 0).items()}
