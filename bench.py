@@ -462,6 +462,18 @@ def main_ours(args):
     if rank == 0 and world == 1 and not args.no_fullstep and not args.no_configs:
         fullstep = run_fullstep(max(3, args.steps // 4))
 
+    producers_blk = None
+    if rank == 0 and world == 1 and not args.no_configs and args.workload == "acdc2d_trainstep":
+        # the loss INCLUDING its producers (fea4 / q_representation), reference composition vs fused
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        try:
+            import bench_producers
+            producers_blk = bench_producers.run(args.workload)
+        except Exception as e:                                  # noqa: BLE001 -- reported, never fatal for the bench line
+            producers_blk = {"error": repr(e)[:300]}
+        gc.collect()
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = run_cpu(args.workload, 2, 1, args.func, budget_s=25.0)
@@ -484,7 +496,7 @@ def main_ours(args):
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "aten_gpu_baseline": aten, "stages": stages,
             "step_alg_bytes": head.get("step_alg_bytes"), "step_frac_hbm": head.get("step_frac_hbm"),
             "multi_gpu_check": head.get("multi_gpu_check"), "cuda_graph_replay": head.get("cuda_graph_replay"), "configs": configs,
-            "acdc2d_fullstep": fullstep,
+            "acdc2d_fullstep": fullstep, "producers": producers_blk,
         }
         print(json.dumps(line))
     if world > 1:

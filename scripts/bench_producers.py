@@ -39,8 +39,15 @@ def timed(fn, n=10, warm=3):
     return e0.elapsed_time(e1) / n
 
 
-def main():
-    workload = sys.argv[1] if len(sys.argv) > 1 else "acdc2d_trainstep"
+def run(workload="acdc2d_trainstep", emit=None):
+    """Returns the list of result dicts (also handed to ``emit`` one by one as they are produced)."""
+    results = []
+
+    def out(d):
+        results.append(d)
+        if emit is not None:
+            emit(d)
+
     spec, x = bench_inputs(workload, dev)
     D = spec.feat
     g = torch.Generator(device=dev).manual_seed(3)
@@ -81,14 +88,14 @@ def main():
     ms_fused_sparse = timed(lambda: fused(True), n=20, warm=3)
     pixels = spec.pixels
     conv_flop = 2.0 * pixels * D * D
-    print(json.dumps({
+    out(({
         "what": "contrastive loss incl. its producers (teacher fea4; student fea4 + q_representation), fwd+bwd", "workload": workload,
         "dtype": str(cdt), "pixels": pixels, "D": D,
-        "ms_reference_composition": ms_ref, "ms_fused_producers": ms_fused, "ms_fused_producers_sparse_grad": ms_fused_sparse,
+        "ms_reference_composition": ms_ref, "ms_fused_producers": ms_fused, "ms_fused_producers_sparse_grad_leaf_input": ms_fused_sparse,
         "speedup": ms_ref / ms_fused,
         "note": "reference composition = 4 forward + 6 backward 1x1-conv GEMMs of %.0f GFLOP each through torch (cuDNN/cuBLAS) "
                 "around arco_b200.compute_contra_memobank_loss; fused = no rep / rep_teacher tensor, weights applied to the "
-                "K key rows (tcgen05), the C x D class sums (fp64) and the C*Q anchor rows" % (conv_flop / 1e9)}), flush=True)
+                "K key rows (tcgen05), the C x D class sums (fp64) and the C*Q anchor rows" % (conv_flop / 1e9)}))
 
     # ---- the new kernels alone (staged C-ABI calls on a prepared workspace) ----
     bank, ptr, _ = bench_bank(spec)
@@ -118,12 +125,12 @@ def main():
     byts = 2.0 * K * D * e + D * D * e
     tf_peak = float(PEAKS.get("bf16_tflops_sustained", PEAKS.get("bf16_tflops", 1378.6)))
     hbm = float(PEAKS.get("hbm_gbs", 6539.2))
-    print(json.dumps({
+    out(({
         "kernel": "keys_transform_kernel<%s>" % ("tf32 x3" if ring_f32 else "bf16"), "K_rows": K, "D": D, "ms": ms_kt,
         "issued_tflops": flop / ms_kt / 1e9, "alg_bytes": byts, "gbs": byts / ms_kt / 1e6,
         "frac_of_hbm_peak": byts / ms_kt / 1e6 / hbm, "frac_of_bf16_tensor_peak": flop / ms_kt / 1e9 / tf_peak,
         "note": "%d tiles of 128 rows over 148 persistent CTAs (<= 2 per CTA): start-up + one tile's latency, neither roofline binds"
-                % ((K + 127) // 128)}), flush=True)
+                % ((K + 127) // 128)}))
     proto_x, proto = dbg["proto_sums_x"], torch.empty_like(dbg["proto_sums_x"])
     ms_pt = timed(lambda: _cabi.check(_cabi.lib.arco_proto_transform(spec.classes, D, wk_ring.data_ptr(), _cabi.F32 if ring_f32 else _cabi.BF16,
                                                                       proto_x.data_ptr(), proto.data_ptr(), sp), "pt"), n=50, warm=5)
@@ -131,8 +138,13 @@ def main():
     pix = torch.empty((spec.classes * 256,), dtype=torch.int32, device=dev)
     ms_ag = timed(lambda: _cabi.check(_cabi.lib.arco_anchor_gather(C.byref(dims), xs.detach().data_ptr(), dbg["idx_anchor"].data_ptr(),
                                                                     rows.data_ptr(), pix.data_ptr(), wsbuf.data_ptr(), sp), "ag"), n=50, warm=5)
-    print(json.dumps({"kernel": "proto_transform_kernel", "ms": ms_pt}), flush=True)
-    print(json.dumps({"kernel": "anchor_gather_kernel", "ms": ms_ag, "rows": spec.classes * 256}), flush=True)
+    out({"kernel": "proto_transform_kernel", "ms": ms_pt})
+    out({"kernel": "anchor_gather_kernel", "ms": ms_ag, "rows": spec.classes * 256})
+    return results
+
+
+def main():
+    run(sys.argv[1] if len(sys.argv) > 1 else "acdc2d_trainstep", emit=lambda d: print(json.dumps(d), flush=True))
 
 
 if __name__ == "__main__":

@@ -55,6 +55,30 @@ def main():
                 torch.cuda.synchronize()
                 assert torch.isfinite(loss)
         print("ok", spec.name, float(loss))
+    if only is None or "producers" in only:
+        # in-place tcgen05 key-row transform (bf16 kind::f16 and fp32 kind::tf32 x3), anchors as rows
+        from arco_b200 import producers
+        for dt in ("bf16", "f32"):
+            spec = CaseSpec("producers_" + dt, 1, 2, 4, (32, 32), 80, queries=16, negatives=12, dtype=dt, bank_init="fill:150",
+                            caps=[200] * 4, mask_frac=0.9)
+            bank, ptr, caps = make_bank(spec)
+            if dt == "bf16":
+                for m in bank:
+                    m[0] = m[0].to(torch.bfloat16).to(torch.float32)
+            gen = torch.Generator(device=dev).manual_seed(5)
+            ws = [(torch.randn(80, 80, device=dev, generator=gen) / 9).requires_grad_(True) for _ in range(3)]
+            wk = torch.randn(80, 80, device=dev, generator=gen) / 9
+            for step in range(2):
+                g = {k: v.to(dev) for k, v in exact_case(spec, step).items()}
+                xs = g["rep"].clone().requires_grad_(True)
+                _, loss = producers.compute_contra_memobank_loss_from_features(
+                    xs, g["rep_teacher"], ws, wk, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"], g["low_mask"], g["high_mask"],
+                    bank, ptr, caps, delta_n=spec.delta_n, func=spec.func, num_queries=spec.queries, num_negatives=spec.negatives,
+                    temp=spec.temp, seed=7)
+                loss.backward()
+                torch.cuda.synchronize()
+                assert torch.isfinite(loss)
+            print("ok", spec.name, float(loss))
     if only is None or "prepare" in only:
         n, c, s = 2, 4, 64 * 64
         gen = torch.Generator(device=dev).manual_seed(3)
