@@ -67,6 +67,10 @@ class Bank(C.Structure):
     ]
 
 
+class Exchange(C.Structure):
+    _fields_ = [("peers", C.c_void_p), ("seq", C.c_uint64), ("slot_doubles", C.c_int64), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 class StepIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rep", "rep_teacher", "label_l", "label_u", "prob_l", "prob_u", "low_mask", "high_mask", "proto_sums",
@@ -124,6 +128,7 @@ def _load():
         "arco_grid_sample": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "arco_eqv_loss": (C.c_int, [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "arco_scale_rows": (C.c_int, [vp, vp, vp, i32, i64, vp, vp]),
+        "arco_infonce_sharded": (C.c_int, [dp, vp, bp, C.POINTER(Exchange), i32, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
         "arco_keys_transform_scratch_bytes": (C.c_int64, [i32, i32]),
         "arco_keys_transform": (C.c_int, [dp, bp, vp, vp, vp, vp]),
         "arco_proto_transform": (C.c_int, [i32, i32, vp, i32, vp, vp, vp]),

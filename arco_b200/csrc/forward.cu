@@ -61,19 +61,24 @@ extern "C" int arco_forward(const arco_dims* dims, const arco_step_io* io, const
     ARCO_REQUIRE(!sharded || io->exchange_local, "arco_forward: exchange_local is NULL");
     if ((rc = arco_proto_enqueue(dims, io->rep_teacher, bank, sharded ? io->exchange_local : io->proto_sums, workspace, main_st)) != ARCO_OK)
         return rc;
+    ARCO_CUDA_CHECK(cudaStreamWaitEvent(main_st, ss->join_sample, 0));
     if (sharded) {
-        // the one exchange step: global (feature sum, count) per class, then the valid-class list from the GLOBAL counts
-        if ((rc = arco_proto_allreduce_p2p(dims, io->exchange_peers, io->exchange_rank, io->exchange_world, io->exchange_seq,
-                                           io->exchange_slot, io->proto_sums, workspace, main_st)) != ARCO_OK)
+        // The one exchange step (global class sums, then the valid-class list from the GLOBAL counts) runs INSIDE the InfoNCE
+        // launch, underneath its negatives pass on the rank-local plan (arco_infonce_sharded).  The two gated launches after
+        // it only do work when the global counts changed the plan (a rank lacks a class another rank has).
+        arco_exchange x;
+        x.peers = (const uint64_t*)io->exchange_peers; x.seq = io->exchange_seq; x.slot_doubles = io->exchange_slot;
+        x.rank = io->exchange_rank; x.world = io->exchange_world;
+        if ((rc = arco_infonce_sharded(dims, io->rep, bank, &x, 0, (double*)io->proto_sums, io->idx_anchor, io->idx_neg, io->temp,
+                                       io->loss, io->grad_anchor, io->anchor_pix, io->logits, io->momentum, io->momentum_on,
+                                       io->ema_decay, io->ema_keep, io->proto_out, workspace, main_st)) != ARCO_OK)
             return rc;
-        ARCO_CUDA_CHECK(cudaStreamWaitEvent(main_st, ss->join_sample, 0));    // the speculative sampler has read the local plan
-        if ((rc = arco_replan_global(dims, io->proto_sums, workspace, main_st)) != ARCO_OK) return rc;
         if ((rc = arco_sample_if_replanned(dims, io->func, io->seed, io->step, io->idx_anchor, io->idx_neg, workspace, main_st)) != ARCO_OK)
             return rc;
-    } else {
-        ARCO_CUDA_CHECK(cudaStreamWaitEvent(main_st, ss->join_sample, 0));
-    }
-    if (io->momentum)
+        rc = arco_infonce_sharded(dims, io->rep, bank, nullptr, 1, (double*)io->proto_sums, io->idx_anchor, io->idx_neg, io->temp,
+                                  io->loss, io->grad_anchor, io->anchor_pix, io->logits, io->momentum, io->momentum_on,
+                                  io->ema_decay, io->ema_keep, io->proto_out, workspace, main_st);
+    } else if (io->momentum)
         rc = arco_infonce_ema(dims, io->rep, bank, io->proto_sums, io->idx_anchor, io->idx_neg, io->temp, io->loss,
                               io->grad_anchor, io->anchor_pix, io->logits, io->momentum, io->momentum_on, io->ema_decay,
                               io->ema_keep, io->proto_out, workspace, main_st);

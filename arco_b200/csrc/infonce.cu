@@ -50,6 +50,16 @@ struct InfoParams {
     // fp32 [C*Q][D] array and its pixel id -- instead of being rank-selected and gathered from a [B,D,S] tensor here
     const float* anchor_rows;
     const int32_t* anchor_pix_in;
+    // Multi-GPU (arco_infonce_sharded): the exchange step of the path runs INSIDE this launch.  Block 0 is an extra CTA that
+    // trades the C x (D+1) fp64 class sums with the peers over NVLink and re-derives the valid-class list while the query
+    // CTAs (blocks 1..nq) run their negatives pass on the rank-local plan; they meet at plan->reserved0 before the merge.
+    const unsigned long long* xchg_peers;   // NULL: no exchange in this launch
+    double* xchg_out;                       // == proto_sums (written by block 0)
+    unsigned long long xchg_seq;
+    int64_t xchg_slot;                      // doubles per slot of the peer-mapped buffer
+    int32_t xchg_rank, xchg_world;
+    int32_t gate_replanned;                 // 1: this launch is the redo; it does nothing unless plan->replanned
+    int32_t nq;                             // C * Q query CTAs
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -158,23 +168,20 @@ __device__ __forceinline__ void anchor_select_warp(const InfoParams& p, int j, i
     }
 }
 
-// Anchor rank-select, anchor and prototype rows -> a_hat / k0hat (unit vectors in shared memory), |a| and cos(a, k0).
-// Called by all 128 threads of the CTA.
-__device__ __forceinline__ AnchorInfo info_prologue(const InfoParams& p, int j, int q, int bank_cls, float* a_hat,
-                                                    float* k0hat, float (*s_red)[2], int* s_pix) {
+// Anchor rank-select and anchor row -> a_hat (unit vector in shared memory), |a|.  Called by all 128 threads of the CTA.
+// The prototype half of the prologue (info_proto) runs AFTER the negatives pass: nothing in that pass needs the prototype,
+// and on a batch shard the global class sums arrive while it runs.
+__device__ __forceinline__ AnchorInfo info_anchor(const InfoParams& p, int j, int q, float* a_hat, float (*s_red)[2], int* s_pix) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D;
-    const arco_plan* pl = p.plan;
     // ---- anchor rank-select: idx-th anchor candidate of class j (... anchors by POSITION j) ----
     if (warp == 0 && p.anchor_rows == nullptr) anchor_select_warp(p, j, q, s_pix);
     __syncthreads();
     const int pix = p.anchor_rows ? p.anchor_pix_in[(int64_t)j * p.Q + q] : *s_pix;
     const int ab = (int)(pix / p.S);
     const int64_t as = pix - (int64_t)ab * p.S;
-
-    // ---- anchor row (D strided loads, one 32-B sector each) and prototype row ----
-    float n2a = 0.f, n2k = 0.f;
-    const double cntj = p.proto_sums[(int64_t)j * (D + 1) + D];
+    // ---- anchor row (D strided loads, one 32-B sector each) ----
+    float n2a = 0.f;
     for (int d = tid; d < D; d += 128) {
         float v;
         if (p.anchor_rows)
@@ -183,41 +190,178 @@ __device__ __forceinline__ AnchorInfo info_prologue(const InfoParams& p, int j, 
             v = bf16_bits_to_float(reinterpret_cast<const unsigned short*>(p.rep)[((int64_t)ab * D + d) * p.S + as]);
         else
             v = reinterpret_cast<const float*>(p.rep)[((int64_t)ab * D + d) * p.S + as];
-        float k = (float)(p.proto_sums[(int64_t)j * (D + 1) + d] / cntj);   // class mean (:380-384)
+        a_hat[d] = v;
+        n2a += v * v;
+    }
+    n2a = warp_sum(n2a);
+    if (lane == 0) s_red[warp][0] = n2a;
+    __syncthreads();
+    const float na = sqrtf(s_red[0][0] + s_red[1][0] + s_red[2][0] + s_red[3][0]);
+    const float inv_na = 1.f / fmaxf(na, kEps);
+    for (int d = tid; d < D; d += 128) a_hat[d] *= inv_na;
+    __syncthreads();
+    AnchorInfo out;
+    out.pix = pix;
+    out.na = na;
+    out.cos0 = 0.f;
+    return out;
+}
+
+// Prototype row (class mean, optionally the EMA blend) -> k0hat (unit vector) and cos(a, k0).  All 128 threads.
+__device__ __forceinline__ float info_proto(const InfoParams& p, int j, int q, int bank_cls, const float* a_hat, float* k0hat) {
+    __shared__ float s_k[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = p.D;
+    const volatile double* ps = p.proto_sums;                 // on a batch shard block 0 of THIS launch wrote them
+    const double cntj = ps[(int64_t)j * (D + 1) + D];
+    float n2k = 0.f;
+    for (int d = tid; d < D; d += 128) {
+        float k = (float)(ps[(int64_t)j * (D + 1) + d] / cntj);   // class mean (:380-384)
         if (p.momentum) {
             // positive = (1-a)*proto + a*momentum_prototype[valid_classes[i]][q]  (:490-495); prototype[...] = positive (:497)
             const int64_t mo = ((int64_t)bank_cls * p.Q + q) * D + d;
             if (*p.momentum_on) k = p.ema_keep * k + p.ema_decay * p.momentum[mo];
             if (p.proto_out) p.proto_out[mo] = k;
         }
-        a_hat[d] = v;
         k0hat[d] = k;
-        n2a += v * v;
         n2k += k * k;
     }
-    n2a = warp_sum(n2a);
     n2k = warp_sum(n2k);
-    if (lane == 0) { s_red[warp][0] = n2a; s_red[warp][1] = n2k; }
+    __syncthreads();                       // s_k may still be read by a previous use
+    if (lane == 0) s_k[warp] = n2k;
     __syncthreads();
-    const float na = sqrtf(s_red[0][0] + s_red[1][0] + s_red[2][0] + s_red[3][0]);
-    const float nk0 = sqrtf(s_red[0][1] + s_red[1][1] + s_red[2][1] + s_red[3][1]);
-    const float inv_na = 1.f / fmaxf(na, kEps), inv_nk0 = 1.f / fmaxf(nk0, kEps);
+    const float nk0 = sqrtf(s_k[0] + s_k[1] + s_k[2] + s_k[3]);
+    const float inv_nk0 = 1.f / fmaxf(nk0, kEps);
     float c0 = 0.f;
     for (int d = tid; d < D; d += 128) {
-        const float a = a_hat[d] * inv_na, k = k0hat[d] * inv_nk0;
-        a_hat[d] = a;
+        const float k = k0hat[d] * inv_nk0;
         k0hat[d] = k;
-        c0 += a * k;
+        c0 += a_hat[d] * k;
     }
     c0 = warp_sum(c0);
-    __syncthreads();                       // everyone is done reading s_red
-    if (lane == 0) s_red[warp][0] = c0;
+    __syncthreads();                       // everyone is done reading s_k
+    if (lane == 0) s_k[warp] = c0;
     __syncthreads();
-    AnchorInfo out;
-    out.pix = pix;
-    out.na = na;
-    out.cos0 = s_red[0][0] + s_red[1][0] + s_red[2][0] + s_red[3][0];
-    return out;
+    return s_k[0] + s_k[1] + s_k[2] + s_k[3];
+}
+
+// ---- the exchange step inside the launch (batch shards) -------------------------------------------------------------
+__device__ __forceinline__ void x_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long x_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double x_ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long x_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Block 0 of a sharded launch (128 threads).  Same protocol as proto_allreduce_p2p_kernel (allreduce.cu): raise this step's
+// sequence number in every peer's flag row, wait for theirs, add the W peer slots in rank order (bit-identical sums on every
+// rank) -- then re-derive valid_class / slot_active / inv_scale from the GLOBAL counts (replan_global_kernel, scan_plan.cu)
+// and publish plan->reserved0 = 1 for the query CTAs of this launch.
+struct XchgArgs {                                             // passed BY VALUE to the out-of-line exchange block
+    const unsigned long long* xchg_peers;
+    double* xchg_out;
+    unsigned long long xchg_seq;
+    int64_t xchg_slot;
+    arco_plan* plan;
+    int32_t xchg_rank, xchg_world, C, D, Q;
+};
+__device__ __noinline__ void exchange_block(const XchgArgs p) {
+    const int tid = threadIdx.x;
+    const int world = p.xchg_world, rank = p.xchg_rank;
+    const int n = p.C * (p.D + 1);
+    const int64_t slot = (int64_t)(p.xchg_seq & 1ull) * p.xchg_slot;
+    const int64_t flag_off = 2 * p.xchg_slot;
+    arco_plan* pl = p.plan;
+    __threadfence_system();                                   // the prototype kernel's sums (previous launch) before the flag
+    if (tid < world && tid != rank)
+        x_st_release_sys(reinterpret_cast<unsigned long long*>(p.xchg_peers[tid]) + flag_off + rank, p.xchg_seq);
+    if (tid < world && tid != rank) {
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(p.xchg_peers[rank]) + flag_off + tid;
+        const unsigned long long t0 = x_globaltimer_ns();     // a peer that never arrives must fail loudly: 10 s of wall time
+        unsigned int polls = 0;
+        while (x_ld_acquire_sys(mine) < p.xchg_seq) {
+            if ((++polls & 1023u) == 0 && x_globaltimer_ns() - t0 > 10000000000ull) {
+                atomicOr(&pl->status, (uint32_t)ARCO_ST_EXCHANGE_TIMEOUT);
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    // 4 elements x up to 8 peers of independent NVLink loads in flight per thread, added in rank order afterwards
+    for (int i0 = tid * 4; i0 < n; i0 += 128 * 4) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r0 = 0; r0 < world; r0 += 8) {
+            double v[8][4];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    v[r][e] = (r0 + r < world && i0 + e < n)
+                                  ? x_ld_relaxed_sys_f64(reinterpret_cast<const double*>(p.xchg_peers[r0 + r]) + slot + i0 + e) : 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] += v[r][e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (i0 + e < n) p.xchg_out[i0 + e] = acc[e];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const volatile double* sums = p.xchg_out;
+        const int C = p.C, D = p.D;
+        int nv = 0;
+        uint32_t changed = 0;
+        for (int k = 0; k < C; ++k)
+            if (sums[(int64_t)k * (D + 1) + D] > 0.0) { changed |= pl->valid_class[nv] != k; pl->valid_class[nv++] = k; }
+        for (int k = nv; k < ARCO_MAX_CLASSES; ++k) { changed |= pl->valid_class[k] != -1; pl->valid_class[k] = -1; }
+        pl->n_valid = nv;
+        for (int pos = 0; pos < ARCO_MAX_CLASSES; ++pos) {
+            int act = 0;
+            if (nv > 1 && pos < nv) {
+                const int bank_cls = pl->valid_class[pos];
+                act = (pl->n_anchor[pos] > 0 && pl->bank_len[bank_cls] > 0) ? 1 : 0;
+            }
+            changed |= pl->slot_active[pos] != act;
+            pl->slot_active[pos] = act;
+        }
+        pl->inv_scale = nv > 1 ? 1.0f / ((float)p.Q * (float)nv) : 0.f;
+        pl->replanned = changed;
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&pl->reserved0), "r"(1u) : "memory");
+    }
+}
+
+// Query CTAs of a sharded launch: wait (after the negatives pass) until block 0 has published the global sums and plan.
+// Returns true when the plan changed under the speculation: this launch then emits nothing and the gated redo launch that
+// follows it (after arco_sample_if_replanned) does the whole job on the global plan.  All 128 threads.
+__device__ __forceinline__ bool exchange_wait(const InfoParams& p) {
+    if (p.xchg_peers == nullptr) return false;
+    if (threadIdx.x == 0) {
+        uint32_t v = 0;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&p.plan->reserved0) : "memory");
+            if (v) break;
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    return *reinterpret_cast<volatile uint32_t*>(&p.plan->replanned) != 0;
 }
 
 // d loss / d anchor and the per-query loss from the merged softmax statistics.  gsum(d) = sum_k e_k k_hat_k[d] over the
@@ -251,12 +395,12 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
     const int tid = threadIdx.x;
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&p.plan->loss_done, 1u) == gridDim.x - 1;
+    if (tid == 0) s_last = atomicAdd(&p.plan->loss_done, 1u) == (uint32_t)p.nq - 1u;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     const volatile float* lp = p.loss_parts;
-    const int total = gridDim.x;
+    const int total = p.nq;
     float acc = 0.f;
     const int per = (total + 127) / 128;
     for (int i = tid * per; i < min(total, (tid + 1) * per); ++i) acc += lp[i];
@@ -285,6 +429,30 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
     if (p.step_ctr && tid == 0) *p.step_ctr = seq;
 }
 
+// Common entry of the three InfoNCE kernels.  Declares bid, j, q, pl, bank_cls0, active, redo.
+//  * a gated launch (the redo after a changed plan) returns at once unless plan->replanned;
+//  * block 0 of a sharded launch is the exchange block;
+//  * `active` also requires a non-empty bank: on a batch shard the plan may be re-derived by block 0 WHILE the query CTAs read
+//    it; valid classes are only ever added (global counts >= local counts), so valid_class[j] stays a class id, but its bank
+//    may be empty -- such a launch is discarded (replanned != 0) and must merely stay in bounds.
+#define INFO_ENTRY(p)                                                                                                  \
+    if ((p).gate_replanned && *reinterpret_cast<volatile uint32_t*>(&(p).plan->replanned) == 0u) return;                \
+    const int xc_ = (p).xchg_peers ? 1 : 0;                                                                            \
+    if (xc_ && blockIdx.x == 0) {                                                                                      \
+        XchgArgs xa_;                                                                                                   \
+        xa_.xchg_peers = (p).xchg_peers; xa_.xchg_out = (p).xchg_out; xa_.xchg_seq = (p).xchg_seq;                      \
+        xa_.xchg_slot = (p).xchg_slot; xa_.plan = (p).plan; xa_.xchg_rank = (p).xchg_rank;                              \
+        xa_.xchg_world = (p).xchg_world; xa_.C = (p).C; xa_.D = (p).D; xa_.Q = (p).Q;                                   \
+        exchange_block(xa_);                                                                                            \
+        return;                                                                                                        \
+    }                                                                                                                  \
+    const int bid = (int)blockIdx.x - xc_;                                                                             \
+    const int j = bid / (p).Q, q = bid % (p).Q;                   /* LOOP-2 position (loss_helper_3d.py:435), query */  \
+    arco_plan* pl = (p).plan;                                                                                          \
+    const int bank_cls0 = pl->valid_class[j];                                                                          \
+    const bool active = pl->slot_active[j] != 0 && bank_cls0 >= 0 && pl->bank_len[bank_cls0] > 0;                      \
+    bool redo = false
+
 // MAXIT: 16-byte chunks per lane in pass 2 (ceil(chunks per row / 32)); BF16BANK: the ring stores bf16 rows
 template <int MAXIT, bool BF16BANK>
 __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
@@ -301,29 +469,21 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
     __shared__ int s_pix;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bid = blockIdx.x;
-    const int j = bid / p.Q;                                      // LOOP-2 position (loss_helper_3d.py:435)
-    const int q = bid % p.Q;
-    arco_plan* pl = p.plan;
-    const bool active = pl->slot_active[j] != 0;
-
+    INFO_ENTRY(p);                                                // gated redo / exchange block / bid, j, q, pl, active, redo
     if (active) {
-        const int bank_cls = pl->valid_class[j];                  // trap 1: bank by CLASS ID ...
+        const int bank_cls = bank_cls0;                           // trap 1: bank by CLASS ID ...
         const int blen = pl->bank_len[bank_cls];
         const int bhead = pl->bank_head[bank_cls];
         const int cap = p.cap[bank_cls];
         const uint32_t row_bytes = (uint32_t)D * (BF16BANK ? 2u : 4u);
         const unsigned char* bank = reinterpret_cast<const unsigned char*>(p.bank_rows) + p.row_off[bank_cls] * (int64_t)row_bytes;
-        const float inv_scale = pl->inv_scale;
 
         if (tid < 4) mbar_init(&bars[tid], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
-        const AnchorInfo ai = info_prologue(p, j, q, bank_cls, a_hat, k0hat, s_red, &s_pix);
-        const int pix = ai.pix;
-        const float na = ai.na, cos0 = ai.cos0;
+        AnchorInfo ai = info_anchor(p, j, q, a_hat, s_red, &s_pix);
+        if (!p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);   // single GPU: under the first gathers
         const float inv_temp = 1.f / p.temp;
-        const float z0 = cos0 * inv_temp;
 
         // ---- this warp's share of the negatives ----
         const int KC = p.KC, RS16 = p.RS16;
@@ -342,7 +502,7 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
             __syncwarp();
             if (lane < nv) {
                 int r = my_idx[chunk * KC + lane];
-                if (r < 0 || r >= blen) { atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
+                if (r < 0 || r >= blen) { if (!p.xchg_peers) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
                 int phys = bhead + r;
                 if (phys >= cap) phys -= cap;
                 bulk_g2s(wstage + (size_t)lane * RS16, bank + (int64_t)phys * row_bytes, row_bytes, &bars[warp]);
@@ -444,28 +604,37 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         if (lane == 0) { s_stats[warp][0] = m_run; s_stats[warp][1] = S_run; s_stats[warp][2] = S2_run; }
         __syncthreads();
 
-        // ---- merge the 4 partial softmaxes with the positive key, emit loss and d loss / d anchor ----
-        float m_all = z0;
+        redo = exchange_wait(p);                                  // batch shard: the global sums / plan are in place now
+        if (!redo) {
+            // ---- the positive key, then merge the 4 partial softmaxes with it, emit loss and d loss / d anchor ----
+            const float inv_scale = pl->inv_scale;
+            if (p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
+            const float cos0 = ai.cos0;
+            const float z0 = cos0 * inv_temp;
+            float m_all = z0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) m_all = fmaxf(m_all, s_stats[w][0]);
-        float f[4];
-        const float e0 = __expf(z0 - m_all);
-        float S_all = e0, S2_all = e0 * cos0;
+            for (int w = 0; w < 4; ++w) m_all = fmaxf(m_all, s_stats[w][0]);
+            float f[4];
+            const float e0 = __expf(z0 - m_all);
+            float S_all = e0, S2_all = e0 * cos0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            f[w] = s_stats[w][1] > 0.f ? __expf(s_stats[w][0] - m_all) : 0.f;
-            S_all += s_stats[w][1] * f[w];
-            S2_all += s_stats[w][2] * f[w];
+            for (int w = 0; w < 4; ++w) {
+                f[w] = s_stats[w][1] > 0.f ? __expf(s_stats[w][0] - m_all) : 0.f;
+                S_all += s_stats[w][1] * f[w];
+                S2_all += s_stats[w][2] * f[w];
+            }
+            info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, S_all, S2_all, a_hat, k0hat, [&](int d) {
+                return gbuf[d] * f[0] + gbuf[D + d] * f[1] + gbuf[2 * D + d] * f[2] + gbuf[3 * D + d] * f[3];
+            });
         }
-        info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, S_all, S2_all, a_hat, k0hat, [&](int d) {
-            return gbuf[d] * f[0] + gbuf[D + d] * f[1] + gbuf[2 * D + d] * f[2] + gbuf[3 * D + d] * f[3];
-        });
-    } else if (tid == 0) {
-        p.loss_parts[bid] = 0.f;
-        p.anchor_pix[bid] = -1;
+    } else {
+        redo = exchange_wait(p);
+        if (!redo && tid == 0) {
+            p.loss_parts[bid] = 0.f;
+            p.anchor_pix[bid] = -1;
+        }
     }
-
-    info_fold_loss(p);
+    if (!redo) info_fold_loss(p);
 }
 
 
@@ -492,17 +661,12 @@ __global__ void __launch_bounds__(128, 3) infonce_lane_kernel(InfoParams p) {
     __shared__ int s_pix;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bid = blockIdx.x;
-    const int j = bid / p.Q, q = bid % p.Q;
-    arco_plan* pl = p.plan;
-    const bool active = pl->slot_active[j] != 0;
-
+    INFO_ENTRY(p);
     if (active) {
-        const int bank_cls = pl->valid_class[j];                  // trap 1: bank by CLASS ID
+        const int bank_cls = bank_cls0;                           // trap 1: bank by CLASS ID
         const int blen = pl->bank_len[bank_cls], bhead = pl->bank_head[bank_cls], cap = p.cap[bank_cls];
         constexpr uint32_t row_bytes = NCH * 16;
         const unsigned char* bank = reinterpret_cast<const unsigned char*>(p.bank_rows) + p.row_off[bank_cls] * (int64_t)row_bytes;
-        const float inv_scale = pl->inv_scale;
         {
             const int32_t* src = p.idx_n + ((int64_t)j * p.Q + q) * p.N;
             bool bad = false;
@@ -513,11 +677,11 @@ __global__ void __launch_bounds__(128, 3) infonce_lane_kernel(InfoParams p) {
                 if (phys >= cap) phys -= cap;
                 s_idx[n] = phys;
             }
-            if (bad) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE);
+            if (bad && !p.xchg_peers) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE);   // (a speculative pass may see a plan in flux)
         }
-        const AnchorInfo ai = info_prologue(p, j, q, bank_cls, a_hat, k0hat, s_red, &s_pix);   // (contains __syncthreads)
+        AnchorInfo ai = info_anchor(p, j, q, a_hat, s_red, &s_pix);   // (contains __syncthreads)
+        if (!p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
         const float inv_temp = 1.f / p.temp;
-        const float z0 = ai.cos0 * inv_temp;
 
         const int npw = (p.N + 3) / 4;
         const int n_begin = min(p.N, warp * npw), n_end = min(p.N, n_begin + npw);
@@ -570,17 +734,26 @@ __global__ void __launch_bounds__(128, 3) infonce_lane_kernel(InfoParams p) {
         S2 = warp_sum(S2);
         if (lane == 0) { s_stats[warp][0] = S; s_stats[warp][1] = S2; }
         __syncthreads();
-        const float m_all = inv_temp;                             // offset of every exponential: z <= 1/temp
-        const float e0 = __expf(z0 - m_all);
-        const float S_all = e0 + s_stats[0][0] + s_stats[1][0] + s_stats[2][0] + s_stats[3][0];
-        const float S2_all = e0 * ai.cos0 + s_stats[0][1] + s_stats[1][1] + s_stats[2][1] + s_stats[3][1];
-        info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, S_all, S2_all, a_hat, k0hat,
-                      [&](int d) { return gbuf[d] + gbuf[DD + d] + gbuf[2 * DD + d] + gbuf[3 * DD + d]; });
-    } else if (tid == 0) {
-        p.loss_parts[bid] = 0.f;
-        p.anchor_pix[bid] = -1;
+        redo = exchange_wait(p);
+        if (!redo) {
+            const float inv_scale = pl->inv_scale;
+            if (p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
+            const float z0 = ai.cos0 * inv_temp;
+            const float m_all = inv_temp;                         // offset of every exponential: z <= 1/temp
+            const float e0 = __expf(z0 - m_all);
+            const float S_all = e0 + s_stats[0][0] + s_stats[1][0] + s_stats[2][0] + s_stats[3][0];
+            const float S2_all = e0 * ai.cos0 + s_stats[0][1] + s_stats[1][1] + s_stats[2][1] + s_stats[3][1];
+            info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, S_all, S2_all, a_hat, k0hat,
+                          [&](int d) { return gbuf[d] + gbuf[DD + d] + gbuf[2 * DD + d] + gbuf[3 * DD + d]; });
+        }
+    } else {
+        redo = exchange_wait(p);
+        if (!redo && tid == 0) {
+            p.loss_parts[bid] = 0.f;
+            p.anchor_pix[bid] = -1;
+        }
     }
-    info_fold_loss(p);
+    if (!redo) info_fold_loss(p);
 }
 
 // ======================================================================================================================
@@ -643,19 +816,14 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int bid = blockIdx.x;
-    const int j = bid / p.Q, q = bid % p.Q;
-    arco_plan* pl = p.plan;
-    const bool active = pl->slot_active[j] != 0;
-
+    INFO_ENTRY(p);
     if (active) {
-        const int bank_cls = pl->valid_class[j];
+        const int bank_cls = bank_cls0;
         const int blen = pl->bank_len[bank_cls];
         const int bhead = pl->bank_head[bank_cls];
         const int cap = p.cap[bank_cls];
         const uint32_t row_bytes = (uint32_t)D * 2u;
         const unsigned char* bank = reinterpret_cast<const unsigned char*>(p.bank_rows) + p.row_off[bank_cls] * (int64_t)row_bytes;
-        const float inv_scale = pl->inv_scale;
         const int stage_u4 = MMA_KEYS * RS16;
 
         if (tid < NSTG) mbar_init(&bars[tid], 1);
@@ -678,7 +846,7 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
             if (lane == 0) mbar_expect_tx(&bars[s], (uint32_t)nv * row_bytes);
             __syncwarp();
             if (lane < nv) {
-                if (r < 0 || r >= blen) { atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
+                if (r < 0 || r >= blen) { if (!p.xchg_peers) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
                 int phys = bhead + r;
                 if (phys >= cap) phys -= cap;
                 bulk_g2s(stage + (size_t)s * stage_u4 + (size_t)lane * RS16, bank + (int64_t)phys * row_bytes, row_bytes, &bars[s]);
@@ -689,9 +857,9 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
             for (int c = 0; c < NSTG && c < nch; ++c) issue(c, load_idx(c));
         int r_next = load_idx(NSTG);                              // every warp: any of them may issue the next chunk
 
-        const AnchorInfo ai = info_prologue(p, j, q, bank_cls, a_hat, k0hat, s_red, &s_pix);
+        AnchorInfo ai = info_anchor(p, j, q, a_hat, s_red, &s_pix);
+        if (!p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
         const float inv_temp = 1.f / p.temp;
-        const float z0 = ai.cos0 * inv_temp;
         // A-fragment rows 8..10 of every k-step: lane (g < 3, t) holds terms g of a_hat[16ks + 2t, +1] and [.. + 8, + 9]
         // (slots 12..15 of a k-step are zero: the rows 11..15 of the A operand, read by the lanes with g >= 3)
         for (int i = tid; i < KS * 16; i += 128) {
@@ -818,15 +986,24 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
             if (lane == 0) { s_red[0][0] = S; s_red[0][1] = S2; }
         }
         __syncthreads();
-        const float m_all = inv_temp;                             // offset of every exponential: z <= 1/temp
-        const float e0 = __expf(z0 - m_all);
-        info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, e0 + s_red[0][0], e0 * ai.cos0 + s_red[0][1], a_hat, k0hat,
-                      [&](int d) { return gbuf[d]; });
-    } else if (tid == 0) {
-        p.loss_parts[bid] = 0.f;
-        p.anchor_pix[bid] = -1;
+        redo = exchange_wait(p);
+        if (!redo) {
+            const float inv_scale = pl->inv_scale;
+            if (p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
+            const float z0 = ai.cos0 * inv_temp;
+            const float m_all = inv_temp;                         // offset of every exponential: z <= 1/temp
+            const float e0 = __expf(z0 - m_all);
+            info_epilogue(p, bid, j, q, ai, inv_scale, e0, m_all, e0 + s_red[0][0], e0 * ai.cos0 + s_red[0][1], a_hat, k0hat,
+                          [&](int d) { return gbuf[d]; });
+        }
+    } else {
+        redo = exchange_wait(p);
+        if (!redo && tid == 0) {
+            p.loss_parts[bid] = 0.f;
+            p.anchor_pix[bid] = -1;
+        }
     }
-    info_fold_loss(p);
+    if (!redo) info_fold_loss(p);
 }
 
 
@@ -867,7 +1044,8 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
                         const int32_t* idx_anchor, const int32_t* idx_neg, float temp, float* loss,
                         float* grad_anchor, int32_t* anchor_pix, float* logits, const float* momentum,
                         const int32_t* momentum_on, float ema_decay, float ema_keep, float* proto_out, void* workspace, void* stream,
-                        const float* anchor_rows = nullptr, const int32_t* anchor_pix_in = nullptr) {
+                        const float* anchor_rows = nullptr, const int32_t* anchor_pix_in = nullptr,
+                        const arco_exchange* xchg = nullptr, int gate_replanned = 0) {
     ARCO_REQUIRE(dims && (rep || anchor_rows) && bank && proto_sums && idx_anchor && idx_neg && loss && grad_anchor && anchor_pix &&
                      workspace, "arco_infonce: NULL argument");
     const arco_dims& d = *dims;
@@ -884,6 +1062,14 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     p.plan = (arco_plan*)(ws + L.plan);
     p.loss = loss; p.g_anchor = grad_anchor; p.anchor_pix = anchor_pix; p.logits = logits;
     p.anchor_rows = anchor_rows; p.anchor_pix_in = anchor_pix_in;
+    p.xchg_peers = nullptr; p.xchg_out = nullptr; p.xchg_seq = 0; p.xchg_slot = 0; p.xchg_rank = 0; p.xchg_world = 1;
+    p.gate_replanned = gate_replanned; p.nq = d.classes * d.queries;
+    if (xchg) {
+        ARCO_REQUIRE(xchg->peers && xchg->world >= 1 && xchg->world <= 64 && xchg->rank >= 0 && xchg->rank < xchg->world && xchg->seq > 0 &&
+                         xchg->slot_doubles >= (int64_t)d.classes * (d.feat + 1), "arco_infonce_sharded: bad exchange descriptor");
+        p.xchg_peers = (const unsigned long long*)xchg->peers; p.xchg_out = const_cast<double*>(proto_sums);
+        p.xchg_seq = xchg->seq; p.xchg_slot = xchg->slot_doubles; p.xchg_rank = xchg->rank; p.xchg_world = xchg->world;
+    }
     p.loss_parts = (float*)(ws + L.loss_parts);
     p.momentum = momentum; p.momentum_on = momentum_on; p.proto_out = proto_out; p.ema_decay = ema_decay; p.ema_keep = ema_keep;
     p.host_mirror = bank->host_mirror; p.host_queue_ptr = bank->host_queue_ptr;
@@ -918,7 +1104,7 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     if (kc >= 8) { while ((rs16 & 1) == 0) ++rs16; } else { while ((rs16 & 3) != 2) ++rs16; }
     p.KC = kc; p.RS16 = rs16;
     const size_t smem = (size_t)6 * d.feat * 4 + (size_t)4 * kc * rs16 * 16;
-    const int grid = d.classes * d.queries;
+    const int grid = d.classes * d.queries + (xchg ? 1 : 0);         // + the exchange block (block 0)
     cudaStream_t st = (cudaStream_t)stream;
 #define ARCO_INFONCE(MI, BF)                                                                                               \
     do {                                                                                                                   \
@@ -1018,4 +1204,15 @@ extern "C" int arco_infonce_rows(const arco_dims* dims, const float* anchor_rows
     ARCO_REQUIRE(anchor_rows && anchor_pix_in, "arco_infonce_rows: NULL anchor rows");
     return infonce_impl(dims, nullptr, bank, proto_sums, idx_anchor, idx_neg, temp, loss, grad_anchor, anchor_pix, logits,
                         nullptr, nullptr, 0.f, 1.f, nullptr, workspace, stream, anchor_rows, anchor_pix_in);
+}
+
+// ---- batch shards: InfoNCE with the exchange step of the path inside the launch -----------------------------
+extern "C" int arco_infonce_sharded(const arco_dims* dims, const void* rep, const arco_bank* bank, const arco_exchange* exchange,
+                                    int32_t gate_replanned, double* proto_sums, const int32_t* idx_anchor, const int32_t* idx_neg,
+                                    float temp, float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits,
+                                    const float* momentum, const int32_t* momentum_on, float ema_decay, float ema_keep,
+                                    float* proto_out, void* workspace, void* stream) {
+    ARCO_REQUIRE((exchange != nullptr) != (gate_replanned != 0), "arco_infonce_sharded: pass the exchange descriptor OR gate_replanned");
+    return infonce_impl(dims, rep, bank, proto_sums, idx_anchor, idx_neg, temp, loss, grad_anchor, anchor_pix, logits, momentum,
+                        momentum_on, ema_decay, ema_keep, proto_out, workspace, stream, nullptr, nullptr, exchange, gate_replanned);
 }

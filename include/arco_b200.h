@@ -104,7 +104,7 @@ typedef struct arco_plan {
     int32_t  bank_skip[ARCO_MAX_CLASSES];    /* leading keys dropped because n_key > capacity         */
     int32_t  bank_len[ARCO_MAX_CLASSES];     /* bank rows after this call                             */
     int32_t  bank_head[ARCO_MAX_CLASSES];    /* ring position of logical row 0 after this call        */
-    int32_t  reserved0;                      /* explicit padding (8-byte alignment of queue_ptr), written as 0 */
+    int32_t  reserved0;                      /* padding (8-byte alignment of queue_ptr); 0 from the plan, set to 1 by the exchange block of arco_infonce_sharded */
     int64_t  queue_ptr[ARCO_MAX_CLASSES];    /* reference pointer bookkeeping (:24-30)                */
     float    inv_scale;                      /* 1 / (Q * valid_seg), 0 when valid_seg <= 1            */
     uint32_t status;                         /* ARCO_ST_* bits                                        */
@@ -417,6 +417,26 @@ ARCO_API int arco_infonce_rows(const arco_dims* dims, const float* anchor_rows, 
                                const double* proto_sums, const int32_t* idx_anchor, const int32_t* idx_neg, float temp,
                                float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits, void* workspace,
                                void* stream);
+
+/* ---- batch shards: the exchange step INSIDE the InfoNCE launch ---------------------------------------------------------------
+   arco_proto_allreduce_p2p + arco_replan_global put the one exchange of the multi-GPU path between the
+   prototype pass and InfoNCE: +30..43 us per step of launch gaps, NVLink round trips and rank skew.  The negatives pass of
+   InfoNCE needs neither the prototype nor the global counts, so arco_infonce_sharded(exchange != NULL) runs it on the
+   rank-local plan while an extra block 0 trades the class sums with the peers (same protocol and summation order as
+   arco_proto_allreduce_p2p), re-derives the valid-class list and publishes both before the merge.  If the plan changed under
+   the speculation the launch emits nothing; the caller always enqueues  arco_sample_if_replanned  and a second
+   arco_infonce_sharded(exchange = NULL, gate_replanned = 1), both of which return at once unless plan->replanned. */
+typedef struct arco_exchange {
+    const uint64_t* peers;        /* device array [world]: this rank's exchange buffer as mapped for every peer              */
+    uint64_t        seq;          /* step sequence number (> 0, grows by one per step)                                         */
+    int64_t         slot_doubles; /* doubles per slot; layout [slot 0][slot 1][flags: one u64 per source rank]                 */
+    int32_t         rank, world;
+} arco_exchange;
+ARCO_API int arco_infonce_sharded(const arco_dims* dims, const void* rep, const arco_bank* bank, const arco_exchange* exchange,
+                                  int32_t gate_replanned, double* proto_sums, const int32_t* idx_anchor, const int32_t* idx_neg,
+                                  float temp, float* loss, float* grad_anchor, int32_t* anchor_pix, float* logits,
+                                  const float* momentum, const int32_t* momentum_on, float ema_decay, float ema_keep,
+                                  float* proto_out, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }
