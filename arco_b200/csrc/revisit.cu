@@ -13,16 +13,21 @@
 // The pass is a [2bs x L] x [L x K] contraction with M = 24, N = 36 -- 864 FMAs per 60 loaded values, i.e. FMA- and
 // HBM-time are about equal (0.8 vs 0.95 ms at the reference shape), so it runs on the CUDA cores in exact fp32 (a
 // single-pass TF32 MMA would truncate both operands: 1e-3 relative on a dot, the loss needs 1e-5): a warp owns a
-// 6-row x 9-column tile of the output, its lanes stride over L (conflict-free shared-memory reads, 3.6 FMAs per read),
-// chunks of L are double-buffered in shared memory with cp.async, CTAs are persistent and the 54 accumulators per lane
+// 12-row x 9-column tile of the output, its lanes stride over L (conflict-free shared-memory reads, 10 FMAs per 8-byte read),
+// chunks of L are staged in a 3-4 deep shared-memory ring by whole-row TMA bulk copies (mbarrier full / empty), CTAs are persistent and the 108 accumulators per lane
 // meet in shuffles once, at the end.  Per-CTA partials are folded in fp64 in a fixed order (deterministic).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "arco_common.cuh"
+#include "tc_common.cuh"
 
 namespace arco {
 
-constexpr int RV_TM = 6, RV_TN = 9;          // output tile of a warp: rows (reps) x columns (pool rows)
+constexpr int RV_TM = 12, RV_TN = 9;          // output tile of a warp: rows (reps) x columns (pool rows)
 constexpr int RV_TC = 256;                   // elements of L per staged chunk
-constexpr int RV_MAX_WARPS = 16;             // 512 threads: 128 registers per thread for the 54 + 6 accumulators
+constexpr int RV_MAX_ST = 4;                 // stages of the chunk ring
+constexpr int RV_MAX_WARPS = 8;               // 256 threads x 255 registers: 108 + 12 accumulators and 42 operands per lane
 
 struct RevisitParams {
     const void* rep_s;       // [bs][L]
@@ -30,14 +35,11 @@ struct RevisitParams {
     const float* pool;       // [K][L]
     float* partials;         // [grid][MP*NP + MP]
     int64_t L;
-    int32_t bs, K, MT, NT_, MP, NP;   // tiles and padded sizes: MP = MT*6 >= 2bs, NP = NT_*9 >= K
+    int32_t bs, K, MT, NT_, MP, NP, NST;
+    int32_t probe;           // tuning probe (ARCO_RV_PROBE): 1 = stage only (no math), 2 = math only (no copies)   // tiles and padded sizes: MP = MT*6 >= 2bs, NP = NT_*9 >= K
     int64_t nchunks;
 };
 
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
-}
 
 template <typename T> __device__ __forceinline__ float rv_load(const T* p);
 template <> __device__ __forceinline__ float rv_load<float>(const float* p) { return *p; }
@@ -55,48 +57,64 @@ template <> __device__ __forceinline__ void rv_load2<__nv_bfloat16>(const __nv_b
     x = __uint_as_float(v << 16); y = __uint_as_float(v & 0xffff0000u);
 }
 
+// Staging history (B200, bs 12, K 36, L = 32.5 M; ARCO_RV_PROBE=1 / 2 time the staging / the math alone):
+//   v1  every thread issues 16-byte cp.async copies with per-copy row / column arithmetic, two block-wide barriers per
+//       256-element chunk, 16 warps x (6 x 9) tiles:                                    2.53 ms bf16 / 2.77 ms fp32
+//   v2  one 1-D bulk copy per row, mbarrier ring, 8 warps x (12 x 9) tiles:             2.36 / 2.48  (a warp's lane 0 issued ~8
+//       UBLKCP per chunk, serialised; 64-bit div/mod per chunk; a lone producer warp issuing all 60 was slower still: 2.9)
+//   v3  incremental stage / phase bookkeeping, straight-line math for a whole chunk:    2.17 / 2.11
+//   v4  a chunk = THREE 2-D TMA boxes (student rows, teacher rows, pool rows x 256 elements, no swizzle -> the row-major
+//       layout the math loop reads; the tail of L arrives zero-filled), issued by one lane:   1.58 / 1.55 ms
+//       = staging alone 0.95 / 1.17 ms (6.5 / 6.6 TB/s), math alone 1.46 / 1.41 ms (the FMA pipe at ~60 %).
+// Stages form a ring of NST (3-4), handed back through an `empty` mbarrier every warp arrives on; no __syncthreads in the loop.
 template <typename T>
-__global__ void __launch_bounds__(512, 1) revisit_dots_kernel(RevisitParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(256, 1) revisit_dots_kernel(const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_t,
+                                                              const __grid_constant__ CUtensorMap map_p, RevisitParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[RV_MAX_ST], empty_bar[RV_MAX_ST];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthr = blockDim.x;
-    const int MP = p.MP, NP = p.NP;
+    const int nthr = blockDim.x, nwarps = nthr >> 5;
+    const int MP = p.MP, NP = p.NP, NST = p.NST;
     const size_t rep_bytes = (size_t)MP * RV_TC * sizeof(T), pool_bytes = (size_t)NP * RV_TC * 4;
     const size_t buf_bytes = rep_bytes + pool_bytes;
     auto rep_buf = [&](int b) { return reinterpret_cast<T*>(smem_raw + (size_t)b * buf_bytes); };
     auto pool_buf = [&](int b) { return reinterpret_cast<float*>(smem_raw + (size_t)b * buf_bytes + rep_bytes); };
 
-    // padding rows (>= 2bs, >= K) are zero and never reloaded
-    for (size_t i = tid; i < 2 * buf_bytes / 16; i += nthr) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // padding rows (>= 2bs, >= K) are zero and never loaded
+    for (size_t i = tid; i < (size_t)NST * buf_bytes / 16; i += nthr) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], (uint32_t)nwarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill (generic proxy) before any bulk copy lands
     __syncthreads();
 
-    constexpr int PER16 = 16 / (int)sizeof(T);
-    const int rep_pieces = RV_TC / PER16;                    // 16-byte pieces per rep row per chunk
-    const int pool_pieces = RV_TC / 4;
-    auto issue = [&](int64_t ch, int b) {
-        const int64_t c0 = ch * RV_TC;
-        const int n_rep = 2 * p.bs * rep_pieces, n_pool = p.K * pool_pieces;
-        for (int i = tid; i < n_rep + n_pool; i += nthr) {
-            if (i < n_rep) {
-                const int row = i / rep_pieces, pc = i - row * rep_pieces;
-                const int64_t c = c0 + (int64_t)pc * PER16;
-                const T* src = reinterpret_cast<const T*>(row < p.bs ? p.rep_s : p.rep_t) + (int64_t)(row < p.bs ? row : row - p.bs) * p.L + c;
-                int64_t left = (p.L - c) * (int64_t)sizeof(T);
-                const int nb = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
-                cp_async16(rep_buf(b) + (size_t)row * RV_TC + pc * PER16, nb > 0 ? (const void*)src : (const void*)p.pool, nb);
-            } else {
-                const int k = i - n_rep;
-                const int row = k / pool_pieces, pc = k - row * pool_pieces;
-                const int64_t c = c0 + (int64_t)pc * 4;
-                const float* src = p.pool + (int64_t)row * p.L + c;
-                int64_t left = (p.L - c) * 4;
-                const int nb = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
-                cp_async16(pool_buf(b) + (size_t)row * RV_TC + pc * 4, nb > 0 ? (const void*)src : (const void*)p.pool, nb);
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t n_my = first < p.nchunks ? (p.nchunks - first + stride - 1) / stride : 0;
+    // The next chunk to issue goes to stage `is` (phase bit `iph`).  A chunk is THREE 2-D TMA boxes (student rows, teacher rows,
+    // pool rows x 256 elements, no swizzle = the row-major stage layout the math loop reads), issued by lane 0 of warp 0; the
+    // tail of L is zero-filled by the TMA unit.  (One bulk copy per row, the previous version, cost every warp ~8 serialised
+    // UBLKCP issues per chunk.)  Stage and phase are carried incrementally -- a chunk is only four trips of the math loop, so
+    // bookkeeping instructions count.
+    int is = 0;
+    uint32_t iph = 1;                                             // parity to wait for on `empty`: passes at once on first use
+    int64_t ic = first;                                           // next chunk to issue
+    const uint32_t tx_bytes = (uint32_t)(2 * p.bs) * RV_TC * (uint32_t)sizeof(T) + (uint32_t)p.K * RV_TC * 4u;
+    auto issue = [&]() {
+        if (warp == 0 && p.probe != 2) {
+            bar_wait(&empty_bar[is], iph);                        // every warp has left the chunk that used this stage
+            if (lane == 0) {
+                const int c0 = (int)(ic * RV_TC);
+                bar_expect_tx(&full_bar[is], tx_bytes);
+                tma_load_2d(rep_buf(is), &map_s, &full_bar[is], c0, 0);
+                tma_load_2d(rep_buf(is) + (size_t)p.bs * RV_TC, &map_t, &full_bar[is], c0, 0);
+                tma_load_2d(pool_buf(is), &map_p, &full_bar[is], c0, 0);
             }
+            __syncwarp();
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        ic += stride;
+        if (++is == NST) { is = 0; iph ^= 1u; }
     };
-
     const int mt = warp / p.NT_, nt = warp % p.NT_;
     const bool has_tile = warp < p.MT * p.NT_;
     float acc[RV_TM][RV_TN], sq[RV_TM];
@@ -107,25 +125,19 @@ __global__ void __launch_bounds__(512, 1) revisit_dots_kernel(RevisitParams p) {
         for (int k = 0; k < RV_TN; ++k) acc[r][k] = 0.f;
     }
 
-    int64_t ch = blockIdx.x;
+    const int n_chunks = (int)n_my;
+    int n_issued = 0;
+    for (; n_issued < NST - 1 && n_issued < n_chunks; ++n_issued) issue();
     int b = 0;
-    if (ch < p.nchunks) issue(ch, 0);
-    for (; ch < p.nchunks; ch += gridDim.x, b ^= 1) {
-        const int64_t nxt = ch + gridDim.x;
-        if (nxt < p.nchunks) {
-            issue(nxt, b ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        if (has_tile) {
+    uint32_t bph = 0;
+    for (int i = 0; i < n_chunks; ++i) {
+        if (n_issued < n_chunks) { issue(); ++n_issued; }
+        if (p.probe != 2) bar_wait(&full_bar[b], bph);
+        if (has_tile && p.probe != 1) {
             const T* ar = rep_buf(b) + (size_t)(mt * RV_TM) * RV_TC;
             const float* br = pool_buf(b) + (size_t)(nt * RV_TN) * RV_TC;
-            // a lane takes PAIRS of consecutive elements: one 8-byte (fp32) / 4-byte (bf16) shared load feeds two FMAs per
-            // output, 7.2 FMAs per load instruction instead of 3.6 (the loop is issue- and shared-memory-bound)
-#pragma unroll 2
-            for (int c = 2 * lane; c < RV_TC; c += 64) {
+            // a lane takes PAIRS of consecutive elements: one 8-byte (fp32) / 4-byte (bf16) shared load feeds two FMAs per output
+            auto body = [&](int c) {
                 float a0[RV_TM], a1[RV_TM], b0[RV_TN], b1[RV_TN];
 #pragma unroll
                 for (int r = 0; r < RV_TM; ++r) rv_load2<T>(ar + (size_t)r * RV_TC + c, a0[r], a1[r]);
@@ -137,15 +149,26 @@ __global__ void __launch_bounds__(512, 1) revisit_dots_kernel(RevisitParams p) {
 #pragma unroll
                 for (int r = 0; r < RV_TM; ++r) {
 #pragma unroll
-                    for (int k = 0; k < RV_TN; ++k) { acc[r][k] += a0[r] * b0[k]; acc[r][k] += a1[r] * b1[k]; }
+                    for (int k = 0; k < RV_TN; ++k) acc[r][k] = fmaf(a0[r], b0[k], acc[r][k]);
+                }
+#pragma unroll
+                for (int r = 0; r < RV_TM; ++r) {
+#pragma unroll
+                    for (int k = 0; k < RV_TN; ++k) acc[r][k] = fmaf(a1[r], b1[k], acc[r][k]);
                 }
                 if (nt == 0) {
 #pragma unroll
-                    for (int r = 0; r < RV_TM; ++r) { sq[r] += a0[r] * a0[r]; sq[r] += a1[r] * a1[r]; }
+                    for (int r = 0; r < RV_TM; ++r) sq[r] = fmaf(a0[r], a0[r], sq[r]);
+#pragma unroll
+                    for (int r = 0; r < RV_TM; ++r) sq[r] = fmaf(a1[r], a1[r], sq[r]);
                 }
-            }
+            };
+#pragma unroll
+            for (int it = 0; it < RV_TC / 64; ++it) body(2 * lane + 64 * it);   // straight-line: the tail of L arrives as zeros
         }
-        __syncthreads();                                     // buffer b may be refilled by the next iteration's issue
+        __syncwarp();
+        if (lane == 0) bar_arrive(&empty_bar[b]);                 // this warp is done reading stage b
+        if (++b == NST) { b = 0; bph ^= 1u; }
     }
     if (has_tile) {
         float* out = p.partials + (size_t)blockIdx.x * (MP * NP + MP);
@@ -267,28 +290,54 @@ extern "C" int arco_revisit_loss(const void* rep_u, const void* rep_u_teacher, c
                                  int64_t length, int32_t rep_dtype, int32_t topk, float* loss, int32_t* nn_index, float* stats,
                                  void* scratch, void* stream) {
     ARCO_REQUIRE(rep_u && rep_u_teacher && pool && loss && nn_index && stats && scratch, "arco_revisit_loss: NULL argument");
-    ARCO_REQUIRE(bs >= 1 && bs <= 64 && pool_rows >= 1 && topk >= 1 && topk <= pool_rows && length > 0, "arco_revisit_loss: bad sizes");
+    ARCO_REQUIRE(bs >= 1 && bs <= 64 && pool_rows >= 1 && pool_rows <= 256 && topk >= 1 && topk <= pool_rows && length > 0, "arco_revisit_loss: bad sizes");
     const int esz = rep_dtype == ARCO_BF16 ? 2 : 4;
     ARCO_REQUIRE((length * esz) % 16 == 0 && (length * 4) % 16 == 0, "arco_revisit_loss: D*H*W must make 16-byte aligned rows");
     ARCO_REQUIRE((((uintptr_t)rep_u | (uintptr_t)rep_u_teacher | (uintptr_t)pool) & 15) == 0, "arco_revisit_loss: tensors must be 16-byte aligned");
     int MT, NT_;
     const int warps = arco::revisit_geometry(bs, pool_rows, &MT, &NT_);
-    ARCO_REQUIRE(warps <= arco::RV_MAX_WARPS, "arco_revisit_loss: ceil(2*bs/6) * ceil(K/9) must be <= 16 (the trainers: bs 12, K 36)");
+    ARCO_REQUIRE(warps <= arco::RV_MAX_WARPS, "arco_revisit_loss: ceil(2*bs/12) * ceil(K/9) must be <= 8 (the trainers: bs 12, K 36)");
     arco::RevisitParams p;
     p.rep_s = rep_u; p.rep_t = rep_u_teacher; p.pool = pool; p.partials = (float*)scratch;
     p.L = length; p.bs = bs; p.K = pool_rows; p.MT = MT; p.NT_ = NT_; p.MP = MT * arco::RV_TM; p.NP = NT_ * arco::RV_TN;
     p.nchunks = (length + arco::RV_TC - 1) / arco::RV_TC;
+    { const char* e = getenv("ARCO_RV_PROBE"); p.probe = e ? atoi(e) : 0; }
     int grid = arco::sm_count();
     if ((int64_t)grid > p.nchunks) grid = (int)p.nchunks;
-    const int threads = ((warps + 3) / 4) * 4 * 32;
-    const size_t smem = 2 * ((size_t)p.MP * arco::RV_TC * esz + (size_t)p.NP * arco::RV_TC * 4);
+    const int threads = warps * 32;
+    const size_t stage = (size_t)p.MP * arco::RV_TC * esz + (size_t)p.NP * arco::RV_TC * 4;
+    p.NST = (int)((size_t)(200 * 1024) / stage);
+    if (p.NST > arco::RV_MAX_ST) p.NST = arco::RV_MAX_ST;
+    ARCO_REQUIRE(p.NST >= 2, "arco_revisit_loss: a chunk of 2*bs + K rows does not fit two shared-memory stages");
+    const size_t smem = (size_t)p.NST * stage;
     cudaStream_t st = (cudaStream_t)stream;
+    ARCO_REQUIRE(length < (1ll << 31) - arco::RV_TC, "arco_revisit_loss: D*H*W must be below 2^31");
+    CUtensorMap map_s, map_t, map_p;
+    {
+        arco::EncodeTiledFn enc = arco::encode_fn();
+        ARCO_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+        auto make = [&](CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int e, int rows) -> int {
+            const cuuint64_t gdim[2] = {(cuuint64_t)length, (cuuint64_t)rows};
+            const cuuint64_t gstr[1] = {(cuuint64_t)length * (cuuint64_t)e};
+            const cuuint32_t box[2] = {(cuuint32_t)arco::RV_TC, (cuuint32_t)rows};
+            const cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { arco::set_error("cuTensorMapEncodeTiled (revisit) failed with CUresult %d", (int)r); return ARCO_ERR_CUDA; }
+            return ARCO_OK;
+        };
+        const CUtensorMapDataType rdt = rep_dtype == ARCO_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+        int rc;
+        if ((rc = make(&map_s, rep_u, rdt, esz, bs)) != ARCO_OK) return rc;
+        if ((rc = make(&map_t, rep_u_teacher, rdt, esz, bs)) != ARCO_OK) return rc;
+        if ((rc = make(&map_p, pool, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, pool_rows)) != ARCO_OK) return rc;
+    }
     if (rep_dtype == ARCO_BF16) {
         ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::revisit_dots_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        arco::revisit_dots_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p);
+        arco::revisit_dots_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(map_s, map_t, map_p, p);
     } else {
         ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::revisit_dots_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        arco::revisit_dots_kernel<float><<<grid, threads, smem, st>>>(p);
+        arco::revisit_dots_kernel<float><<<grid, threads, smem, st>>>(map_s, map_t, map_p, p);
     }
     ARCO_LAUNCH_CHECK();
     const int n_all = 2 * bs * pool_rows + 2 * bs;

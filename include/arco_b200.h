@@ -354,7 +354,7 @@ ARCO_API int arco_prepare_contrast(const float* pred_u, const float* pred_l_teac
    reference materialises are never written.
    loss f32[1]; nn_index int32 [bs, topk] (the top-k smallest STUDENT distances, ties: lower row first);
    stats f32 [2*bs*pool_rows dots (student rows, then teacher rows) | 2*bs squared norms] -- input of arco_revisit_enqueue.
-   Limits: ceil(2*bs/6) * ceil(pool_rows/9) <= 16 (the trainers: bs 12, K 36), 16-byte aligned rows. */
+   Limits: ceil(2*bs/12) * ceil(pool_rows/9) <= 8 (the trainers: bs 12, K 36), pool_rows <= 256, 16-byte aligned rows. */
 ARCO_API int64_t arco_revisit_scratch_bytes(int32_t bs, int32_t pool_rows);
 ARCO_API int arco_revisit_loss(const void* rep_u, const void* rep_u_teacher, const float* pool, int32_t bs, int32_t pool_rows,
                                int64_t length, int32_t rep_dtype, int32_t topk, float* loss, int32_t* nn_index, float* stats,
