@@ -171,20 +171,21 @@ __device__ __forceinline__ void anchor_select_warp(const InfoParams& p, int j, i
 // Anchor rank-select and anchor row -> a_hat (unit vector in shared memory), |a|.  Called by all 128 threads of the CTA.
 // The prototype half of the prologue (info_proto) runs AFTER the negatives pass: nothing in that pass needs the prototype,
 // and on a batch shard the global class sums arrive while it runs.
+template <bool ROWS>
 __device__ __forceinline__ AnchorInfo info_anchor(const InfoParams& p, int j, int q, float* a_hat, float (*s_red)[2], int* s_pix) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D;
     // ---- anchor rank-select: idx-th anchor candidate of class j (... anchors by POSITION j) ----
-    if (warp == 0 && p.anchor_rows == nullptr) anchor_select_warp(p, j, q, s_pix);
+    if (!ROWS && warp == 0) anchor_select_warp(p, j, q, s_pix);
     __syncthreads();
-    const int pix = p.anchor_rows ? p.anchor_pix_in[(int64_t)j * p.Q + q] : *s_pix;
+    const int pix = ROWS ? p.anchor_pix_in[(int64_t)j * p.Q + q] : *s_pix;
     const int ab = (int)(pix / p.S);
     const int64_t as = pix - (int64_t)ab * p.S;
     // ---- anchor row (D strided loads, one 32-B sector each) ----
     float n2a = 0.f;
     for (int d = tid; d < D; d += 128) {
         float v;
-        if (p.anchor_rows)
+        if (ROWS)
             v = p.anchor_rows[((int64_t)j * p.Q + q) * D + d];
         else if (p.rep_dtype == ARCO_BF16)
             v = bf16_bits_to_float(reinterpret_cast<const unsigned short*>(p.rep)[((int64_t)ab * D + d) * p.S + as]);
@@ -300,25 +301,25 @@ __device__ __noinline__ void exchange_block(const XchgArgs p) {
         }
     }
     __syncthreads();
-    // 4 elements x up to 8 peers of independent NVLink loads in flight per thread, added in rank order afterwards
-    for (int i0 = tid * 4; i0 < n; i0 += 128 * 4) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // 2 elements x up to 8 peers of independent NVLink loads in flight per thread, added in rank order afterwards.  Kept
+    // small on purpose: this function is out of line, and a kernel's register allocation covers its callees -- a wider
+    // unroll here raised EVERY InfoNCE kernel to 96 registers (5 instead of 7 CTAs per SM).
+    for (int i0 = tid * 2; i0 < n; i0 += 128 * 2) {
+        double acc0 = 0.0, acc1 = 0.0;
         for (int r0 = 0; r0 < world; r0 += 8) {
-            double v[8][4];
+            double v[8][2];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int r = 0; r < 8; ++r) {
+                const bool on = r0 + r < world;
+                const double* src = reinterpret_cast<const double*>(p.xchg_peers[on ? r0 + r : rank]) + slot + i0;
+                v[r][0] = on ? x_ld_relaxed_sys_f64(src) : 0.0;
+                v[r][1] = (on && i0 + 1 < n) ? x_ld_relaxed_sys_f64(src + 1) : 0.0;
+            }
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    v[r][e] = (r0 + r < world && i0 + e < n)
-                                  ? x_ld_relaxed_sys_f64(reinterpret_cast<const double*>(p.xchg_peers[r0 + r]) + slot + i0 + e) : 0.0;
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[e] += v[r][e];
+            for (int r = 0; r < 8; ++r) { acc0 += v[r][0]; acc1 += v[r][1]; }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (i0 + e < n) p.xchg_out[i0 + e] = acc[e];
+        p.xchg_out[i0] = acc0;
+        if (i0 + 1 < n) p.xchg_out[i0 + 1] = acc1;
     }
     __threadfence();
     __syncthreads();
@@ -351,7 +352,6 @@ __device__ __noinline__ void exchange_block(const XchgArgs p) {
 // Returns true when the plan changed under the speculation: this launch then emits nothing and the gated redo launch that
 // follows it (after arco_sample_if_replanned) does the whole job on the global plan.  All 128 threads.
 __device__ __forceinline__ bool exchange_wait(const InfoParams& p) {
-    if (p.xchg_peers == nullptr) return false;
     if (threadIdx.x == 0) {
         uint32_t v = 0;
         while (true) {
@@ -436,9 +436,11 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
 //    it; valid classes are only ever added (global counts >= local counts), so valid_class[j] stays a class id, but its bank
 //    may be empty -- such a launch is discarded (replanned != 0) and must merely stay in bounds.
 #define INFO_ENTRY(p)                                                                                                  \
-    if ((p).gate_replanned && *reinterpret_cast<volatile uint32_t*>(&(p).plan->replanned) == 0u) return;                \
-    const int xc_ = (p).xchg_peers ? 1 : 0;                                                                            \
-    if (xc_ && blockIdx.x == 0) {                                                                                      \
+    constexpr bool ROWS = MODE == 1, SHARD = MODE == 2;           /* MODE: 0 plain, 1 anchors as rows, 2 batch shard */  \
+    if (SHARD && (p).gate_replanned && *reinterpret_cast<volatile uint32_t*>(&(p).plan->replanned) == 0u) return;       \
+    const int xc_ = (SHARD && (p).xchg_peers) ? 1 : 0;                                                                 \
+    const bool SPEC = xc_ != 0;                                   /* speculative pass on the rank-local plan */         \
+    if (SHARD && xc_ && blockIdx.x == 0) {                                                                             \
         XchgArgs xa_;                                                                                                   \
         xa_.xchg_peers = (p).xchg_peers; xa_.xchg_out = (p).xchg_out; xa_.xchg_seq = (p).xchg_seq;                      \
         xa_.xchg_slot = (p).xchg_slot; xa_.plan = (p).plan; xa_.xchg_rank = (p).xchg_rank;                              \
@@ -450,11 +452,11 @@ __device__ __forceinline__ void info_fold_loss(const InfoParams& p) {
     const int j = bid / (p).Q, q = bid % (p).Q;                   /* LOOP-2 position (loss_helper_3d.py:435), query */  \
     arco_plan* pl = (p).plan;                                                                                          \
     const int bank_cls0 = pl->valid_class[j];                                                                          \
-    const bool active = pl->slot_active[j] != 0 && bank_cls0 >= 0 && pl->bank_len[bank_cls0] > 0;                      \
+    const bool active = pl->slot_active[j] != 0 && (!SHARD || (bank_cls0 >= 0 && pl->bank_len[bank_cls0] > 0));        \
     bool redo = false
 
 // MAXIT: 16-byte chunks per lane in pass 2 (ceil(chunks per row / 32)); BF16BANK: the ring stores bf16 rows
-template <int MAXIT, bool BF16BANK>
+template <int MAXIT, bool BF16BANK, int MODE>
 __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CHD = BF16BANK ? 8 : 4;                         // feature dims per 16-byte chunk of a bank row
@@ -481,8 +483,8 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         if (tid < 4) mbar_init(&bars[tid], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
-        AnchorInfo ai = info_anchor(p, j, q, a_hat, s_red, &s_pix);
-        if (!p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);   // single GPU: under the first gathers
+        AnchorInfo ai = info_anchor<ROWS>(p, j, q, a_hat, s_red, &s_pix);
+        if (!SPEC) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);   // single GPU: under the first gathers
         const float inv_temp = 1.f / p.temp;
 
         // ---- this warp's share of the negatives ----
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
             __syncwarp();
             if (lane < nv) {
                 int r = my_idx[chunk * KC + lane];
-                if (r < 0 || r >= blen) { if (!p.xchg_peers) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
+                if (r < 0 || r >= blen) { if (!SPEC) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
                 int phys = bhead + r;
                 if (phys >= cap) phys -= cap;
                 bulk_g2s(wstage + (size_t)lane * RS16, bank + (int64_t)phys * row_bytes, row_bytes, &bars[warp]);
@@ -604,11 +606,11 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
         if (lane == 0) { s_stats[warp][0] = m_run; s_stats[warp][1] = S_run; s_stats[warp][2] = S2_run; }
         __syncthreads();
 
-        redo = exchange_wait(p);                                  // batch shard: the global sums / plan are in place now
+        redo = SPEC ? exchange_wait(p) : false;                                  // batch shard: the global sums / plan are in place now
         if (!redo) {
             // ---- the positive key, then merge the 4 partial softmaxes with it, emit loss and d loss / d anchor ----
             const float inv_scale = pl->inv_scale;
-            if (p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
+            if (SPEC) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
             const float cos0 = ai.cos0;
             const float z0 = cos0 * inv_temp;
             float m_all = z0;
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
             });
         }
     } else {
-        redo = exchange_wait(p);
+        redo = SPEC ? exchange_wait(p) : false;
         if (!redo && tid == 0) {
             p.loss_parts[bid] = 0.f;
             p.anchor_pix[bid] = -1;
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(128) infonce_kernel(InfoParams p) {
 // once per warp at the end.  ~7 warp instructions per key.  cos <= 1, so every exponential is taken at the fixed offset
 // 1/temp (no running maximum; needs temp >= 0.03 like the mma.sync kernel).
 // ======================================================================================================================
-template <int NCH, bool BF16BANK>
+template <int NCH, bool BF16BANK, int MODE>
 __global__ void __launch_bounds__(128, 3) infonce_lane_kernel(InfoParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CHD = BF16BANK ? 8 : 4;                         // feature dims per 16-byte chunk
@@ -677,10 +679,10 @@ __global__ void __launch_bounds__(128, 3) infonce_lane_kernel(InfoParams p) {
                 if (phys >= cap) phys -= cap;
                 s_idx[n] = phys;
             }
-            if (bad && !p.xchg_peers) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE);   // (a speculative pass may see a plan in flux)
+            if (bad && !SPEC) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE);   // (a speculative pass may see a plan in flux)
         }
-        AnchorInfo ai = info_anchor(p, j, q, a_hat, s_red, &s_pix);   // (contains __syncthreads)
-        if (!p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
+        AnchorInfo ai = info_anchor<ROWS>(p, j, q, a_hat, s_red, &s_pix);   // (contains __syncthreads)
+        if (!SPEC) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
         const float inv_temp = 1.f / p.temp;
 
         const int npw = (p.N + 3) / 4;
@@ -734,10 +736,10 @@ __global__ void __launch_bounds__(128, 3) infonce_lane_kernel(InfoParams p) {
         S2 = warp_sum(S2);
         if (lane == 0) { s_stats[warp][0] = S; s_stats[warp][1] = S2; }
         __syncthreads();
-        redo = exchange_wait(p);
+        redo = SPEC ? exchange_wait(p) : false;
         if (!redo) {
             const float inv_scale = pl->inv_scale;
-            if (p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
+            if (SPEC) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
             const float z0 = ai.cos0 * inv_temp;
             const float m_all = inv_temp;                         // offset of every exponential: z <= 1/temp
             const float e0 = __expf(z0 - m_all);
@@ -747,7 +749,7 @@ __global__ void __launch_bounds__(128, 3) infonce_lane_kernel(InfoParams p) {
                           [&](int d) { return gbuf[d] + gbuf[DD + d] + gbuf[2 * DD + d] + gbuf[3 * DD + d]; });
         }
     } else {
-        redo = exchange_wait(p);
+        redo = SPEC ? exchange_wait(p) : false;
         if (!redo && tid == 0) {
             p.loss_parts[bid] = 0.f;
             p.anchor_pix[bid] = -1;
@@ -798,7 +800,7 @@ __device__ __forceinline__ uint32_t bf16_term(float x, int part) {
     return __float_as_uint(__bfloat162float(__float2bfloat16_rn(r1 - mid))) >> 16;
 }
 
-template <int NSTG>
+template <int NSTG, int MODE>
 __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(InfoParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = p.D;
@@ -846,7 +848,7 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
             if (lane == 0) mbar_expect_tx(&bars[s], (uint32_t)nv * row_bytes);
             __syncwarp();
             if (lane < nv) {
-                if (r < 0 || r >= blen) { if (!p.xchg_peers) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
+                if (r < 0 || r >= blen) { if (!SPEC) atomicOr(&p.plan->status, (uint32_t)ARCO_ST_INDEX_RANGE); r = min(max(r, 0), blen - 1); }
                 int phys = bhead + r;
                 if (phys >= cap) phys -= cap;
                 bulk_g2s(stage + (size_t)s * stage_u4 + (size_t)lane * RS16, bank + (int64_t)phys * row_bytes, row_bytes, &bars[s]);
@@ -857,8 +859,8 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
             for (int c = 0; c < NSTG && c < nch; ++c) issue(c, load_idx(c));
         int r_next = load_idx(NSTG);                              // every warp: any of them may issue the next chunk
 
-        AnchorInfo ai = info_anchor(p, j, q, a_hat, s_red, &s_pix);
-        if (!p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
+        AnchorInfo ai = info_anchor<ROWS>(p, j, q, a_hat, s_red, &s_pix);
+        if (!SPEC) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
         const float inv_temp = 1.f / p.temp;
         // A-fragment rows 8..10 of every k-step: lane (g < 3, t) holds terms g of a_hat[16ks + 2t, +1] and [.. + 8, + 9]
         // (slots 12..15 of a k-step are zero: the rows 11..15 of the A operand, read by the lanes with g >= 3)
@@ -986,10 +988,10 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
             if (lane == 0) { s_red[0][0] = S; s_red[0][1] = S2; }
         }
         __syncthreads();
-        redo = exchange_wait(p);
+        redo = SPEC ? exchange_wait(p) : false;
         if (!redo) {
             const float inv_scale = pl->inv_scale;
-            if (p.xchg_peers) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
+            if (SPEC) ai.cos0 = info_proto(p, j, q, bank_cls, a_hat, k0hat);
             const float z0 = ai.cos0 * inv_temp;
             const float m_all = inv_temp;                         // offset of every exponential: z <= 1/temp
             const float e0 = __expf(z0 - m_all);
@@ -997,7 +999,7 @@ __global__ void __launch_bounds__(128, NSTG == 1 ? 7 : 5) infonce_mma_kernel(Inf
                           [&](int d) { return gbuf[d]; });
         }
     } else {
-        redo = exchange_wait(p);
+        redo = SPEC ? exchange_wait(p) : false;
         if (!redo && tid == 0) {
             p.loss_parts[bid] = 0.f;
             p.anchor_pix[bid] = -1;
@@ -1106,22 +1108,32 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     const size_t smem = (size_t)6 * d.feat * 4 + (size_t)4 * kc * rs16 * 16;
     const int grid = d.classes * d.queries + (xchg ? 1 : 0);         // + the exchange block (block 0)
     cudaStream_t st = (cudaStream_t)stream;
-#define ARCO_INFONCE(MI, BF)                                                                                               \
+    // Three instantiations of every kernel: MODE 0 = the plain single-GPU op (nothing of the other two modes is compiled in:
+    // they cost registers, and 72 registers = 7 CTAs per SM = ONE wave at C*Q = 1024 is what the small shapes live on),
+    // 1 = anchors given as rows (arco_infonce_rows), 2 = batch shard (exchange block / gated redo, arco_infonce_sharded).
+    const int mode = anchor_rows ? 1 : ((xchg || gate_replanned) ? 2 : 0);
+    ARCO_REQUIRE(!(anchor_rows && (xchg || gate_replanned)), "arco_infonce: anchors-as-rows and the sharded exchange do not combine");
+#define ARCO_LAUNCH_MODE(KERNEL, SMEM, ...)                                                                                \
     do {                                                                                                                   \
-        ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_kernel<MI, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        arco::infonce_kernel<MI, BF><<<grid, 128, smem, st>>>(p);                                                           \
+        if (mode == 0) {                                                                                                   \
+            ARCO_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<__VA_ARGS__, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
+            KERNEL<__VA_ARGS__, 0><<<grid, 128, (SMEM), st>>>(p);                                                          \
+        } else if (mode == 1) {                                                                                            \
+            ARCO_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<__VA_ARGS__, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
+            KERNEL<__VA_ARGS__, 1><<<grid, 128, (SMEM), st>>>(p);                                                          \
+        } else {                                                                                                           \
+            ARCO_CUDA_CHECK(cudaFuncSetAttribute(KERNEL<__VA_ARGS__, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
+            KERNEL<__VA_ARGS__, 2><<<grid, 128, (SMEM), st>>>(p);                                                          \
+        }                                                                                                                  \
     } while (0)
+#define ARCO_INFONCE(MI, BF) ARCO_LAUNCH_MODE(arco::infonce_kernel, smem, MI, BF)
     static const bool lane_ok = [] { const char* e = getenv("ARCO_INFONCE_LANE"); return !(e && e[0] == '0'); }();
     // Measured on B200 (cold bank, Q=256, N=512): 128-byte rows and shorter gain (LA D=16: 0.027 vs 0.036 ms staged), a 256-byte
     // row does not (ACDC D=64: 0.086 vs 0.051 ms -- 32 lanes x 2 lines per load instruction thrash L1), so longer rows stay staged.
     if (lane_ok && temp >= 0.03f && cpl <= 8 && (cpl == 2 || cpl == 4 || cpl == 8)) {
         // short rows: one lane per key (see infonce_lane_kernel)
         const size_t sm = (size_t)6 * d.feat * 4 + (size_t)(d.negatives > 0 ? d.negatives : 1) * 4;
-#define ARCO_INFONCE_LANE(NC, BF)                                                                                        \
-        do {                                                                                                             \
-            ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_lane_kernel<NC, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-            arco::infonce_lane_kernel<NC, BF><<<grid, 128, sm, st>>>(p);                                                  \
-        } while (0)
+#define ARCO_INFONCE_LANE(NC, BF) ARCO_LAUNCH_MODE(arco::infonce_lane_kernel, sm, NC, BF)
         if (bf16bank) { if (cpl == 2) ARCO_INFONCE_LANE(2, true); else if (cpl == 4) ARCO_INFONCE_LANE(4, true); else if (cpl == 8) ARCO_INFONCE_LANE(8, true); else goto staged; }
         else { if (cpl == 2) ARCO_INFONCE_LANE(2, false); else if (cpl == 4) ARCO_INFONCE_LANE(4, false); else ARCO_INFONCE_LANE(8, false); }
 #undef ARCO_INFONCE_LANE
@@ -1142,19 +1154,15 @@ staged:
         size_t stage_bytes = (size_t)nstg * arco::MMA_KEYS * r16 * 16;
         if (stage_bytes < (size_t)ks * 64) stage_bytes = (size_t)ks * 64;   // G[16*ks] lives there after the loop
         const size_t sm = (size_t)2 * d.feat * 4 + (size_t)ks * 16 * 8 + 2 * 4 * arco::MMA_KEYS * 2 * 4 + stage_bytes;
-        if (nstg == 1) {
-            ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            arco::infonce_mma_kernel<1><<<grid, 128, sm, st>>>(p);
-        } else {
-            ARCO_CUDA_CHECK(cudaFuncSetAttribute(arco::infonce_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            arco::infonce_mma_kernel<2><<<grid, 128, sm, st>>>(p);
-        }
+        if (nstg == 1) ARCO_LAUNCH_MODE(arco::infonce_mma_kernel, sm, 1);
+        else ARCO_LAUNCH_MODE(arco::infonce_mma_kernel, sm, 2);
     } else if (bf16bank) {
         if (cpl <= 32) ARCO_INFONCE(1, true); else ARCO_INFONCE(2, true);
     } else {
         if (cpl <= 32) ARCO_INFONCE(1, false); else if (cpl <= 64) ARCO_INFONCE(2, false); else ARCO_INFONCE(4, false);
     }
 #undef ARCO_INFONCE
+#undef ARCO_LAUNCH_MODE
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
 }
