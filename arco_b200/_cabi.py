@@ -128,6 +128,8 @@ def _load():
         "arco_grid_sample": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "arco_eqv_loss": (C.c_int, [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "arco_scale_rows": (C.c_int, [vp, vp, vp, i32, i64, vp, vp]),
+        "arco_entropy_thresholds": (C.c_int, [vp, vp, i64, f32, f32, vp, vp, vp]),
+        "arco_classify_plan_logits": (C.c_int, [dp, vp, vp, vp, vp, vp, vp, f32, f32, i32, i32, bp, vp, vp]),
         "arco_infonce_sharded": (C.c_int, [dp, vp, bp, C.POINTER(Exchange), i32, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
         "arco_keys_transform_scratch_bytes": (C.c_int64, [i32, i32]),
         "arco_keys_transform": (C.c_int, [dp, bp, vp, vp, vp, vp]),

@@ -206,7 +206,7 @@ class _ContraLoss(torch.autograd.Function):
         sp = stream.cuda_stream
         lib = _cabi.lib
         layout = st["layout"]
-        if st["inject"] is None and (st["debug"] is None or st["debug"].get("fused")):
+        if st.get("logits") is None and st["inject"] is None and (st["debug"] is None or st["debug"].get("fused")):
             # one FFI call; multi-GPU too when the exchange buffer could be peer-mapped (no NCCL call between the stages)
             p2p = _p2p_exchange(st["group"], dev, dims.classes * (dims.feat + 1)) if st["group"] is not None else None
             if st["group"] is None or p2p is not None:
@@ -226,13 +226,36 @@ class _ContraLoss(torch.autograd.Function):
             _cabi.check(lib.arco_grad_zero(d, buf.data_ptr(), side0.cuda_stream), "arco_grad_zero")
             st["grad_buf"], st["side"] = buf, side0
 
+        lg = st.get("logits")
+        if lg is not None:
+            # logits-in: student entropy -> two percentile thresholds (device), then classify reads the teacher LOGITS, the label
+            # maps and the entropy directly; no probability / mask tensor is ever written (arco_classify_plan_logits)
+            n_u_px = dims.n_unlab * dims.space
+            ent = torch.empty(max(n_u_px, 1), dtype=torch.float32, device=dev)
+            thr = torch.full((2,), float("nan"), dtype=torch.float32, device=dev)
+            if dims.n_unlab:
+                _cabi.check(lib.arco_softmax_rows(lg["pred_u"].data_ptr(), dims.n_unlab, Cn, dims.space, None, ent.data_ptr(), sp),
+                            "arco_softmax_rows")
+                scratch = torch.empty(int(lib.arco_entropy_masks_scratch()), dtype=torch.uint8, device=dev)
+                _cabi.check(lib.arco_entropy_thresholds(ent.data_ptr(), st["label_u"].data_ptr(), n_u_px, lg["q_low"], lg["q_high"],
+                                                        thr.data_ptr(), scratch.data_ptr(), sp), "arco_entropy_thresholds")
+            _cabi.check(lib.arco_classify_plan_logits(
+                d, st["label_l"].data_ptr() if st["label_l"] is not None else None,
+                st["label_u"].data_ptr() if st["label_u"] is not None else None,
+                lg["pred_l_teacher"].data_ptr() if dims.n_lab else None, lg["pred_u_teacher"].data_ptr() if dims.n_unlab else None,
+                ent.data_ptr(), thr.data_ptr(), DELTA_P, float(st["delta_n"]), LOW_RANK, HIGH_RANK, b, wsp, sp),
+                "arco_classify_plan_logits")
+            st["thresholds"] = thr
         ins = (st["label_l"].data_ptr() if st["label_l"] is not None else None,
                st["label_u"].data_ptr() if st["label_u"] is not None else None,
                st["prob_l"].data_ptr() if st["prob_l"] is not None else None,
                st["prob_u"].data_ptr() if st["prob_u"] is not None else None,
-               st["low_mask"].data_ptr(), st["high_mask"].data_ptr(),
+               st["low_mask"].data_ptr() if st["low_mask"] is not None else None,
+               st["high_mask"].data_ptr() if st["high_mask"] is not None else None,
                DELTA_P, float(st["delta_n"]), LOW_RANK, HIGH_RANK)
-        if st["debug"] is not None and st["debug"].get("legacy_scan"):
+        if lg is not None:
+            pass
+        elif st["debug"] is not None and st["debug"].get("legacy_scan"):
             # the two-launch form of the C ABI (memset + classify, then the stand-alone scan/plan kernel)
             _cabi.check(lib.arco_classify_count(d, *ins, wsp, sp), "arco_classify_count")
             _cabi.check(lib.arco_scan_plan(d, b, wsp, sp), "arco_scan_plan")
@@ -579,3 +602,100 @@ def compute_contra_memobank_loss(
     if mom is not None:
         return state["prototype_out"].to(momentum_prototype.dtype), keys, loss
     return keys, loss
+
+
+def compute_contra_memobank_loss_from_logits(
+    rep,
+    train_l_label,
+    train_u_aug_label,
+    pred_l_teacher,
+    pred_u_teacher,
+    pred_u,
+    alpha_t,
+    memobank,
+    queue_prtlis,
+    queue_size,
+    rep_teacher,
+    delta_n=1.0,
+    func="asmc",
+    num_queries=256,
+    num_negatives=512,
+    temp=0.5,
+    *,
+    seed: Optional[int] = None,
+    sparse_grad: bool = False,
+    _debug: Optional[dict] = None,
+):
+    """The trainers' mask preparation AND the loss in one op, from the raw tensors (``train_arco_2d.py:345-398``):
+
+        prob_*_teacher = softmax(pred_*_teacher); entropy = H(softmax(pred_u)); low / high thresholds = np.percentile(entropy[valid],
+        alpha_t / 100 - alpha_t); low_mask_all / high_mask_all; label_onehot;
+        compute_contra_memobank_loss(rep, label_l, label_u, prob_l_teacher, prob_u_teacher, low_mask_all, high_mask_all, ...)
+
+    Equivalent -- bit for bit -- to ``prepare_contrast_inputs(...)`` followed by ``compute_contra_memobank_loss(...)`` on its
+    outputs, but no probability, mask or one-hot tensor is written: the classify kernel reads the C teacher logits, the int64
+    label (ignore label negative) and the student entropy per pixel and forms softmax and masks in registers
+    (``arco_classify_plan_logits``).  ``pred_*`` are float32 ``[B_x, C, *S]`` logits (2 <= C <= 8), labels int64 ``[B_x, *S]``.
+    Returns ``(new_keys, loss)``; ``_debug`` receives the thresholds."""
+    from .prepare import _q32
+    if not (torch.is_tensor(rep) and rep.is_cuda):
+        raise RuntimeError("arco_b200 needs CUDA tensors: there is no CPU fallback")
+    if rep.dim() not in (4, 5) or rep.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("rep must be float32 / bfloat16 [B,D,*S]")
+    if rep_teacher.shape != rep.shape or rep_teacher.dtype != rep.dtype or rep_teacher.device != rep.device:
+        raise ValueError("rep_teacher must match rep in shape, dtype and device")
+    dev = rep.device
+    B, D = int(rep.shape[0]), int(rep.shape[1])
+    spatial = tuple(rep.shape[2:])
+    S = 1
+    for x in spatial:
+        S *= int(x)
+    n_lab, n_unlab = int(train_l_label.shape[0]), int(train_u_aug_label.shape[0])
+    if n_lab + n_unlab != B:
+        raise ValueError("labelled + unlabelled images != rep batch")
+    Cn = int(pred_u_teacher.shape[1]) if n_unlab else int(pred_l_teacher.shape[1])
+    if not 2 <= Cn <= 8:
+        raise ValueError(f"the logits-in op supports 2 <= C <= 8 classes, got {Cn}; use prepare_contrast_inputs + compute_contra_memobank_loss")
+    if S % 4 != 0:
+        raise ValueError("the logits-in op needs prod(spatial) % 4 == 0")
+    for name, t, n in (("pred_l_teacher", pred_l_teacher, n_lab), ("pred_u_teacher", pred_u_teacher, n_unlab), ("pred_u", pred_u, n_unlab)):
+        if not (t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == (n, Cn) + spatial):
+            raise ValueError(f"{name} must be CUDA float32 [{n},{Cn},*spatial], got {t.dtype} {tuple(t.shape)}")
+    for name, t, n in (("train_l_label", train_l_label, n_lab), ("train_u_aug_label", train_u_aug_label, n_unlab)):
+        if t.dtype != torch.int64 or tuple(t.shape) != (n,) + spatial:
+            raise ValueError(f"{name} must be int64 [{n},*spatial]")
+    if D % 4 != 0 or D > 512 or len(memobank) != Cn or B * S >= 2 ** 31 or num_queries <= 0 or num_negatives < 0 or temp <= 0:
+        raise ValueError("bad D / memobank / sizes (see compute_contra_memobank_loss)")
+    with torch.cuda.device(dev):
+        bank = DeviceMemoryBank.adopt(memobank, queue_prtlis, queue_size, D, dev, rep.dtype)
+        bank.poll()
+        bank.begin_step()
+        sampler_seed, sampler_step = _sampler_stream(seed, bank, dev)
+        label_kind = _cabi.LABEL_INDEX_I64
+        key = (n_lab, n_unlab, Cn, D, S, int(num_queries), int(num_negatives), rep.dtype, label_kind, dev.index)
+        cached = _GEOMETRY.get(key)
+        if cached is None:
+            dims = _cabi.Dims(n_lab, n_unlab, Cn, D, S, int(num_queries), int(num_negatives),
+                              _cabi.BF16 if rep.dtype == torch.bfloat16 else _cabi.F32, label_kind)
+            cached = _GEOMETRY[key] = (dims, _cabi.workspace_layout(dims))
+        dims, layout = cached
+        state = dict(
+            dims=dims, layout=layout, bank=bank,
+            label_l=train_l_label.to(dev).contiguous() if n_lab else None,
+            label_u=train_u_aug_label.to(dev).contiguous() if n_unlab else None,
+            prob_l=None, prob_u=None, low_mask=None, high_mask=None,
+            logits=dict(pred_l_teacher=pred_l_teacher.detach().contiguous(), pred_u_teacher=pred_u_teacher.detach().contiguous(),
+                        pred_u=pred_u.detach().contiguous(), q_low=_q32(alpha_t), q_high=_q32(100 - alpha_t)),
+            rep_teacher=rep_teacher.detach().contiguous(), rep_data=rep.detach().contiguous(),
+            delta_n=delta_n, temp=temp, func=_FUNC.get(func, _cabi.FUNC_UNIFORM), seed=sampler_seed, step=sampler_step,
+            group=None, inject=None, debug=_debug, momentum=None, ema_decay=0.0,
+            prefill=bool(rep.requires_grad and torch.is_grad_enabled() and _PREFILL_GRAD
+                         and rep.numel() * rep.element_size() >= _PREFILL_MIN_BYTES),
+        )
+        state["sparse"] = _sparse_state(bank, rep, Cn * int(num_queries)) if (sparse_grad and rep.requires_grad and torch.is_grad_enabled()) else None
+        if state["sparse"] is not None:
+            state["prefill"] = False
+        loss = _ContraLoss.apply(rep, state)
+        if _debug is not None:
+            _debug["thresholds"] = state.get("thresholds")
+    return LazyKeys(bank, Cn, state["plan_view"]), loss

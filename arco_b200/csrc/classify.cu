@@ -25,6 +25,10 @@ struct ClassifyParams {
     const float* prob_u;
     const float* low_mask;
     const float* high_mask;
+    // logits mode (arco_classify_plan_logits): prob_l / prob_u hold the TEACHER LOGITS, the masks are derived in the kernel from
+    // the student entropy of the unlabelled images and the two percentile thresholds (train_arco_2d.py:356-392)
+    const float* entropy_u;     // [n_unlab, S]
+    const float* thresholds;    // device float[2]: low, high
     uint8_t* codes;
     uint32_t* tile_flagged;
     uint32_t* cnt_anchor;
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(256, 4) classify_kernel(ClassifyParams p) {
 // pass), which kept it at 0.2-0.3 of the HBM roofline on the small shapes.  Per-class counts are packed 8 bits per class
 // (<= 4 per thread, <= 128 per warp), reduced with redux.sync, and added to the tile counters by one lane per warp.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int C, int KIND, bool TAIL>
+template <int C, int KIND, bool TAIL, bool LOGITS = false>
 __global__ void __launch_bounds__(256) classify_small_kernel(ClassifyParams p) {
     constexpr int NLAB = KIND == ARCO_LABEL_ONEHOT_I64 ? C : 1;
     __shared__ uint32_t s_anchor[8], s_key[8], s_lv[8];
@@ -331,10 +335,42 @@ __global__ void __launch_bounds__(256) classify_small_kernel(ClassifyParams p) {
             la[c][0] = __ldg(reinterpret_cast<const longlong2*>(lp + (int64_t)c * S));
             la[c][1] = __ldg(reinterpret_cast<const longlong2*>(lp + (int64_t)c * S + 2));
         }
-        lm4 = __ldg(reinterpret_cast<const float4*>(p.low_mask + (int64_t)b * S + s));
-        hm4 = __ldg(reinterpret_cast<const float4*>(p.high_mask + (int64_t)b * S + s));
+        if (LOGITS) {
+            if (!labelled) lm4 = __ldg(reinterpret_cast<const float4*>(p.entropy_u + (int64_t)bx * S + s));   // the student entropy
+        } else {
+            lm4 = __ldg(reinterpret_cast<const float4*>(p.low_mask + (int64_t)b * S + s));
+            hm4 = __ldg(reinterpret_cast<const float4*>(p.high_mask + (int64_t)b * S + s));
+        }
     }
-    const float lm[4] = {lm4.x, lm4.y, lm4.z, lm4.w}, hm[4] = {hm4.x, hm4.y, hm4.z, hm4.w};
+    float lm[4] = {lm4.x, lm4.y, lm4.z, lm4.w}, hm[4] = {hm4.x, hm4.y, hm4.z, hm4.w};
+    if (LOGITS) {
+        // (1) teacher softmax in registers -- the operations of softmax_rows_kernel (prepare.cu) in the same order, so the
+        //     probabilities are bit-identical to the materialised ones (train_arco_2d.py:356-357)
+        // (2) the masks: labelled pixels count when their label is valid, unlabelled ones when in addition the student
+        //     entropy is <= the low / >= the high percentile threshold (:363-392)
+        const float lo = __ldg(p.thresholds), hi = __ldg(p.thresholds + 1);
+        float x[C][4];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { x[c][0] = pr[c].x; x[c][1] = pr[c].y; x[c][2] = pr[c].z; x[c][3] = pr[c].w; }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < C; ++c) m = fmaxf(m, x[c][v]);
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { x[c][v] = expf(x[c][v] - m); sum += x[c][v]; }
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c][v] = x[c][v] / sum;
+            const long long l = v == 0 ? la[0][0].x : v == 1 ? la[0][0].y : v == 2 ? la[0][1].x : la[0][1].y;
+            const bool valid = in_range && l >= 0;
+            const float e = lm[v];
+            lm[v] = (valid && (labelled || e <= lo)) ? 1.f : 0.f;
+            hm[v] = (valid && (labelled || e >= hi)) ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) pr[c] = make_float4(x[c][0], x[c][1], x[c][2], x[c][3]);
+    }
     uint32_t packed = 0, status = 0;
     unsigned long long n_lv = 0ull, n_an = 0ull, n_key = 0ull;
 #pragma unroll
@@ -418,10 +454,10 @@ __global__ void __launch_bounds__(256) classify_small_kernel(ClassifyParams p) {
     }
 }
 
-template <int KIND, bool TAIL>
+template <int KIND, bool TAIL, bool LOGITS = false>
 static bool launch_classify_small(const ClassifyParams& p, int grid, cudaStream_t st) {
     switch (p.C) {
-#define ARCO_CS(CC) case CC: classify_small_kernel<CC, KIND, TAIL><<<grid, 256, 0, st>>>(p); return true;
+#define ARCO_CS(CC) case CC: classify_small_kernel<CC, KIND, TAIL, LOGITS><<<grid, 256, 0, st>>>(p); return true;
         ARCO_CS(2) ARCO_CS(3) ARCO_CS(4) ARCO_CS(5) ARCO_CS(6) ARCO_CS(7) ARCO_CS(8)
 #undef ARCO_CS
         default: return false;
@@ -458,8 +494,11 @@ extern "C" int arco_label_onehot(const int64_t* labels, float* out, int64_t batc
 
 static int classify_launch(const arco_dims* dims, const int64_t* label_l, const int64_t* label_u, const float* prob_l,
                            const float* prob_u, const float* low_mask, const float* high_mask, float delta_p, float delta_n,
-                           int32_t low_rank, int32_t high_rank, const arco_bank* bank, void* workspace, void* stream) {
+                           int32_t low_rank, int32_t high_rank, const arco_bank* bank, void* workspace, void* stream,
+                           const float* entropy_u = nullptr, const float* thresholds = nullptr) {
     ARCO_REQUIRE(dims && workspace, "arco_classify_count: NULL dims/workspace");
+    const bool logits = thresholds != nullptr;
+    if (logits) { low_mask = thresholds; high_mask = thresholds; }           // (only checked for NULL / alignment below)
     const arco_dims& d = *dims;
     ARCO_REQUIRE(d.classes >= 1 && d.classes <= ARCO_MAX_CLASSES, "classes must be in [1, 32]");
     ARCO_REQUIRE(d.n_lab >= 0 && d.n_unlab >= 0 && d.n_lab + d.n_unlab > 0 && d.space > 0, "bad batch/space");
@@ -475,7 +514,7 @@ static int classify_launch(const arco_dims* dims, const int64_t* label_l, const 
 
     arco::ClassifyParams p;
     p.label_l = label_l; p.label_u = label_u; p.prob_l = prob_l; p.prob_u = prob_u;
-    p.low_mask = low_mask; p.high_mask = high_mask;
+    p.low_mask = low_mask; p.high_mask = high_mask; p.entropy_u = entropy_u; p.thresholds = thresholds;
     p.codes = (uint8_t*)(ws + L.codes);
     p.tile_flagged = (uint32_t*)(ws + L.tile_flagged);
     p.cnt_anchor = (uint32_t*)(ws + L.cnt_anchor);
@@ -507,6 +546,16 @@ static int classify_launch(const arco_dims* dims, const int64_t* label_l, const 
     int grid = arco::sm_count() * per_sm;
     if (grid > L.n_tiles) grid = L.n_tiles;
     static const bool small_ok = [] { const char* e = getenv("ARCO_CLASSIFY_SMALL"); return !(e && e[0] == '0'); }();
+    if (logits) {
+        ARCO_REQUIRE(tail && d.label_kind == ARCO_LABEL_INDEX_I64 && d.classes >= 2 && d.classes <= 8 && d.space % 4 == 0 &&
+                         aligned16(label_l) && aligned16(label_u) && aligned16(prob_l) && aligned16(prob_u) && aligned16(entropy_u) &&
+                         (d.n_unlab == 0 || entropy_u),
+                     "arco_classify_plan_logits: needs integer label maps, 2 <= C <= 8, S % 4 == 0 and 16-byte aligned tensors");
+        const bool done = arco::launch_classify_small<ARCO_LABEL_INDEX_I64, true, true>(p, L.n_tiles, st);
+        ARCO_REQUIRE(done, "arco_classify_plan_logits: unsupported class count");
+        ARCO_LAUNCH_CHECK();
+        return ARCO_OK;
+    }
     if (vec && small_ok && d.classes >= 2 && d.classes <= 8) {
         // one tile per CTA, every load independent (see classify_small_kernel)
         const int g = L.n_tiles;
@@ -543,4 +592,13 @@ extern "C" int arco_classify_plan(const arco_dims* dims, const int64_t* label_l,
     ARCO_REQUIRE(bank != nullptr, "arco_classify_plan: NULL bank");
     return classify_launch(dims, label_l, label_u, prob_l, prob_u, low_mask, high_mask, delta_p, delta_n, low_rank, high_rank,
                            bank, workspace, stream);
+}
+
+extern "C" int arco_classify_plan_logits(const arco_dims* dims, const int64_t* label_l, const int64_t* label_u,
+                                         const float* logits_l_teacher, const float* logits_u_teacher, const float* entropy_u,
+                                         const float* thresholds, float delta_p, float delta_n, int32_t low_rank,
+                                         int32_t high_rank, const arco_bank* bank, void* workspace, void* stream) {
+    ARCO_REQUIRE(bank != nullptr && thresholds != nullptr, "arco_classify_plan_logits: NULL bank / thresholds");
+    return classify_launch(dims, label_l, label_u, logits_l_teacher, logits_u_teacher, nullptr, nullptr, delta_p, delta_n, low_rank,
+                           high_rank, bank, workspace, stream, entropy_u, thresholds);
 }

@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(1024) entropy_mask_kernel(const float* __restr
         if (blockIdx.x == 0 && thresholds) { thresholds[0] = s_thr[0]; thresholds[1] = s_thr[1]; }
     }
     __syncthreads();
+    if (low_mask == nullptr) return;                          // thresholds only (arco_entropy_thresholds)
     const float lo = s_thr[0], hi = s_thr[1];
     const int64_t total = n_l + n_u;
     for (int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 1024) {
@@ -299,6 +300,22 @@ extern "C" int arco_entropy_masks(const float* entropy, const int64_t* label_l, 
     const int mgrid = (int)((total + 1023) / 1024 < 148 * 2 ? (total + 1023) / 1024 : 148 * 2);
     arco::entropy_mask_kernel<<<mgrid > 0 ? mgrid : 1, 1024, 0, st>>>(entropy, label_l, label_u, n_lab_px, n_unlab_px, q_low, q_high, s,
                                                                      low_mask, high_mask, thresholds);
+    ARCO_LAUNCH_CHECK();
+    return ARCO_OK;
+}
+
+extern "C" int arco_entropy_thresholds(const float* entropy, const int64_t* label_u, int64_t n_unlab_px, float q_low, float q_high,
+                                       float* thresholds, void* scratch, void* stream) {
+    ARCO_REQUIRE(entropy && label_u && thresholds && scratch && n_unlab_px > 0 && n_unlab_px < (1ll << 32), "arco_entropy_thresholds: bad argument");
+    ARCO_REQUIRE(q_low >= 0.f && q_low <= 1.f && q_high >= 0.f && q_high <= 1.f, "quantiles must be in [0, 1]");
+    cudaStream_t st = (cudaStream_t)stream;
+    arco::SelectState* s = (arco::SelectState*)scratch;
+    ARCO_CUDA_CHECK(cudaMemsetAsync(s, 0, sizeof(arco::SelectState), st));
+    const int grid = (int)((n_unlab_px + 4095) / 4096 < 148 ? (n_unlab_px + 4095) / 4096 : 148);
+    arco::select_hist_kernel<1><<<grid, 1024, arco::SEL_B1 * 4, st>>>(entropy, label_u, n_unlab_px, q_low, q_high, s);
+    arco::select_hist_kernel<2><<<grid, 1024, arco::SEL_RANKS * arco::SEL_B2 * 4, st>>>(entropy, label_u, n_unlab_px, q_low, q_high, s);
+    arco::select_hist_kernel<3><<<grid, 1024, arco::SEL_RANKS * arco::SEL_B3 * 4, st>>>(entropy, label_u, n_unlab_px, q_low, q_high, s);
+    arco::entropy_mask_kernel<<<1, 1024, 0, st>>>(entropy, nullptr, label_u, 0, n_unlab_px, q_low, q_high, s, nullptr, nullptr, thresholds);
     ARCO_LAUNCH_CHECK();
     return ARCO_OK;
 }

@@ -438,6 +438,21 @@ ARCO_API int arco_infonce_sharded(const arco_dims* dims, const void* rep, const 
                                   const float* momentum, const int32_t* momentum_on, float ema_decay, float ema_keep,
                                   float* proto_out, void* workspace, void* stream);
 
+/* ---- logits-in loss (SURVEY.md section 8(f) rank 1 rationale): classify straight from the trainers' raw tensors ------------------
+   arco_prepare_contrast materialises teacher probabilities [B,C,S] and two masks [B,1,S] only for arco_classify_plan to read them
+   back.  Here the teacher softmax and both masks are formed in the classify kernel's registers (same operations in the same
+   order: results are bit-identical to the two-call path): per pixel it reads the C teacher logits, the int64 label (ignore -1)
+   and, on unlabelled images, the student entropy; nothing intermediate is written.  2 <= C <= 8, integer label maps
+   (dims->label_kind = ARCO_LABEL_INDEX_I64), S % 4 == 0.
+   arco_entropy_thresholds: the two np.percentile thresholds (train_arco_2d.py:360-369) of the valid unlabelled entropies ->
+   thresholds[2] on the device (3-level radix select; scratch: arco_entropy_masks_scratch()). */
+ARCO_API int arco_entropy_thresholds(const float* entropy, const int64_t* label_u, int64_t n_unlab_px, float q_low, float q_high,
+                                     float* thresholds, void* scratch, void* stream);
+ARCO_API int arco_classify_plan_logits(const arco_dims* dims, const int64_t* label_l, const int64_t* label_u,
+                                       const float* logits_l_teacher, const float* logits_u_teacher, const float* entropy_u,
+                                       const float* thresholds, float delta_p, float delta_n, int32_t low_rank,
+                                       int32_t high_rank, const arco_bank* bank, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
