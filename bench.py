@@ -489,10 +489,10 @@ def main_ours(args):
                 "classes": spec.classes, "spatial": list(spec.spatial), "feat": spec.feat, "rep_storage": spec.dtype,
                 "queries": spec.queries, "negatives": spec.negatives, "func": args.func,
                 "labels": "blocky16" if args.blocky else "iid", "banks": ("cold: the trainers' initial one-row banks" if COLD_BANK else "pre-filled to capacity (50000/30000 rows)") + (", bf16-exact rows in a bf16 ring" if bank_dtype == torch.bfloat16 else ", fp32 ring"),
-                "pixels_per_gpu": P, "parallelism": (f"batch-shard x{world}, 1 exchange of C*(D+1) fp64 (" + ("own kernel over NVLink peer memory" if __import__("arco_b200.contra", fromlist=["x"]).P2P_EXCHANGE_USED else "NCCL all-reduce") + ")") if world > 1 else "single GPU",
+                "pixels_per_gpu": P, "parallelism": (f"batch-shard x{world}, 1 exchange of C*(D+1) fp64 (" + ("own exchange block inside the InfoNCE launch, over NVLink peer memory" if __import__("arco_b200.contra", fromlist=["x"]).P2P_EXCHANGE_USED else "NCCL all-reduce") + ")") if world > 1 else "single GPU",
                 "l2": head["l2"], "timing": "CUDA events per step on the launching stream, max over ranks",
             },
-            "clocks": clk, "gpu_launches": args.steps * (KERNELS_PER_STEP + (1 if world > 1 else 0)),
+            "clocks": clk, "gpu_launches": args.steps * (KERNELS_PER_STEP + (3 if world > 1 else 0)),   # N>1: + sample_scan / sample_emit / InfoNCE again, gated on a changed plan (early exit)
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "aten_gpu_baseline": aten, "stages": stages,
             "step_alg_bytes": head.get("step_alg_bytes"), "step_frac_hbm": head.get("step_frac_hbm"),
             "multi_gpu_check": head.get("multi_gpu_check"), "cuda_graph_replay": head.get("cuda_graph_replay"), "configs": configs,
