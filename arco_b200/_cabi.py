@@ -138,6 +138,8 @@ def _load():
         "arco_infonce_rows": (C.c_int, [dp, vp, vp, bp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
         "arco_similarity_dense_scratch": (C.c_int64, [i32, i32, i32, bp, vp]),
         "arco_similarity_dense": (C.c_int, [i32, i32, i32, i32, vp, vp, bp, vp, vp, vp, vp]),
+        "arco_similarity_dense_backward_scratch": (C.c_int64, [i32, i32, i32, bp, vp]),
+        "arco_similarity_dense_backward": (C.c_int, [i32, i32, i32, i32, vp, vp, bp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)      # AttributeError here == header/library mismatch

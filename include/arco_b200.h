@@ -323,6 +323,14 @@ ARCO_API int64_t arco_similarity_dense_scratch(int32_t feat, int32_t queries, in
 ARCO_API int arco_similarity_dense(int32_t feat, int32_t queries, int32_t negatives, int32_t n_slots,
                                    const int32_t* slot_class, const float* anchors, const arco_bank* bank,
                                    const int32_t* idx_neg, float* logits, void* scratch, void* stream);
+/* Backward of the dense form: grad_anchor_hat[slot][q][:] = sum_n grad_logits[slot][q][n] * k_hat[row(idx_neg[slot][q][n])]
+   (the gradient with respect to the UNIT anchors; duplicates of a ring row accumulate) as a second tcgen05 GEMM
+   [Q, M] x [M, D]: scattered weights split into three bf16 terms against the transposed ring. */
+ARCO_API int64_t arco_similarity_dense_backward_scratch(int32_t feat, int32_t queries, int32_t n_slots, const arco_bank* bank,
+                                                        const int32_t* slot_class);
+ARCO_API int arco_similarity_dense_backward(int32_t feat, int32_t queries, int32_t negatives, int32_t n_slots,
+                                            const int32_t* slot_class, const float* grad_logits, const arco_bank* bank,
+                                            const int32_t* idx_neg, float* grad_anchor_hat, void* scratch, void* stream);
 
 /* ---- mask / threshold preparation upstream of the loss -------------------------------
    Replaces train_arco_2d.py:345-393 (train_arco_3d.py:315-353): teacher softmax, student entropy, the two np.percentile

@@ -21,30 +21,35 @@ def main():
            "* gather fp32 / gather bf16: `arco_infonce` (forward + anchor gradient) on an fp32 ring (FFMA) / on a bf16 ring "
            "(FFMA below D = 320, `mma.sync` from there; the forced-mma column shows why);",
            "* dense: `arco_similarity_dense` -- anchor split into 3 bf16 terms, tcgen05 GEMM `[Q,3D] x [3D,M]` into TMEM, "
-           "cosines written ring-row-major, scalar gather; FORWARD logits only, checked against torch at 1e-5 "
-           "(`tests/test_gpu_dense.py`). `dense TFLOP/s` counts the issued `2*4*Q*M*D*3` flop over the whole call "
-           "(anchor prep, row norms, GEMM, gather).\n",
-           "| D | Q | N | Q*N/M | gather fp32 ms | gather bf16 ms | gather bf16 (mma forced) ms | dense fwd ms | dense TFLOP/s | dense vs best gather |",
-           "|---|---|---|---|---|---|---|---|---|---|"]
+           "cosines written ring-row-major, scalar gather, checked against torch at 1e-5 "
+           "(`tests/test_gpu_dense.py`). `dense TFLOP/s` counts the issued `2*4*Q*M*D*3` flop of the forward over the whole call "
+           "(anchor prep, row norms, GEMM, gather);",
+           "* dense fwd+bwd: the same plus `arco_similarity_dense_backward` through autograd -- logit gradients scattered into "
+           "`Wd[Q,M]` (float atomics), split into 3 bf16 terms, second tcgen05 GEMM `[Q,3M] x [3M,D]` against the transposed ring "
+           "(gradient at 1e-5 against autograd of the gather form). This is the like-for-like column: the gather kernels emit the "
+           "anchor gradient in the same pass.\n",
+           "| D | Q | N | Q*N/M | gather fp32 ms | gather bf16 ms | gather bf16 (mma forced) ms | dense fwd ms | dense TFLOP/s | dense fwd+bwd ms | dense fwd vs best gather | dense fwd+bwd vs best gather |",
+           "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     cross = []
     for r in rows:
         k = (r["D"], r["Q"], r["N"])
         best = min(r["ms"], r["ms_gather_bf16"])
-        sp = best / r["ms_dense_fwd"]
+        sp_f = best / r["ms_dense_fwd"]
+        fb = r.get("ms_dense_fwd_bwd", float("nan"))
+        sp = best / fb
         m = mma.get(k)
         out.append(f"| {r['D']} | {r['Q']} | {r['N']} | {r['reuse']:.1f} | {r['ms']:.3f} | {r['ms_gather_bf16']:.3f} | "
-                   f"{(m['ms_gather_bf16'] if m else float('nan')):.3f} | {r['ms_dense_fwd']:.3f} | {r['dense_tflops']:.0f} | {sp:.2f}x |")
+                   f"{(m['ms_gather_bf16'] if m else float('nan')):.3f} | {r['ms_dense_fwd']:.3f} | {r['dense_tflops']:.0f} | {fb:.3f} | {sp_f:.2f}x | {sp:.2f}x |")
         cross.append((r["reuse"], sp, k))
     out.append("")
     byn = {}
     for reuse, sp, (D, Q, N) in cross:
         byn.setdefault(N, []).append(sp)
-    out.append("Reading: the dense form costs ~Q*M (GEMM, cosine matrix write) plus a scalar gather, the paired form Q*N*D bytes, so "
-               "the ratio follows N (rows per query) against M, not Q: " +
+    out.append("Reading (forward + backward on both sides): the dense form costs ~Q*M (two GEMMs, cosine matrix and weight matrix traffic) "
+               "plus scalar gather / scatter, the paired form Q*N*D bytes, so the ratio follows N (rows per query) against M, not Q: " +
                "; ".join(f"N = {n}: {min(v):.2f}x .. {max(v):.2f}x" for n, v in sorted(byn.items())) +
                f". Largest win {max(c[1] for c in cross):.1f}x at (D, Q, N) = {max(cross, key=lambda c: c[1])[2]}. "
-               "At the reference's own Q = 256, N = 512 the gather form is 2-4x faster, which is why the training step keeps it; "
-               "a dense gradient (`W'[Q,M] x K[M,D]`, one more GEMM of the same size) would roughly double the dense column.")
+               "At the reference's own Q = 256, N = 512 the gather form is several times faster, which is why the training step keeps it.")
     with open(os.path.join(ROOT, "profiles", f"{tag}_config5_sweep.md"), "w") as f:
         f.write("\n".join(out) + "\n")
 

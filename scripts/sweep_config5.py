@@ -57,6 +57,14 @@ for D in (64, 128, 256):
                     anchors = torch.randn(Cn, Q, D, device=dev, generator=gen)
                     idx3 = inn.view(Cn, Q, N)
                     res["dense"] = timeit(lambda: dense_similarity(anchors, bank, list(range(Cn)), idx3), 5)
+                    # forward + backward of the dense form (second GEMM: scattered logit gradients x transposed ring), the
+                    # like-for-like comparison with the gather kernels, which emit the anchor gradient in the same pass
+                    a_req = anchors.clone().requires_grad_(True)
+                    g_up = torch.randn(Cn, Q, N, device=dev, generator=gen)
+                    def fb():
+                        a_req.grad = None
+                        dense_similarity(a_req, bank, list(range(Cn)), idx3).backward(g_up)
+                    res["dense_fb"] = timeit(fb, 5)
             ms = res["f32"]
             plan = _cabi.Plan.from_buffer_copy(ws[L.plan: L.plan + C.sizeof(_cabi.Plan)].cpu().numpy().tobytes())
             cv = sum(1 for j in range(Cn) if plan.slot_active[j])
@@ -64,7 +72,7 @@ for D in (64, 128, 256):
             flops = 2 * 2 * cv * Q * (1 + N) * D
             dense_flops = 2 * cv * Q * M * D * 3 * 2      # two GEMMs (scores, gradient), 3-way bf16 split
             gemm_flops = 2 * Cn * Q * M * D * 3                      # what arco_similarity_dense issues (3 bf16 terms, all 4 classes)
-            rec = dict(D=D, Q=Q, N=N, M=M, C_v=cv, ms=ms, ms_gather_bf16=res["bf16"], ms_dense_fwd=res["dense"],
+            rec = dict(D=D, Q=Q, N=N, M=M, C_v=cv, ms=ms, ms_gather_bf16=res["bf16"], ms_dense_fwd=res["dense"], ms_dense_fwd_bwd=res["dense_fb"],
                        gather_gbs=gathered / ms / 1e6, tflops=flops / ms / 1e9, dense_tflops=gemm_flops / res["dense"] / 1e9,
                        reuse=Q * N / M, dense_tflop_needed=dense_flops / 1e12, dense_ms_at_1pf=dense_flops / 1e15 * 1e3 / 1.0)
             out.append(rec); print(json.dumps(rec), flush=True)

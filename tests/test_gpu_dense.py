@@ -1,5 +1,5 @@
-"""GPU: the config-5 dense tensor-core similarity (arco_similarity_dense) against a plain PyTorch fp32 reference of the
-same op -- cos(anchor_q, bank[idx[q, n]]) as loss_helper_3d.py:466-486 forms it -- at 1e-5, including a wrapped ring,
+"""GPU: the config-5 dense tensor-core similarity (arco_similarity_dense) and its backward (arco_similarity_dense_backward)
+against a plain PyTorch fp32 reference of the same op and its autograd gradient -- cos(anchor_q, bank[idx[q, n]]) as loss_helper_3d.py:466-486 forms it -- at 1e-5, including a wrapped ring,
 a ragged last ring tile and a feature size that is not a multiple of the 64-element K block."""
 import pytest
 import torch
@@ -26,11 +26,19 @@ def test_dense_similarity_matches_torch(D, Q, N, caps, fill):
     bank.head[0] = 37
     shifted = torch.roll(bank.rows[: caps[0]].clone(), 37, dims=0)
     bank.rows[: caps[0]] = shifted
-    anchors = (torch.randn(2, Q, D, generator=g) * 3).to(dev)
+    anchors = (torch.randn(2, Q, D, generator=g) * 3).to(dev).requires_grad_(True)
     slot_classes = [1, 0]
     idx = torch.stack([torch.randint(0, fill[c], (Q, N), generator=g) for c in slot_classes]).to(torch.int32).to(dev)
+    idx[:, :, 1] = idx[:, :, 0]                                                  # duplicates of a ring row accumulate in backward
     out = dense_similarity(anchors, bank, slot_classes, idx)
+    g_out = torch.randn(out.shape, generator=g).to(dev)
+    out.backward(g_out)
+    a_ref = anchors.detach().clone().requires_grad_(True)
     for j, c in enumerate(slot_classes):
         keys = rows[c].to(dev)[idx[j].long()]                                    # [Q, N, D]
-        ref = torch.nn.functional.cosine_similarity(anchors[j][:, None, :], keys, dim=2)
-        assert float((out[j] - ref).abs().max()) <= 1e-5, (j, float((out[j] - ref).abs().max()))
+        ref = torch.nn.functional.cosine_similarity(a_ref[j][:, None, :], keys, dim=2)
+        assert float((out[j].detach() - ref.detach()).abs().max()) <= 1e-5, (j, float((out[j].detach() - ref.detach()).abs().max()))
+        (ref * g_out[j]).sum().backward()
+    # the dense backward (second tcgen05 GEMM: scattered logit gradients x transposed ring) against autograd of the gather form
+    err = float((anchors.grad - a_ref.grad).norm() / a_ref.grad.norm())
+    assert err <= 1e-5, err
