@@ -253,20 +253,34 @@ __global__ void __launch_bounds__(256) revisit_enqueue_kernel(const T* __restric
     float* dst = pool + row * L;
     constexpr int PER16 = 16 / (int)sizeof(T);
     const int64_t groups = L / PER16;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-        const uint4 raw = ldg_nc_u4(src + g * PER16);
-        if (PER16 == 4) {
-            float4 o;
-            o.x = __uint_as_float(raw.x) * inv; o.y = __uint_as_float(raw.y) * inv; o.z = __uint_as_float(raw.z) * inv; o.w = __uint_as_float(raw.w) * inv;
-            reinterpret_cast<float4*>(dst)[g] = o;
-        } else {
-            float4 o0, o1;
-            o0.x = __uint_as_float(raw.x << 16) * inv; o0.y = __uint_as_float(raw.x & 0xffff0000u) * inv;
-            o0.z = __uint_as_float(raw.y << 16) * inv; o0.w = __uint_as_float(raw.y & 0xffff0000u) * inv;
-            o1.x = __uint_as_float(raw.z << 16) * inv; o1.y = __uint_as_float(raw.z & 0xffff0000u) * inv;
-            o1.z = __uint_as_float(raw.w << 16) * inv; o1.w = __uint_as_float(raw.w & 0xffff0000u) * inv;
-            reinterpret_cast<float4*>(dst)[2 * g] = o0;
-            reinterpret_cast<float4*>(dst)[2 * g + 1] = o1;
+    // four independent 16-byte loads in flight per thread before the first store (a streaming read + 2x-wide write)
+    constexpr int UN = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < groups; g0 += stride * UN) {
+        uint4 raw[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int64_t g = g0 + u * stride;
+            raw[u] = g < groups ? ldg_nc_u4(src + g * PER16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int64_t g = g0 + u * stride;
+            if (g >= groups) continue;
+            const uint4 r = raw[u];
+            if (PER16 == 4) {
+                float4 o;
+                o.x = __uint_as_float(r.x) * inv; o.y = __uint_as_float(r.y) * inv; o.z = __uint_as_float(r.z) * inv; o.w = __uint_as_float(r.w) * inv;
+                __stcs(reinterpret_cast<float4*>(dst) + g, o);
+            } else {
+                float4 o0, o1;
+                o0.x = __uint_as_float(r.x << 16) * inv; o0.y = __uint_as_float(r.x & 0xffff0000u) * inv;
+                o0.z = __uint_as_float(r.y << 16) * inv; o0.w = __uint_as_float(r.y & 0xffff0000u) * inv;
+                o1.x = __uint_as_float(r.z << 16) * inv; o1.y = __uint_as_float(r.z & 0xffff0000u) * inv;
+                o1.z = __uint_as_float(r.w << 16) * inv; o1.w = __uint_as_float(r.w & 0xffff0000u) * inv;
+                __stcs(reinterpret_cast<float4*>(dst) + 2 * g, o0);
+                __stcs(reinterpret_cast<float4*>(dst) + 2 * g + 1, o1);
+            }
         }
     }
 }

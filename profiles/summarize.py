@@ -23,7 +23,9 @@ METRICS = [
 
 
 def ncu_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .csv is the raw page already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`): the reports themselves are
+    # too large to bring back (gpurun merges at most 64 MiB)
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     res = []
