@@ -84,6 +84,53 @@ def _scenario(scenario, rank, world, dev):
                 replanned=int(plan.replanned), fused=fused)
 
 
+def _scenario_producers(rank, world, dev):
+    """SURVEY 8(f) rank 2 on batch shards: the x-space class sums are all-reduced, then the teacher weight is applied."""
+    from arco_b200 import producers
+    from arco_b200.sharded import shard_batch
+    from arco_b200.synth import CaseSpec, exact_case, make_bank
+    from oracle import producers_oracle as po
+    import arco_b200
+    spec = CaseSpec("dist_prod", 2, 2, 4, (32, 32), 48, queries=32, negatives=8, bank_init="fill:60", caps=[80, 70, 70, 70], seed=77)
+    x = exact_case(spec, 0)
+    mine = shard_batch(x, spec.n_lab, rank, world)
+    gen = torch.Generator().manual_seed(9)
+    ws = [torch.randn(48, 48, generator=gen) / 7 for _ in range(4)]
+    g = {k: v.to(dev) for k, v in mine.items()}
+    bank_g, ptr_g, caps = make_bank(spec)
+    bank_c, ptr_c, _ = make_bank(spec)
+    xs = g["rep"].clone().requires_grad_(True)
+    dbg = {}
+    nk, loss = producers.compute_contra_memobank_loss_from_features(
+        xs, g["rep_teacher"], [w.to(dev) for w in ws[:3]], ws[3].to(dev), g["label_l"], g["label_u"], g["prob_l"], g["prob_u"],
+        g["low_mask"], g["high_mask"], bank_g, ptr_g, caps, delta_n=0.97, func="smc", num_queries=spec.queries,
+        num_negatives=spec.negatives, process_group=dist.group.WORLD, seed=5, _debug=dbg)
+    loss.backward()
+    torch.cuda.synchronize()
+    arco_b200.synchronize_bank(bank_g)
+    plan = bank_g[0].bank.last_plan
+    replay = []
+    for j in range(spec.classes):
+        if plan.slot_active[j]:
+            replay += [dbg["idx_anchor"][j].long().cpu(), dbg["idx_neg"][j, : spec.queries * spec.negatives].long().cpu()]
+    it = iter(replay)
+
+    def global_sums(local):
+        t = local.to(dev)
+        dist.all_reduce(t)
+        return t.cpu()
+
+    xo = mine["rep"].clone().requires_grad_(True)
+    res = po.contra_from_features(xo, mine["rep_teacher"], ws[:3], ws[3], mine["label_l"], mine["label_u"], mine["prob_l"], mine["prob_u"],
+                                  mine["low_mask"], mine["high_mask"], bank_c, ptr_c, caps, delta_n=0.97, sampler=lambda h, s: next(it),
+                                  num_queries=spec.queries, num_negatives=spec.negatives, proto_sum_hook=global_sums)
+    res.loss.backward()
+    lo = float(res.loss.detach())
+    ok = (list(nk) == res.new_keys and abs(float(loss.detach()) - lo) <= 1e-5 * max(1.0, abs(lo))
+          and float((xs.grad.cpu() - xo.grad).norm() / xo.grad.norm()) <= 1e-5)
+    return dict(ok=bool(ok), loss=float(loss.detach()), oracle=lo)
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -91,7 +138,7 @@ def _worker(rank, world, port, out):
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        out[rank] = [_scenario(sc, rank, world, dev) for sc in range(2)]
+        out[rank] = [_scenario(sc, rank, world, dev) for sc in range(2)] + [_scenario_producers(rank, world, dev)]
     finally:
         dist.destroy_process_group()
 
@@ -110,5 +157,6 @@ def test_two_gpu_sharded_loss_matches_oracle():
     for sc in range(2):
         assert all(res[r][sc]["ok"] for r in range(world)), res
         assert res[0][sc]["valid"] == res[1][sc]["valid"]
+    assert all(res[r][2]["ok"] for r in range(world)), res                       # producers folded in, x-space sums all-reduced
     assert res[0][0]["replanned"] == 0 and res[1][0]["replanned"] == 0          # same valid list everywhere
     assert res[0][1]["replanned"] == 1 and res[0][1]["valid"] == [0, 1, 2, 3]    # rank 0 had to redraw
