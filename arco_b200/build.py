@@ -40,7 +40,8 @@ def build(force: bool = False, verbose: bool = False, extra=None, out: str = LIB
     os.makedirs(LIBDIR, exist_ok=True)
     extra = list(extra or [])
     tag = "" if out == LIB else "." + os.path.basename(out).replace(".so", "")
-    headers = [os.path.join(CSRC, "arco_common.cuh"), os.path.join(CSRC, "tc_common.cuh"),
+    headers = [os.path.join(CSRC, "arco_common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "proto_tail.cuh"),
+               os.path.join(CSRC, "plan_common.cuh"),
                os.path.join(HERE, "..", "include", "arco_b200.h")]
     objs, jobs = [], []
     for src in SOURCES:

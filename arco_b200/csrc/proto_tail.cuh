@@ -52,8 +52,18 @@ __device__ __forceinline__ void proto_finalize_tail(const float* __restrict__ pa
         if (valid && d < D) {
             const float* src = partials + (int64_t)c * D + d;
             const int64_t rstride = (int64_t)C * D;
+            // The fold is a chain of L2 round trips (a few hundred partial rows, nothing else left to run on the GPU): sixteen
+            // independent loads in flight per lane -- with four, the LA shape's 592 rows took ~20 serial round trips (~12 us of
+            // a 62 us kernel).
             int r = warp;
-            for (; r + 3 * nwarp < rows; r += 4 * nwarp) {       // four independent loads in flight
+            for (; r + 15 * nwarp < rows; r += 16 * nwarp) {
+                float a[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) a[u] = __ldcg(src + (int64_t)(r + u * nwarp) * rstride);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) s += (double)a[u];
+            }
+            for (; r + 3 * nwarp < rows; r += 4 * nwarp) {
                 const float a0 = __ldcg(src + (int64_t)r * rstride), a1 = __ldcg(src + (int64_t)(r + nwarp) * rstride);
                 const float a2 = __ldcg(src + (int64_t)(r + 2 * nwarp) * rstride), a3 = __ldcg(src + (int64_t)(r + 3 * nwarp) * rstride);
                 s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
