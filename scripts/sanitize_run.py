@@ -79,6 +79,76 @@ def main():
                 torch.cuda.synchronize()
                 assert torch.isfinite(loss)
             print("ok", spec.name, float(loss))
+    if only is None or "revisit" in only:
+        # TMA-box ring (three 2-D boxes per chunk, mbarrier full / empty), ragged tail of L
+        gen = torch.Generator(device=dev).manual_seed(2)
+        bs, K, L = 3, 9, 5 * 4 * 12 * 8
+        pool = torch.nn.functional.normalize(torch.randn(K, L, device=dev, generator=gen), dim=1)
+        for dt in (torch.float32, torch.bfloat16):
+            rs = torch.randn(bs, 5, 4, 12 * 8, device=dev, generator=gen).to(dt)
+            rt = torch.randn(bs, 5, 4, 12 * 8, device=dev, generator=gen).to(dt)
+            loss = arco_b200.get_revisiting_loss(pool, rs, rt, topk=3)
+            arco_b200.revisit_enqueue(rt, pool, torch.zeros(1, dtype=torch.long))
+            torch.cuda.synchronize()
+            assert torch.isfinite(loss)
+        print("ok revisit", float(loss))
+    if only is None or "logits" in only:
+        # logits-in classify (teacher softmax + entropy masks in registers) + thresholds-only select
+        gen = torch.Generator(device=dev).manual_seed(4)
+        n, c = 2, 4
+        pl, pu, ps = (torch.randn(n, c, 32, 32, device=dev, generator=gen) for _ in range(3))
+        ll = torch.randint(0, c, (n, 32, 32), device=dev, generator=gen)
+        lu = torch.randint(-1, c, (n, 32, 32), device=dev, generator=gen)
+        spec = CaseSpec("logits", n, n, c, (32, 32), 32, queries=16, negatives=8, bank_init="fill:40", caps=[64] * c)
+        bank, ptr, caps = make_bank(spec)
+        rep = torch.randn(2 * n, 32, 32, 32, device=dev, generator=gen).requires_grad_(True)
+        _, loss = arco_b200.compute_contra_memobank_loss_from_logits(rep, ll, lu, pl, pu, ps, 20.0, bank, ptr, caps, rep.detach() * 0.5,
+                                                                     delta_n=0.97, func="smc", num_queries=16, num_negatives=8, seed=3)
+        loss.backward()
+        torch.cuda.synchronize()
+        print("ok logits", float(loss))
+    if only is None or "sharded" in only:
+        # the exchange block inside the InfoNCE launch + gated redo launches, with a fake peer buffer on the same GPU
+        from arco_b200 import contra
+        spec = CaseSpec("shard1", 2, 2, 4, (32, 32), 16, queries=32, negatives=8, bank_init="fill:60", caps=[80, 70, 70, 70],
+                        label_mode="absent:1", seed=41)
+        g = {k: v.to(dev) for k, v in exact_case(spec, 0).items()}
+        n_sum = 4 * 17
+        slot = (n_sum + 63) // 64 * 64
+        mine = torch.zeros(2 * slot + 64, dtype=torch.float64, device=dev)
+        peer = torch.zeros(2 * slot + 64, dtype=torch.float64, device=dev)
+        ps = torch.rand(4, 17, dtype=torch.float64) * 5 + 1
+        for sl in range(2):
+            peer[sl * slot: sl * slot + n_sum] = ps.flatten().to(dev)
+        mine.view(torch.int64)[2 * slot + 1] = 1 << 60
+        state = dict(buf=mine, peer_buf=peer, hdl=None, rank=0, world=2, slot=slot, seq=0,
+                     peers=torch.tensor([mine.data_ptr(), peer.data_ptr()], dtype=torch.int64, device=dev))
+        orig = contra._p2p_exchange
+        contra._p2p_exchange = lambda group, d, n: state
+        try:
+            bank, ptr, caps = make_bank(spec)
+            rep = g["rep"].clone().requires_grad_(True)
+            _, loss = arco_b200.compute_contra_memobank_loss(rep, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"], g["low_mask"],
+                                                             g["high_mask"], bank, ptr, caps, g["rep_teacher"], delta_n=0.97, func="smc",
+                                                             num_queries=32, num_negatives=8, seed=5, process_group=object())
+            loss.backward()
+            torch.cuda.synchronize()
+        finally:
+            contra._p2p_exchange = orig
+        print("ok sharded", float(loss))
+    if only is None or "dense" in only:
+        from arco_b200.bank import DeviceMemoryBank
+        from arco_b200.similarity import dense_similarity
+        gen = torch.Generator().manual_seed(5)
+        rows = [torch.randn(200, 72, generator=gen).to(torch.bfloat16).to(torch.float32) for _ in range(2)]
+        bank = DeviceMemoryBank([[r.clone()] for r in rows], [torch.zeros(1, dtype=torch.long) for _ in range(2)], [257, 200], 72, dev,
+                                prefer_bf16=True)
+        a = torch.randn(2, 128, 72, generator=gen).to(dev).requires_grad_(True)
+        idx = torch.randint(0, 200, (2, 128, 8), generator=gen).to(torch.int32).to(dev)
+        out = dense_similarity(a, bank, [1, 0], idx)
+        out.sum().backward()
+        torch.cuda.synchronize()
+        print("ok dense", float(out.sum()))
     if only is None or "prepare" in only:
         n, c, s = 2, 4, 64 * 64
         gen = torch.Generator(device=dev).manual_seed(3)
