@@ -31,8 +31,8 @@ import torch.nn.functional as F
 
 from . import _cabi
 from .bank import DeviceMemoryBank
-from .contra import (DELTA_P, HIGH_RANK, LOW_RANK, LazyKeys, _FUNC, _GEOMETRY, _sampler_stream, _side_stream,
-                     _sparse_state)
+from .contra import (DELTA_P, HIGH_RANK, LOW_RANK, LazyKeys, _FUNC, _GEOMETRY, _PREFILL_GRAD, _PREFILL_MIN_BYTES, _sampler_stream,
+                     _side_stream, _sparse_state)
 
 
 class FeatureExtractor(nn.Module):
@@ -110,6 +110,12 @@ class _GatherRows(torch.autograd.Function):
             grad_x, prev_pix = st["sparse"]
             _cabi.check(_cabi.lib.arco_grad_scatter_sparse(d, g.data_ptr(), ctx.pix.data_ptr(), one.data_ptr(),
                                                            grad_x.data_ptr(), prev_pix.data_ptr(), sp), "arco_grad_scatter_sparse")
+        elif st.get("grad_buf") is not None:
+            # zero-filled during forward on the side stream (underneath the read-bound forward kernels): scatter only
+            grad_x = st["grad_buf"]
+            st["grad_buf"] = None                            # a second backward (retain_graph) takes the slow path
+            _cabi.check(_cabi.lib.arco_grad_scatter_add(d, g.data_ptr(), ctx.pix.data_ptr(), one.data_ptr(), grad_x.data_ptr(), sp),
+                        "arco_grad_scatter_add")
         else:
             grad_x = torch.empty(ctx.x_shape, dtype=ctx.x_dtype, device=dev)
             _cabi.check(_cabi.lib.arco_grad_scatter(d, g.data_ptr(), ctx.pix.data_ptr(), one.data_ptr(), grad_x.data_ptr(), sp),
@@ -251,6 +257,14 @@ def compute_contra_memobank_loss_from_features(
         xs = x_student.detach().contiguous()
         xt = x_teacher.detach().contiguous()
         hold = [t.contiguous() for t in (label_l, label_u, prob_l, prob_u, low_mask, high_mask)]
+        grad_buf, fill_side = None, None
+        if (x_student.requires_grad and torch.is_grad_enabled() and not sparse_grad and _PREFILL_GRAD
+                and x_student.numel() * x_student.element_size() >= _PREFILL_MIN_BYTES):
+            # the dense gradient of x_student must be zero-filled whatever the inputs are: start that now on a side stream
+            fill_side = _side_stream(dev, 1)
+            grad_buf = torch.empty(x_student.shape, dtype=cdt, device=dev)
+            fill_side.wait_stream(stream)
+            _cabi.check(lib.arco_grad_zero(d, grad_buf.data_ptr(), fill_side.cuda_stream), "arco_grad_zero")
         ptr = lambda t, n: t.data_ptr() if n else None
         _cabi.check(lib.arco_classify_plan(d, ptr(hold[0], n_lab), ptr(hold[1], n_unlab), ptr(hold[2], n_lab), ptr(hold[3], n_unlab),
                                            hold[4].data_ptr(), hold[5].data_ptr(), DELTA_P, float(delta_n), LOW_RANK, HIGH_RANK,
@@ -303,7 +317,7 @@ def compute_contra_memobank_loss_from_features(
                     "arco_anchor_gather")
         needs_grad = torch.is_grad_enabled() and (x_student.requires_grad or any(w.requires_grad for w in w_s))
         state = dict(dims=dims, bank=bank, ws=ws, proto_sums=proto_sums, idx_a=idx_a, idx_n=idx_n, pix=pix, temp=temp,
-                     debug=_debug,
+                     debug=_debug, grad_buf=grad_buf,
                      sparse=_sparse_state(bank, x_student, Cn * Q) if (sparse_grad and x_student.requires_grad
                                                                         and torch.is_grad_enabled()) else None)
         a = _GatherRows.apply(x_student, rows_x, pix, state) if (needs_grad and x_student.requires_grad) else rows_x
@@ -311,6 +325,8 @@ def compute_contra_memobank_loss_from_features(
         for w in w_s:                                        # [C*Q, D] x [D, D]: plain library products, autograd's
             a = a @ w.to(cdt).t()
         loss = _InfoNCERows.apply(a, state)
+        if fill_side is not None:
+            stream.wait_stream(fill_side)                   # from here on the buffer is ordinary main-stream memory
         bank.post_step(plan_view)
         if _debug is not None:
             _debug.update(ws=ws, layout=layout, dims=dims, proto_sums=proto_sums, proto_sums_x=proto_x, anchor_pix=pix.view(Cn, Q),
