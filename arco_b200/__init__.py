@@ -17,7 +17,7 @@ _EXPORTS = {
     "ArcoError": "_cabi", "version": "_cabi",
     "BankSlot": "bank", "DeviceMemoryBank": "bank", "synchronize_bank": "bank",
     "compute_contra_memobank_loss": "contra", "compute_contra_memobank_loss_from_logits": "contra",
-    "compute_contra_memobank_loss_from_features": "producers", "FeatureExtractor": "producers", "make_q_representation": "producers",
+    "compute_contra_memobank_loss_from_features": "producers", "FeatureExtractor": "producers", "FeatureExtractor_3d": "producers", "make_q_representation": "producers",
     "prepare_contrast_inputs": "prepare", "softmax_entropy": "prepare", "entropy_masks": "prepare",
     "dense_similarity": "similarity",
     "compute_unsupervised_loss": "stepterms", "RandTPS": "stepterms", "tps_equivariance_loss": "stepterms",

@@ -74,13 +74,51 @@ class FeatureExtractor(nn.Module):
         return self.fea4(self.trunk(fea_list))
 
 
+class FeatureExtractor_3d(nn.Module):
+    """Twin of ``model_3D.FeatureExtractor_3d`` (``model_3D.py:20-63``, used by ``train_arco_3d.py:212-213``): the same chain with
+    ``Conv3d`` / trilinear up-sampling.  Its last convolution is ``[output_dim = 16] x [256]`` -- NOT square -- so folding it into
+    the loss would make the prototype pass read the 256-channel input instead of the 16-channel output; that does not pay
+    (and with C = 2 no key is ever enqueued, trap 3), so the 3-D producers stay a module: ``forward`` only."""
+
+    def __init__(self, fea_dim=(128, 64, 32, 16, 16), output_dim=128) -> None:
+        super().__init__()
+        fea_dim = list(fea_dim)
+        if len(fea_dim) != 5:
+            raise AssertionError("input_dim is not correct")
+        cnt = fea_dim[0]
+        self.fea0 = nn.Conv3d(cnt, cnt, kernel_size=1, bias=False)
+        cnt += fea_dim[1]
+        self.fea1 = nn.Conv3d(cnt, cnt, kernel_size=1, bias=False)
+        cnt += fea_dim[2]
+        self.fea2 = nn.Conv3d(cnt, cnt, kernel_size=1, bias=False)
+        cnt += fea_dim[3]
+        self.fea3 = nn.Conv3d(cnt, cnt, kernel_size=1, bias=False)
+        cnt += fea_dim[4]
+        self.fea4 = nn.Conv3d(cnt, output_dim, kernel_size=1, bias=False)
+
+    def trunk(self, fea_list):
+        f0, f1, f2, f3, f4 = fea_list[:5]
+        up = lambda t, ref: F.interpolate(t, size=ref.shape[-3:], mode="trilinear", align_corners=True)
+        x = self.fea0(f0) + f0
+        x = torch.cat((up(x, f1), f1), dim=1)
+        x = self.fea1(x) + x
+        x = torch.cat((up(x, f2), f2), dim=1)
+        x = self.fea2(x) + x
+        x = torch.cat((up(x, f3), f3), dim=1)
+        x = self.fea3(x) + x
+        return torch.cat((up(x, f4), f4), dim=1)
+
+    def forward(self, fea_list):
+        return self.fea4(self.trunk(fea_list))
+
+
 def make_q_representation(dim: int = 256 + 128 + 64 + 32 + 16) -> nn.Sequential:
     """``train_arco_2d.py:231-234``."""
     return nn.Sequential(nn.Conv2d(dim, dim, kernel_size=1, bias=False), nn.Conv2d(dim, dim, kernel_size=1, bias=False))
 
 
 def _w2d(w: torch.Tensor, D: int, name: str) -> torch.Tensor:
-    if w.dim() == 4 and tuple(w.shape[2:]) == (1, 1):
+    if w.dim() in (4, 5) and all(int(k) == 1 for k in w.shape[2:]):       # Conv2d / Conv3d 1x1(x1) weight
         w = w.reshape(w.shape[0], w.shape[1])
     if tuple(w.shape) != (D, D):
         raise ValueError(f"{name} must be a bias-free 1x1 convolution weight [{D},{D}] or [{D},{D},1,1], got {tuple(w.shape)}")

@@ -233,3 +233,27 @@ def producer_inputs(case, step=0):
     return dict(w_q_fe=w_q_fe, w_k_fe=w_k_fe, w_q_rep=w_q_rep,
                 maps_l=maps(spec.n_lab), maps_u=maps(spec.n_unlab),
                 maps_l_teacher=maps(spec.n_lab), maps_u_teacher=maps(spec.n_unlab))
+
+
+def producer_inputs_3d():
+    """Inputs of the 3-D producers twin check: the 3-D trainer's channel plan [128, 64, 32, 16, 16] -> 256 -> output_dim 16
+    (train_arco_3d.py:212-213) on a tiny pyramid (1 .. 8 voxels per axis), exact integer-derived values."""
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(733)
+    fea = [128, 64, 32, 16, 16]
+
+    def tri(shape, scale):
+        a = rs.randint(-256, 257, size=shape).astype(np.int32) + rs.randint(-256, 257, size=shape).astype(np.int32)
+        return torch.from_numpy((a.astype(np.float32) * np.float32(scale)).astype(np.float32))
+
+    ws, cnt = [], 0
+    for i in range(5):
+        cnt += fea[i]
+        out = cnt if i < 4 else 16
+        ws.append(tri((out, cnt), 2.0 ** -12))
+    w_rep = [tri((16, 16), 2.0 ** -9), tri((16, 16), 2.0 ** -9)]
+    sizes = [1, 2, 4, 8, 8]
+    maps = [torch.from_numpy((rs.randint(-256, 257, size=(2, fea[i], sizes[i], sizes[i], sizes[i])).astype(np.float32)
+                              / np.float32(128.0)).astype(np.float32)) for i in range(5)]
+    return dict(w_fe=ws, w_rep=w_rep, maps=maps)

@@ -30,7 +30,7 @@ nn.Module.cuda = lambda self, *a, **k: self
 
 import loss_helper_3d as ref2d                       # noqa: E402
 from arco_b200.synth import exact_case, make_bank   # noqa: E402
-from cases import PRODUCER_CASES, producer_inputs   # noqa: E402
+from cases import PRODUCER_CASES, producer_inputs, producer_inputs_3d   # noqa: E402
 
 MODEL = "/root/reference/code/model_2D.py"
 TRAINER = "/root/reference/code/train_arco_2d.py"
@@ -129,6 +129,30 @@ def run(case):
     return out
 
 
+def run_3d():
+    """model_3D.FeatureExtractor_3d (model_3D.py:20-63) with the 3-D trainer's channel plan and q_representation
+    (train_arco_3d.py:206-213): output samples for the twin module."""
+    lines = open("/root/reference/code/model_3D.py").read().split("\n")
+    d0 = next(i for i, ln in enumerate(lines) if ln.startswith("class FeatureExtractor_3d("))
+    d1 = next(i for i in range(d0 + 1, len(lines)) if lines[i] and not lines[i][0].isspace())
+    ns = dict(torch=torch, nn=nn, F=F, np=np)
+    exec(compile("\n".join(lines[d0:d1]), "<model_3D.FeatureExtractor_3d>", "exec"), ns)
+    tl = open("/root/reference/code/train_arco_3d.py").read().split("\n")
+    a = next(i for i, ln in enumerate(tl) if ln.strip().startswith("q_representation = nn.Sequential("))
+    b = next(i for i in range(a, len(tl)) if tl[i].strip().startswith("q_feature_extractor = FeatureExtractor_3d("))
+    exec(compile(textwrap.dedent("\n".join(tl[a:b + 1])), "<train_arco_3d.py:206-213>", "exec"), ns)
+    q_rep, q_fe = ns["q_representation"], ns["q_feature_extractor"]
+    x = producer_inputs_3d()
+    with torch.no_grad():
+        for i in range(5):
+            getattr(q_fe, f"fea{i}").weight.copy_(x["w_fe"][i].view_as(getattr(q_fe, f"fea{i}").weight))
+        q_rep[0].weight.copy_(x["w_rep"][0].view_as(q_rep[0].weight))
+        q_rep[1].weight.copy_(x["w_rep"][1].view_as(q_rep[1].weight))
+        fea = q_fe(x["maps"])
+        rep = q_rep(fea)
+    return dict(fea=fea.numpy().copy(), rep=rep.numpy().copy())
+
+
 def main():
     import warnings
     warnings.filterwarnings("ignore")
@@ -139,6 +163,12 @@ def main():
         spec = case["spec"]
         print(case["name"], [float(res[f"s{t}_loss"]) for t in range(spec.steps)],
               [res[f"s{t}_new_keys"].tolist() for t in range(spec.steps)], f"{os.path.getsize(path) / 1024:.0f} KB")
+
+
+    res = run_3d()
+    path = os.path.join(HERE, "producers_3d.npz")
+    np.savez_compressed(path, **res)
+    print("producers_3d", res["rep"].shape, f"{os.path.getsize(path) / 1024:.0f} KB")
 
 
 if __name__ == "__main__":

@@ -71,3 +71,24 @@ def test_feature_extractor_twin_matches_reference(case):
         assert torch.equal(q_fe.fea4(q_fe.trunk(pin["maps_u"])), q_fe(pin["maps_u"]))
     assert _rel(rep[:, ::8, ::4, ::4], gold["s0_rep_sample"]) <= 1e-6
     assert _rel(rep_t[:, ::8, ::4, ::4], gold["s0_rep_teacher_sample"]) <= 1e-6
+
+
+def test_feature_extractor_3d_twin_matches_reference():
+    """arco_b200.producers.FeatureExtractor_3d against the reference class's own output (model_3D.py:20-63, the 3-D trainer's
+    channel plan and q_representation, train_arco_3d.py:206-213)."""
+    import torch.nn as nn
+    from arco_b200.producers import FeatureExtractor_3d
+    from cases import producer_inputs_3d
+    gold = load_golden("producers_3d")
+    x = producer_inputs_3d()
+    fe = FeatureExtractor_3d([128, 64, 32, 16, 16], 16)
+    assert list(fe.state_dict().keys()) == [f"fea{i}.weight" for i in range(5)]
+    fe.load_state_dict({f"fea{i}.weight": x["w_fe"][i][:, :, None, None, None] for i in range(5)})
+    q_rep = nn.Sequential(nn.Conv3d(16, 16, kernel_size=1, bias=False), nn.Conv3d(16, 16, kernel_size=1, bias=False))
+    q_rep.load_state_dict({f"{i}.weight": x["w_rep"][i][:, :, None, None, None] for i in range(2)})
+    with torch.no_grad():
+        fea = fe(x["maps"])
+        rep = q_rep(fea)
+        assert torch.equal(fe.fea4(fe.trunk(x["maps"])), fea)
+    assert _rel(fea, gold["fea"]) <= 1e-6
+    assert _rel(rep, gold["rep"]) <= 1e-6
