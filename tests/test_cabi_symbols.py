@@ -67,3 +67,24 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
+
+
+def test_widened_ops_refuse_cpu_tensors():
+    """The ops added for SURVEY 8(f) have no CPU / PyTorch fallback either: CPU tensors raise before anything runs."""
+    import pytest
+    import torch
+
+    import arco_b200
+    x = torch.zeros(2, 16, 8, 8)
+    lab = torch.zeros(1, 8, 8, dtype=torch.int64)
+    prob = torch.zeros(1, 4, 8, 8)
+    mask = torch.zeros(2, 1, 8, 8)
+    bank = [[torch.zeros(1, 16)] for _ in range(4)]
+    ptr = [torch.zeros(1, dtype=torch.long) for _ in range(4)]
+    w = torch.eye(16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        arco_b200.compute_contra_memobank_loss_from_features(x, x, [w, w, w], w, lab, lab, prob, prob, mask, mask, bank, ptr, [8] * 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        arco_b200.compute_contra_memobank_loss_from_logits(x, lab, lab, prob, prob, prob, 20.0, bank, ptr, [8] * 4, x)
+    with pytest.raises((RuntimeError, ValueError)):
+        arco_b200.get_revisiting_loss(torch.zeros(4, 16 * 64), x, x, topk=2)
