@@ -112,6 +112,8 @@ def _load():
         "arco_grad_scatter_add": (C.c_int, [dp, vp, vp, vp, vp, vp]),
         "arco_grad_scatter_sparse": (C.c_int, [dp, vp, vp, vp, vp, vp, vp]),
         "arco_forward": (C.c_int, [dp, C.POINTER(StepIO), bp, vp, vp]),
+        "arco_forward_replay": (C.c_int, [i32]),
+        "arco_forward_replay_stats": (C.c_int, [vp]),
         "arco_export_list": (C.c_int, [dp, i32, i32, vp, i64, vp, vp, vp]),
         "arco_bank_read": (C.c_int, [bp, i32, i32, vp, vp]),
         "arco_softmax_rows": (C.c_int, [vp, i64, i32, i64, vp, vp, vp]),

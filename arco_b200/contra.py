@@ -158,6 +158,9 @@ def _p2p_exchange(group, dev: torch.device, n: int):
     return state
 
 
+_BANK_SERIAL = 0          # banks that took the default-seed path, in creation order (deterministic across restarts)
+
+
 def _sampler_stream(seed, bank: DeviceMemoryBank, dev: torch.device):
     """(Philox seed, per-step stream id) of the in-kernel sampler.
 
@@ -166,7 +169,7 @@ def _sampler_stream(seed, bank: DeviceMemoryBank, dev: torch.device):
     Explicit ``seed=``: deterministic replay -- stream id = number of steps this bank has completed (tests, benchmarks).
     Default: behave like the reference, which CONSUMES global RNG state (Python ``random`` + torch's CPU generator,
     loss_helper_3d.py:157-177): the seed is torch's CUDA seed mixed with the process's distributed rank (DDP ranks seeded
-    alike must not draw identical index streams), and the stream id is taken from -- and advances -- the device's
+    alike must not draw identical index streams), and the stream id starts at -- and every step advances -- the device's
     default CUDA generator offset, so a resumed run that restores (or re-seeds) torch's RNG state continues (or
     replays) exactly like the reference would, instead of restarting at stream 0 whenever a bank is re-adopted."""
     if seed is not None:
@@ -176,7 +179,17 @@ def _sampler_stream(seed, bank: DeviceMemoryBank, dev: torch.device):
     off = int(gen.get_offset())
     gen.set_offset(off + 4)                                  # one Philox counter block per step, never reused
     s0 = (int(gen.initial_seed()) ^ ((rank + 1) * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
-    return s0, off // 4
+    # The stream id handed to the kernels is the generator offset AT THE BANK'S FIRST STEP; the device adds the bank's step
+    # counter.  Every later step still advances the generator (so the offset a checkpoint saves keeps growing and a resumed
+    # run's first offset lies beyond every stream this run used), but the launch parameter stays constant from step to
+    # step -- which is what lets arco_forward replay its launch sequence as a CUDA graph (forward.cu).
+    # Banks that live side by side (two loss heads) get different Philox keys: their stream ids overlap by construction.
+    base = bank.__dict__.get("_stream_base")
+    if base is None or base[0] != s0:
+        global _BANK_SERIAL
+        _BANK_SERIAL += 1
+        base = bank.__dict__["_stream_base"] = (s0, off // 4, (s0 ^ (_BANK_SERIAL * 0xD1B54A32D192ED03)) & (2 ** 63 - 1))
+    return base[2], base[1]
 
 
 def _sparse_state(bank: DeviceMemoryBank, rep: torch.Tensor, rows: int):

@@ -106,6 +106,18 @@ __device__ __forceinline__ void classify_tail(const ClassifyParams& p, int n_cta
 }
 
 
+// tile_flagged[tile] is a bit mask: bit g is set when the 32-pixel group g of the tile holds a low-valid or key pixel, i.e.
+// something the prototype / enqueue pass has to read.  The tensor-core kernels skip whole 32- / 64-pixel steps whose bits are
+// clear (entropy masks are spatially coherent on real images); every consumer treats 0 as "skip the tile".
+// With 4 consecutive pixels per thread a warp covers groups 4*warp .. 4*warp+3 (8 lanes each).
+__device__ __forceinline__ uint32_t group_bits4(uint32_t ballot, int warp) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if ((ballot >> (8 * k)) & 0xffu) bits |= 1u << (4 * warp + k);
+    return bits;
+}
+
 template <int NV>
 struct PixVec;
 template <>
@@ -253,6 +265,7 @@ __global__ void __launch_bounds__(256, 4) classify_kernel(ClassifyParams p) {
         }
 
         uint32_t packed = 0;
+        bool needed = false;                                 // this thread holds a pixel the prototype pass must read
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             uint32_t code = 0;
@@ -262,14 +275,19 @@ __global__ void __launch_bounds__(256, 4) classify_kernel(ClassifyParams p) {
             packed |= code << (8 * v);
             // warp-aggregated counting: one shared atomic per distinct code value in the warp
             const uint32_t flags = code & (CODE_LV | CODE_ANCHOR | CODE_KEY);
+            needed |= (flags & (CODE_LV | CODE_KEY)) != 0;
             const uint32_t peers = __match_any_sync(0xffffffffu, code);
             if (flags && (__ffs(peers) - 1) == (tid & 31)) {
                 const uint32_t n = __popc(peers), c = code & CODE_CLS_MASK;
                 if (flags & CODE_LV) atomicAdd(&s_lv[c], n);
                 if (flags & CODE_ANCHOR) atomicAdd(&s_anchor[c], n);
                 if (flags & CODE_KEY) atomicAdd(&s_key[c], n);
-                if (flags & (CODE_LV | CODE_KEY)) atomicAdd(&s_flagged, n);
             }
+        }
+        {
+            const uint32_t bal = __ballot_sync(0xffffffffu, needed);
+            if ((tid & 31) == 0 && bal)
+                atomicOr(&s_flagged, NV == 4 ? group_bits4(bal, tid >> 5) : 1u << ((tid >> 5) + 8 * pass));
         }
         if (in_range) {
             const int64_t gp = (int64_t)b * S + s;
@@ -423,8 +441,8 @@ __global__ void __launch_bounds__(256) classify_small_kernel(ClassifyParams p) {
         w[4] = C > 4 ? __reduce_add_sync(0xffffffffu, (uint32_t)(n_an >> 32)) : 0u;
         w[5] = C > 4 ? __reduce_add_sync(0xffffffffu, (uint32_t)(n_key >> 32)) : 0u;
         const uint32_t st = __reduce_or_sync(0xffffffffu, status);
+        const uint32_t bal = __ballot_sync(0xffffffffu, (n_lv | n_key) != 0ull);
         if ((tid & 31) == 0) {
-            uint32_t flagged = 0;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int sh = 8 * (c & 3), hi = c >> 2;
@@ -432,9 +450,8 @@ __global__ void __launch_bounds__(256) classify_small_kernel(ClassifyParams p) {
                 if (a) atomicAdd(&s_lv[c], a);
                 if (bq) atomicAdd(&s_anchor[c], bq);
                 if (k) atomicAdd(&s_key[c], k);
-                flagged += a + k;
             }
-            if (flagged) atomicAdd(&s_flagged, flagged);
+            if (bal) atomicOr(&s_flagged, group_bits4(bal, tid >> 5));
             if (st) atomicOr(&s_status, st);
         }
     }

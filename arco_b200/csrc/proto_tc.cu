@@ -106,10 +106,12 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
         while (t < p.NT && p.tile_flagged[t] == 0) t += ngrid;
         return t;
     };
-    auto steps_in_tile = [&](int t) {
-        const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
-        const int64_t left = S - s_tile;
-        return (int)min((int64_t)(ARCO_TILE / TC_KPX), (left + TC_KPX - 1) / TC_KPX);
+    // 64-pixel steps of tile t that hold a low-valid or key pixel (classify.cu writes one bit per 32-pixel group; bit 2*st of
+    // the result stands for step st).  Steps without one are never loaded: on real images the entropy masks are spatially
+    // coherent and whole runs of an unlabelled image drop out; pixels past the end of an image are never flagged.
+    auto step_mask = [&](int t) {
+        const uint32_t f = p.tile_flagged[t];
+        return (f | (f >> 1)) & 0x55555555u;
     };
 
     if (warp == 0) {
@@ -118,8 +120,8 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
             for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
                 const int b = t / p.tpi;
                 const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
-                const int ns = steps_in_tile(t);
-                for (int st = 0; st < ns; ++st, ++it) {
+                for (uint32_t m = step_mask(t); m; m &= m - 1, ++it) {
+                    const int st = (__ffs(m) - 1) >> 1;
                     const int s = it % NST;
                     bar_wait(&empty_bar[s], ((it / NST) & 1) ^ 1);
                     TC_STAMP(0, it);
@@ -134,8 +136,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
-                const int ns = steps_in_tile(t);
-                for (int st = 0; st < ns; ++st, ++it) {
+                for (uint32_t m = step_mask(t); m; m &= m - 1, ++it) {
                     const int s = it % NST;
                     const uint32_t ph = (it / NST) & 1;
                     bar_wait(&full_bar[s], ph);
@@ -181,14 +182,14 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
         };
         pre = fetch(t);
         for (; t < p.NT;) {
-            const int ns = steps_in_tile(t);
             asm volatile("bar.sync 1, 64;" ::: "memory");        // every builder is done with the previous tile's codes
             reinterpret_cast<uint4*>(s_codes)[at] = pre;
             if (at < p.C) s_run[at] = p.off_key[(int64_t)at * (p.NT + 1) + t];
             const int t_next = next_tile(t + ngrid);
             pre = fetch(t_next);
             asm volatile("bar.sync 1, 64;" ::: "memory");
-            for (int st = 0; st < ns; ++st, ++it) {
+            for (uint32_t m = step_mask(t); m; m &= m - 1, ++it) {
+                const int st = (__ffs(m) - 1) >> 1;
                 const int s = it % NST;
                 const uint32_t ph = (it / NST) & 1;
                 unsigned char* btile = base + (size_t)s * stage_bytes + NDB * TC_BOX_BYTES;
@@ -242,8 +243,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
         const uint32_t t_off = (uint32_t)(ct >> 3) * 1024u + (uint32_t)(ct & 7) * 128u;
         uint32_t it = 0;
         for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
-            const int ns = steps_in_tile(t);
-            for (int st = 0; st < ns; ++st, ++it) {
+            for (uint32_t m = step_mask(t); m; m &= m - 1, ++it) {
                 const int s = it % NST;
                 const uint32_t ph = (it / NST) & 1;
                 const uint32_t stage_a = s32(base + (size_t)s * stage_bytes) + t_off;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256, 1) proto_tc_kernel(const __grid_constant_
     __syncwarp();
     if (warp < 4) {
         uint32_t n_it = 0;
-        for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) n_it += steps_in_tile(t);
+        for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) n_it += __popc(step_mask(t));
         if (n_it > 0) {
             bar_wait(&done_bar, 0);
             if (tid == 0) TC_CTA(2);

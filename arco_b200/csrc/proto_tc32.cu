@@ -124,14 +124,12 @@ __global__ void __launch_bounds__(384, 1) proto_tc32_kernel(const __grid_constan
         while (t < p.NT && p.tile_flagged[t] == 0) t += ngrid;
         return t;
     };
-    auto steps_in_tile = [&](int t) {
-        const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
-        const int64_t left = S - s_tile;
-        return (int)min((int64_t)(ARCO_TILE / T32_KPX), (left + T32_KPX - 1) / T32_KPX);
-    };
+    // 32-pixel steps of tile t that hold a low-valid or key pixel: exactly the bits classify.cu wrote.  Steps without one are
+    // never loaded (coherent entropy masks drop whole runs of an unlabelled image); pixels past the image end are never flagged.
+    auto step_mask = [&](int t) { return p.tile_flagged[t]; };
     auto total_steps = [&]() {
         uint32_t n = 0;
-        for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) n += steps_in_tile(t);
+        for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) n += __popc(step_mask(t));
         return n;
     };
 
@@ -141,8 +139,8 @@ __global__ void __launch_bounds__(384, 1) proto_tc32_kernel(const __grid_constan
             for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
                 const int b = t / p.tpi;
                 const int64_t s_tile = (int64_t)(t % p.tpi) * ARCO_TILE;
-                const int ns = steps_in_tile(t);
-                for (int st = 0; st < ns; ++st, ++it) {
+                for (uint32_t m = step_mask(t); m; m &= m - 1, ++it) {
+                    const int st = __ffs(m) - 1;
                     const int s = it % NST;
                     bar_wait(&empty_bar[s], ((it / NST) & 1) ^ 1);
                     T32_STAMP(0, it);
@@ -225,7 +223,6 @@ __global__ void __launch_bounds__(384, 1) proto_tc32_kernel(const __grid_constan
         uint4 pre0, pre1;
         fetch(t, pre0, pre1);
         for (; t < p.NT;) {
-            const int ns = steps_in_tile(t);
             __syncwarp();
             reinterpret_cast<uint4*>(s_codes)[2 * lane] = pre0;
             reinterpret_cast<uint4*>(s_codes)[2 * lane + 1] = pre1;
@@ -233,7 +230,8 @@ __global__ void __launch_bounds__(384, 1) proto_tc32_kernel(const __grid_constan
             const int t_next = next_tile(t + ngrid);
             fetch(t_next, pre0, pre1);
             __syncwarp();
-            for (int st = 0; st < ns; ++st, ++it) {
+            for (uint32_t m = step_mask(t); m; m &= m - 1, ++it) {
+                const int st = __ffs(m) - 1;
                 const int s = it % NST;
                 const uint32_t ph = (it / NST) & 1;
                 unsigned char* btile = base + (size_t)s * stage_bytes + NDB * T32_BOX_BYTES;
@@ -276,8 +274,7 @@ __global__ void __launch_bounds__(384, 1) proto_tc32_kernel(const __grid_constan
         const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t it = 0;
         for (int t = next_tile(blockIdx.x); t < p.NT; t = next_tile(t + ngrid)) {
-            const int ns = steps_in_tile(t);
-            for (int st = 0; st < ns; ++st, ++it) {
+            for (uint32_t m = step_mask(t); m; m &= m - 1, ++it) {
                 const int s = it % NST, l = it % NLO;
                 const uint32_t ph = (it / NST) & 1;
                 const uint32_t stage_a = s32(base + (size_t)s * stage_bytes) + t_off;

@@ -40,6 +40,7 @@ class CaseSpec:
     label_mode: str = "iid"                   # iid | blocky | absent:<c> | single:<c> | noanchor:<c>
     ignore_frac: float = 0.05
     mask_frac: float = 0.2
+    mask_mode: str = "iid"                    # iid | coherent (one smooth entropy-like field, low = bottom / high = top mask_frac of it)
     steps: int = 1
     dtype: str = "f32"                        # f32 | bf16 (representation tensors)
     seed: int = 1337
@@ -102,6 +103,28 @@ def _labels(rs: np.random.RandomState, spec: CaseSpec) -> np.ndarray:
     return lab
 
 
+def _coherent_masks(rs: np.random.RandomState, shape, frac: float, window: int = 15):
+    """Spatially coherent low / high masks the way the trainers derive them (train_arco_2d.py:356-392): ONE entropy-like
+    field per image, low = its bottom ``frac`` quantile, high = its top ``frac`` quantile (disjoint blobs instead of iid
+    pixels).  The field is a box sum of integer noise and the thresholds are integer order statistics, so the masks are the
+    same bits on every machine."""
+    field = rs.randint(-256, 257, size=shape).astype(np.int64)
+    for ax in 3 * list(range(1, len(shape))):                 # three box passes per axis ~ a Gaussian: clean blobs
+        n = shape[ax]
+        w = min(window, n)
+        pad = [(0, 0)] * len(shape)
+        pad[ax] = (w // 2, w - 1 - w // 2)
+        c = np.cumsum(np.pad(field, pad, mode="wrap"), axis=ax)
+        c = np.concatenate([np.zeros_like(np.take(c, [0], axis=ax)), c], axis=ax)
+        field = np.take(c, np.arange(w, w + n), axis=ax) - np.take(c, np.arange(0, n), axis=ax)
+    flat = np.sort(field.reshape(shape[0], -1), axis=1)
+    k = max(1, int(frac * flat.shape[1]))
+    expand = (slice(None),) + (None,) * (len(shape) - 1)
+    lo_thr = flat[:, k - 1][expand]
+    hi_thr = flat[:, flat.shape[1] - k][expand]
+    return field <= lo_thr, field >= hi_thr
+
+
 def onehot_relu(lab: torch.Tensor, classes: int) -> torch.Tensor:
     """What the trainers feed the loss: relu'd labels scattered to one-hot, as int64
     (train_arco_2d.py:349-350,394 ``label_onehot(...).cuda().long()``)."""
@@ -127,8 +150,13 @@ def exact_case(spec: CaseSpec, step: int = 0) -> dict:
     rep = _exact_normal_like(rs, (B, D) + sp)
     rep_t = _exact_normal_like(rs, (B, D) + sp)
     valid = (lab >= 0)
-    low = (rs.random_sample(lab.shape) < spec.mask_frac) & valid
-    high = (rs.random_sample(lab.shape) < spec.mask_frac) & valid
+    if spec.mask_mode == "coherent":
+        low, high = _coherent_masks(rs, lab.shape, spec.mask_frac)
+        low &= valid
+        high &= valid
+    else:
+        low = (rs.random_sample(lab.shape) < spec.mask_frac) & valid
+        high = (rs.random_sample(lab.shape) < spec.mask_frac) & valid
     low[: spec.n_lab] = valid[: spec.n_lab]
     high[: spec.n_lab] = valid[: spec.n_lab]
 
@@ -187,8 +215,24 @@ WORKLOADS = {
 }
 
 
-def bench_inputs(name: str, device, seed: int = 1337, blocky: bool = False, n_lab=None, n_unlab=None):
-    """Device-resident synthetic batch for workload ``name``.  Returns (spec, tensors)."""
+def _coherent_field(shape, device, g, window: int = 31):
+    """Smooth entropy-like field per image (box-filtered N(0,1) noise): thresholding it at its quantiles gives blob-shaped
+    masks like the entropy masks of a real prediction, instead of iid pixels."""
+    import torch.nn.functional as F
+    f = torch.randn((shape[0], 1) + tuple(shape[1:]), device=device, generator=g)
+    nd = len(shape) - 1
+    w = [min(window if nd == 2 else 9, s) | 1 for s in shape[1:]]
+    w = [k if k <= s else k - 2 for k, s in zip(w, shape[1:])]
+    pool = F.avg_pool2d if nd == 2 else F.avg_pool3d
+    for _ in range(3):                                        # three box passes ~ a Gaussian: clean blobs, scale ~ 50 pixels
+        f = pool(f, kernel_size=w, stride=1, padding=[k // 2 for k in w], count_include_pad=False)
+    return f[:, 0]
+
+
+def bench_inputs(name: str, device, seed: int = 1337, blocky: bool = False, n_lab=None, n_unlab=None, coherent: bool = False):
+    """Device-resident synthetic batch for workload ``name``.  Returns (spec, tensors).  ``coherent``: the unlabelled images'
+    low / high masks are the bottom / top 20 % of ONE smooth field per image (how the trainers derive them from the entropy,
+    train_arco_2d.py:356-392) instead of two independent Bernoulli(0.2) draws per pixel."""
     cfg = dict(WORKLOADS[name])
     if n_lab is not None:
         cfg["n_lab"] = n_lab
@@ -211,8 +255,17 @@ def bench_inputs(name: str, device, seed: int = 1337, blocky: bool = False, n_la
     ign[: spec.n_lab] = False
     lab = torch.where(ign, torch.full_like(lab, -1), lab)
     valid = lab >= 0
-    low = (torch.rand(lab.shape, device=device, generator=g) < 0.2) & valid
-    high = (torch.rand(lab.shape, device=device, generator=g) < 0.2) & valid
+    if coherent:
+        f = _coherent_field(lab.shape, device, g)
+        flat = f.reshape(B, -1).float()
+        k = max(1, int(0.2 * flat.shape[1]))
+        srt = flat.sort(dim=1).values
+        ex = (slice(None),) + (None,) * len(sp)
+        low = (f <= srt[:, k - 1][ex]) & valid
+        high = (f >= srt[:, flat.shape[1] - k][ex]) & valid
+    else:
+        low = (torch.rand(lab.shape, device=device, generator=g) < 0.2) & valid
+        high = (torch.rand(lab.shape, device=device, generator=g) < 0.2) & valid
     low[: spec.n_lab] = valid[: spec.n_lab]
     high[: spec.n_lab] = valid[: spec.n_lab]
     prob = torch.softmax(torch.randn((B, C) + sp, device=device, generator=g), dim=1)

@@ -75,7 +75,7 @@ typedef struct arco_ws_layout {
     int64_t total_bytes;
     int64_t plan;          /* arco_plan                                   */
     int64_t codes;         /* uint8  [B*S]   packed per-pixel class/flags */
-    int64_t tile_flagged;  /* uint32 [NT]                                 */
+    int64_t tile_flagged;  /* uint32 [NT]: bit g = 32-pixel group g of the tile holds a low-valid or key pixel */
     int64_t cnt_anchor;    /* uint32 [C][NT]                              */
     int64_t cnt_key;       /* uint32 [C][NT]                              */
     int64_t off_anchor;    /* uint32 [C][NT+1] exclusive scan             */
@@ -299,6 +299,17 @@ typedef struct arco_step_io {
  * arco_sample_if_replanned -> InfoNCE, still one call and no NCCL. */
 ARCO_API int arco_forward(const arco_dims* dims, const arco_step_io* io, const arco_bank* bank, void* workspace,
                           void* stream);
+
+/* Replay cache of arco_forward.  The second time a thread passes the byte-identical (dims, io, bank, workspace) tuple on a
+ * device, arco_forward captures its launch sequence (6-7 kernels on three streams) into a CUDA graph
+ * and from then on that tuple costs one cudaGraphLaunch; any other tuple, a stream that is already capturing and the
+ * multi-GPU step run the launches directly.  Results are identical either way (same kernels, same parameters).
+ * Only steps whose representation tensor is <= 512 MiB replay (the host-bound ones; an HBM-bound step does not hide a graph
+ * launch's start-up cost), unless forced.  arco_forward_replay(1 / 0 / 2) switches the cache on / off / on for every size
+ * for the process and returns whether it was on (-1 only queries; default 1, ARCO_FWD_GRAPH=0 / 2 in the environment).  arco_forward_replay_stats fills, for the calling
+ * thread and current device, stats[0] = steps replayed, stats[1] = graphs captured, stats[2] = first sightings run directly. */
+ARCO_API int arco_forward_replay(int32_t on);
+ARCO_API int arco_forward_replay_stats(int64_t* stats);
 
 /* Parity / inspection helpers (not on the hot path). */
 /* kind: 0 anchor candidates, 1 negative keys, 2 low-valid; writes the raster-ordered flat pixel ids of

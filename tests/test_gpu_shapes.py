@@ -28,6 +28,18 @@ SPECS = [
     CaseSpec("only_unlabelled", 0, 3, 5, (32, 32), 64, queries=16, negatives=8, bank_init="fill:60", caps=[80] * 5),
     CaseSpec("only_labelled", 3, 0, 4, (32, 32), 64, queries=16, negatives=8, bank_init="fill:60", caps=[80] * 4),
     CaseSpec("one_negative", 2, 2, 4, (32, 32), 32, queries=7, negatives=1, bank_init="fill:60", caps=[80] * 4),
+    # spatially coherent entropy masks: whole 32- / 64-pixel steps of the unlabelled images hold nothing the prototype pass needs
+    # and are skipped by the tensor-core kernels (tile_flagged is a per-32-pixel bit mask)
+    CaseSpec("tc_bf16_coherent", 1, 2, 4, (64, 64), 128, queries=16, negatives=8, dtype="bf16", bank_init="fill:60", caps=[90] * 4,
+             mask_mode="coherent", mask_frac=0.1),
+    CaseSpec("tc_bf16_coherent_ragged", 1, 2, 5, (40, 52), 496, queries=16, negatives=8, dtype="bf16", bank_init="fill:60", caps=[90] * 5,
+             mask_mode="coherent", mask_frac=0.15),
+    CaseSpec("tc_bf16_coherent_3d", 0, 2, 5, (32, 32, 16), 64, queries=16, negatives=8, dtype="bf16", bank_init="fill:60", caps=[90] * 5,
+             mask_mode="coherent"),
+    CaseSpec("tc32_f32_coherent", 1, 2, 5, (64, 64), 256, queries=8, negatives=8, bank_init="fill:40", caps=[64] * 5,
+             mask_mode="coherent", mask_frac=0.1),
+    CaseSpec("tc32_f32_coherent_ragged", 0, 2, 19, (36, 44), 132, queries=8, negatives=8, bank_init="fill:40", caps=[64] * 19,
+             mask_mode="coherent", mask_frac=0.15),
     CaseSpec("overflow_tc", 1, 2, 5, (32, 32), 128, queries=8, negatives=8, dtype="bf16", bank_init="fill:10", caps=[16, 12, 12, 12, 12],
              mask_frac=0.9, steps=2),
 ]
