@@ -26,6 +26,11 @@ SPECS = [
     CaseSpec("scalar_odd", 1, 2, 5, (9, 7, 5), 24, queries=12, negatives=3, bank_init="fill:50", caps=[64] * 5),
     CaseSpec("overflow_tc", 1, 2, 5, (32, 32), 128, queries=8, negatives=8, dtype="bf16", bank_init="fill:10",
              caps=[16, 12, 12, 12, 12], mask_frac=0.9, steps=2),
+    # coherent entropy masks: the tensor-core prototype kernels skip the 32- / 64-pixel steps without a needed pixel
+    CaseSpec("tc_bf16_coherent", 1, 2, 4, (64, 64), 128, queries=16, negatives=8, dtype="bf16", bank_init="fill:60", caps=[90] * 4,
+             mask_mode="coherent", mask_frac=0.1),
+    CaseSpec("tc32_coherent", 0, 2, 19, (36, 44), 132, queries=8, negatives=8, bank_init="fill:40", caps=[64] * 19,
+             mask_mode="coherent", mask_frac=0.15),
     CaseSpec("grid_sampler", 2, 2, 4, (48, 48), 32, queries=64, negatives=64, bank_init="fill:400", caps=[500] * 4, func="asmc"),
 ]
 
@@ -55,6 +60,26 @@ def main():
                 torch.cuda.synchronize()
                 assert torch.isfinite(loss)
         print("ok", spec.name, float(loss))
+    if only is None or "replay" in only:
+        # arco_forward's replay cache: direct launches, capture on the second sighting, graph launches afterwards
+        spec = CaseSpec("replay", 1, 2, 4, (32, 32), 64, queries=16, negatives=8, bank_init="fill:60", caps=[80] * 4)
+        bank, ptr, caps = make_bank(spec)
+        g = {k: v.to(dev) for k, v in exact_case(spec, 0).items()}
+        rep = g["rep"].clone().requires_grad_(True)
+        for step in range(8):
+            rep.grad = None
+            _, loss = arco_b200.compute_contra_memobank_loss(
+                rep, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"], g["low_mask"], g["high_mask"], bank, ptr, caps,
+                g["rep_teacher"], delta_n=spec.delta_n, func=spec.func, num_queries=spec.queries, num_negatives=spec.negatives,
+                temp=spec.temp, seed=9)
+            loss.backward()
+            torch.cuda.synchronize()
+        import ctypes
+        st = (ctypes.c_int64 * 3)()
+        arco_b200._cabi.lib.arco_forward_replay_stats(st)
+        # (under compute-sanitizer the allocator never hands back the same workspace address, so every step is a first
+        # sighting and nothing is captured here; tests/test_gpu_replay.py asserts the captures and replays)
+        print("ok replay", float(loss), "replayed / captured / direct:", list(st))
     if only is None or "producers" in only:
         # in-place tcgen05 key-row transform (bf16 kind::f16 and fp32 kind::tf32 x3), anchors as rows
         from arco_b200 import producers
