@@ -17,7 +17,7 @@ TILE = 1024
 F32, BF16 = 0, 1
 LABEL_ONEHOT_I64, LABEL_INDEX_I64 = 0, 1
 FUNC_UNIFORM, FUNC_SMC, FUNC_ASMC = 0, 1, 2
-ST_MULTI_HOT, ST_LABEL_RANGE, ST_INDEX_RANGE, ST_KEYS_DROPPED, ST_EXCHANGE_TIMEOUT = 1, 2, 4, 8, 0x80000000
+ST_MULTI_HOT, ST_LABEL_RANGE, ST_INDEX_RANGE, ST_KEYS_DROPPED, ST_EXCHANGE_DESYNC, ST_EXCHANGE_TIMEOUT = 1, 2, 4, 8, 16, 0x80000000
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ARCO_B200_LIB") or os.path.join(_HERE, "lib", "libarco_b200.so")   # override: A/B builds

@@ -276,6 +276,9 @@ class DeviceMemoryBank:
         if status & _cabi.ST_KEYS_DROPPED:
             raise ValueError("negative keys were counted but not enqueued: the C<=3 register prototype kernel needs "
                              "low_rank >= num_classes")
+        if status & _cabi.ST_EXCHANGE_DESYNC:
+            raise RuntimeError("multi-GPU prototype exchange: the device's step word and the slot of this step disagree "
+                               "(a replayed step ran out of order)")
         if status & _cabi.ST_EXCHANGE_TIMEOUT:
             raise RuntimeError("multi-GPU prototype exchange timed out waiting for a peer")
 

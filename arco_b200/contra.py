@@ -93,6 +93,9 @@ EXCHANGE_PLANE = None    # "nvlink-p2p" | "nccl": which data plane the last mult
 _log = logging.getLogger("arco_b200")
 
 
+_XCHG_STEP_WORD = 1 << 63      # arco_exchange.seq bit 63: the exchange buffer carries a step word behind its flags
+
+
 def _agree(flag: bool, group, dev: torch.device) -> bool:
     """True iff ``flag`` is true on EVERY rank (one MIN all-reduce)."""
     t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
@@ -131,14 +134,14 @@ def _p2p_exchange(group, dev: torch.device, n: int):
     if _agree(symm is not None, group, dev):
         try:
             slot = (n + 63) // 64 * 64
-            buf = symm.empty(2 * slot + 64, dtype=torch.float64, device=dev)
+            buf = symm.empty(2 * slot + 64 + 8, dtype=torch.float64, device=dev)     # two slots, 64 flags, the step word
             buf.zero_()
             hdl = symm.rendezvous(buf, group)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
             if len(ptrs) == world and all(ptrs):
                 torch.cuda.synchronize(dev)
                 torch.distributed.barrier(group)            # every rank's flags are zero before anyone signals
-                state = dict(buf=buf, hdl=hdl, rank=rank, world=world, slot=slot, seq=0,
+                state = dict(buf=buf, hdl=hdl, rank=rank, world=world, slot=slot, seq=0, seq_flags=_XCHG_STEP_WORD,
                              peers=torch.tensor(ptrs, dtype=torch.int64, device=dev))
             else:
                 why = "rendezvous returned an incomplete peer pointer table"
@@ -300,7 +303,8 @@ class _ContraLoss(torch.autograd.Function):
             if p2p is not None:
                 global P2P_EXCHANGE_USED
                 P2P_EXCHANGE_USED = True
-                _cabi.check(lib.arco_proto_allreduce_p2p(d, p2p["peers"].data_ptr(), p2p["rank"], p2p["world"], p2p["seq"],
+                _cabi.check(lib.arco_proto_allreduce_p2p(d, p2p["peers"].data_ptr(), p2p["rank"], p2p["world"],
+                                                         p2p["seq"] | p2p.get("seq_flags", 0),
                                                          p2p["slot"], proto_sums.data_ptr(), wsp, sp),
                             "arco_proto_allreduce_p2p")
             else:
@@ -417,7 +421,7 @@ class _ContraLoss(torch.autograd.Function):
             p2p["seq"] += 1
             io.exchange_peers = p2p["peers"].data_ptr()
             io.exchange_local = p2p["buf"].data_ptr() + (p2p["seq"] & 1) * p2p["slot"] * 8
-            io.exchange_seq, io.exchange_slot = p2p["seq"], p2p["slot"]
+            io.exchange_seq, io.exchange_slot = p2p["seq"] | p2p.get("seq_flags", 0), p2p["slot"]
             io.exchange_rank, io.exchange_world = p2p["rank"], p2p["world"]
         _cabi.check(_cabi.lib.arco_forward(C.byref(dims), C.byref(io), C.byref(bank.c_struct), base, sp), "arco_forward")
         plan_view = buf[layout.plan: layout.plan + C.sizeof(_cabi.Plan)]

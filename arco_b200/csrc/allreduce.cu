@@ -32,13 +32,16 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
 }
 
 // peer_base[r]: this allocation as mapped for rank r (r == rank: the local one).  Layout in doubles:
-// [slot 0: n][slot 1: n][flags: ARCO_P2P_MAX_WORLD u64, one per source rank]
+// [slot 0: n][slot 1: n][flags: 64 u64, one per source rank][step word: u64, present when seq carries ARCO_XCHG_STEP_WORD]
 __global__ void __launch_bounds__(1024) proto_allreduce_p2p_kernel(const unsigned long long* __restrict__ peer_base, int rank, int world,
                                                                    unsigned long long seq, int n, int64_t n_pad, double* __restrict__ out,
                                                                    uint32_t* status) {
     const int tid = threadIdx.x;
-    const int64_t slot = (int64_t)(seq & 1ull) * n_pad;
     const int64_t flag_off = 2 * n_pad;
+    if ((seq & ARCO_XCHG_STEP_WORD) && tid == 0)              // keep the buffer's step word current (see arco_exchange.seq)
+        *(reinterpret_cast<unsigned long long*>(peer_base[rank]) + flag_off + 64) = seq & ARCO_XCHG_SEQ_MASK;
+    seq &= ARCO_XCHG_SEQ_MASK;
+    const int64_t slot = (int64_t)(seq & 1ull) * n_pad;
     __threadfence_system();                                   // the prototype kernel's sums (previous launch) before the flag
     if (tid < world && tid != rank)
         st_release_sys(reinterpret_cast<unsigned long long*>(peer_base[tid]) + flag_off + rank, seq);
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(1024) proto_allreduce_p2p_kernel(const unsigne
 extern "C" int arco_proto_allreduce_p2p(const arco_dims* dims, const uint64_t* peer_base_dev, int32_t rank, int32_t world, uint64_t seq,
                                         int64_t slot_doubles, double* proto_sums_out, void* workspace, void* stream) {
     ARCO_REQUIRE(dims && peer_base_dev && proto_sums_out && workspace, "arco_proto_allreduce_p2p: NULL argument");
-    ARCO_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && seq > 0, "arco_proto_allreduce_p2p: bad rank / world / sequence");
+    ARCO_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && (seq & ARCO_XCHG_SEQ_MASK) > 0 &&
+                     !(seq & ARCO_XCHG_SEQ_FROM_DEVICE), "arco_proto_allreduce_p2p: bad rank / world / sequence");
     const int n = dims->classes * (dims->feat + 1);
     ARCO_REQUIRE(slot_doubles >= n, "arco_proto_allreduce_p2p: slot smaller than C*(D+1)");
     arco_ws_layout L;

@@ -101,8 +101,9 @@ static int forward_launches(const arco_dims* dims, const arco_step_io* io, const
 // the second time the exact same (dims, arco_step_io, arco_bank, workspace) tuple is seen, the launch sequence above is
 // captured into a CUDA graph, instantiated once, and from then on a step is ONE cudaGraphLaunch.
 // Any difference in any byte of the tuple is a different key (a miss runs the launches directly); a stream that is already
-// being captured (torch.cuda.graph around the whole trainer step) and the multi-GPU step (its exchange sequence number is a
-// launch parameter) always run the launches directly.  ARCO_FWD_GRAPH=0 switches the cache off.
+// being captured (torch.cuda.graph around the whole trainer step) always runs the launches directly.  The multi-GPU step
+// replays too when its exchange buffer carries a step word (ARCO_XCHG_STEP_WORD): a replayed exchange takes its sequence
+// number from that word instead of a launch parameter.  ARCO_FWD_GRAPH=0 switches the cache off.
 // ---------------------------------------------------------------------------------------------------------------------
 namespace arco {
 
@@ -151,6 +152,9 @@ static FwdKey* make_key(const arco_dims* dims, const arco_step_io* io, const arc
     if (!k) return nullptr;
     memcpy(&k->dims, dims, sizeof(arco_dims));
     memcpy(&k->io, io, sizeof(arco_step_io));
+    // multi-GPU: the sequence number is taken from the buffer's step word when the step is replayed (exchange_local already
+    // tells the slot parity apart), so it is not part of the key
+    if (k->io.exchange_peers) k->io.exchange_seq = 0;
     memcpy(&k->bank, bank, sizeof(arco_bank));
     k->workspace = workspace;
     return k;
@@ -166,7 +170,8 @@ extern "C" int arco_forward(const arco_dims* dims, const arco_step_io* io, const
     cudaStream_t main_st = (cudaStream_t)stream;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     int dev = -1;
-    if (!arco::replay_enabled() || !arco::replay_worthwhile(*dims) || io->exchange_peers != nullptr || cudaStreamIsCapturing(main_st, &cap) != cudaSuccess ||
+    const bool sharded_ok = io->exchange_peers == nullptr || (io->exchange_seq & ARCO_XCHG_STEP_WORD);
+    if (!arco::replay_enabled() || !arco::replay_worthwhile(*dims) || !sharded_ok || cudaStreamIsCapturing(main_st, &cap) != cudaSuccess ||
         cap != cudaStreamCaptureStatusNone || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
         cudaGetLastError();
         return forward_launches(dims, io, bank, workspace, main_st);
@@ -202,7 +207,10 @@ extern "C" int arco_forward(const arco_dims* dims, const arco_step_io* io, const
         free(key);
         return forward_launches(dims, io, bank, workspace, main_st);
     }
-    const int rc = forward_launches(dims, io, bank, workspace, ss->capture);
+    arco_step_io io_cap = *io;
+    if (io->exchange_peers)                                          // replayed steps read their sequence number on the device
+        io_cap.exchange_seq = ARCO_XCHG_STEP_WORD | ARCO_XCHG_SEQ_FROM_DEVICE | (io->exchange_seq & 1ull);
+    const int rc = forward_launches(dims, &io_cap, bank, workspace, ss->capture);
     cudaGraph_t graph = nullptr;
     const cudaError_t e_end = cudaStreamEndCapture(ss->capture, &graph);
     cudaGraphExec_t exec = nullptr;

@@ -282,17 +282,39 @@ __device__ __noinline__ void exchange_block(const XchgArgs p) {
     const int tid = threadIdx.x;
     const int world = p.xchg_world, rank = p.xchg_rank;
     const int n = p.C * (p.D + 1);
-    const int64_t slot = (int64_t)(p.xchg_seq & 1ull) * p.xchg_slot;
     const int64_t flag_off = 2 * p.xchg_slot;
     arco_plan* pl = p.plan;
+    // The step's sequence number: a launch parameter, or (replayed step, ARCO_XCHG_SEQ_FROM_DEVICE) the buffer's step word + 1.
+    // Either way it is stored back, so direct and replayed steps can follow each other on the same buffer.
+    unsigned long long seq = p.xchg_seq & ARCO_XCHG_SEQ_MASK;
+    if (p.xchg_seq & ARCO_XCHG_STEP_WORD) {
+        __shared__ unsigned long long s_seq;
+        if (tid == 0) {
+            unsigned long long* word = reinterpret_cast<unsigned long long*>(p.xchg_peers[rank]) + flag_off + 64;
+            if (p.xchg_seq & ARCO_XCHG_SEQ_FROM_DEVICE) {
+                const unsigned long long d = *word + 1ull;
+                if ((d ^ seq) & 1ull) {                       // the prototype pass of this step wrote the other slot
+                    atomicOr(&pl->status, (uint32_t)ARCO_ST_EXCHANGE_DESYNC);
+                    __threadfence_system();
+                    __trap();
+                }
+                seq = d;
+            }
+            *word = seq;
+            s_seq = seq;
+        }
+        __syncthreads();
+        seq = s_seq;
+    }
+    const int64_t slot = (int64_t)(seq & 1ull) * p.xchg_slot;
     __threadfence_system();                                   // the prototype kernel's sums (previous launch) before the flag
     if (tid < world && tid != rank)
-        x_st_release_sys(reinterpret_cast<unsigned long long*>(p.xchg_peers[tid]) + flag_off + rank, p.xchg_seq);
+        x_st_release_sys(reinterpret_cast<unsigned long long*>(p.xchg_peers[tid]) + flag_off + rank, seq);
     if (tid < world && tid != rank) {
         const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(p.xchg_peers[rank]) + flag_off + tid;
         const unsigned long long t0 = x_globaltimer_ns();     // a peer that never arrives must fail loudly: 10 s of wall time
         unsigned int polls = 0;
-        while (x_ld_acquire_sys(mine) < p.xchg_seq) {
+        while (x_ld_acquire_sys(mine) < seq) {
             if ((++polls & 1023u) == 0 && x_globaltimer_ns() - t0 > 10000000000ull) {
                 atomicOr(&pl->status, (uint32_t)ARCO_ST_EXCHANGE_TIMEOUT);
                 __threadfence_system();
@@ -1067,7 +1089,9 @@ static int infonce_impl(const arco_dims* dims, const void* rep, const arco_bank*
     p.xchg_peers = nullptr; p.xchg_out = nullptr; p.xchg_seq = 0; p.xchg_slot = 0; p.xchg_rank = 0; p.xchg_world = 1;
     p.gate_replanned = gate_replanned; p.nq = d.classes * d.queries;
     if (xchg) {
-        ARCO_REQUIRE(xchg->peers && xchg->world >= 1 && xchg->world <= 64 && xchg->rank >= 0 && xchg->rank < xchg->world && xchg->seq > 0 &&
+        ARCO_REQUIRE(xchg->peers && xchg->world >= 1 && xchg->world <= 64 && xchg->rank >= 0 && xchg->rank < xchg->world &&
+                         ((xchg->seq & ARCO_XCHG_SEQ_MASK) > 0 || (xchg->seq & ARCO_XCHG_SEQ_FROM_DEVICE)) &&
+                         (!(xchg->seq & ARCO_XCHG_SEQ_FROM_DEVICE) || (xchg->seq & ARCO_XCHG_STEP_WORD)) &&
                          xchg->slot_doubles >= (int64_t)d.classes * (d.feat + 1), "arco_infonce_sharded: bad exchange descriptor");
         p.xchg_peers = (const unsigned long long*)xchg->peers; p.xchg_out = const_cast<double*>(proto_sums);
         p.xchg_seq = xchg->seq; p.xchg_slot = xchg->slot_doubles; p.xchg_rank = xchg->rank; p.xchg_world = xchg->world;

@@ -54,6 +54,8 @@ enum {
     ARCO_ST_INDEX_RANGE = 4,      /* an injected / caller-provided sample index was outside its list (clamped)    */
     ARCO_ST_KEYS_DROPPED = 8,     /* keys were counted but the selected prototype kernel cannot enqueue them
                                      (register kernel for C <= 3: only legal with low_rank >= classes)            */
+    ARCO_ST_EXCHANGE_DESYNC = 16, /* multi-GPU exchange: the device's step word and the slot the caller chose disagree
+                                     (a replayed step ran without its prototype pass, or a launch was lost)           */
     ARCO_ST_EXCHANGE_TIMEOUT = (int)0x80000000u  /* multi-GPU exchange: a peer never raised its flag (10 s)       */
 };
 
@@ -445,10 +447,18 @@ ARCO_API int arco_infonce_rows(const arco_dims* dims, const float* anchor_rows, 
    arco_proto_allreduce_p2p), re-derives the valid-class list and publishes both before the merge.  If the plan changed under
    the speculation the launch emits nothing; the caller always enqueues  arco_sample_if_replanned  and a second
    arco_infonce_sharded(exchange = NULL, gate_replanned = 1), both of which return at once unless plan->replanned. */
+#define ARCO_XCHG_STEP_WORD       (1ull << 63)
+#define ARCO_XCHG_SEQ_FROM_DEVICE (1ull << 62)
+#define ARCO_XCHG_SEQ_MASK        ((1ull << 62) - 1)
 typedef struct arco_exchange {
     const uint64_t* peers;        /* device array [world]: this rank's exchange buffer as mapped for every peer              */
-    uint64_t        seq;          /* step sequence number (> 0, grows by one per step)                                         */
-    int64_t         slot_doubles; /* doubles per slot; layout [slot 0][slot 1][flags: one u64 per source rank]                 */
+    uint64_t        seq;          /* step sequence number (> 0, grows by one per step) in bits 0-61.
+                                     Bit 63 (ARCO_XCHG_STEP_WORD): the buffer carries a u64 step word behind its 64 flags; every
+                                     exchange stores its sequence number there.  Bit 62 (ARCO_XCHG_SEQ_FROM_DEVICE, needs bit 63):
+                                     the sequence number is that word + 1 and bits 0-61 only give its expected parity -- this
+                                     is what lets arco_forward replay a multi-GPU step as a CUDA graph (no launch parameter
+                                     changes from step to step); a parity mismatch sets ARCO_ST_EXCHANGE_DESYNC and traps.    */
+    int64_t         slot_doubles; /* doubles per slot; layout [slot 0][slot 1][flags: 64 u64, one per source rank][step word]   */
     int32_t         rank, world;
 } arco_exchange;
 ARCO_API int arco_infonce_sharded(const arco_dims* dims, const void* rep, const arco_bank* bank, const arco_exchange* exchange,

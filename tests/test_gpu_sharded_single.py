@@ -94,3 +94,76 @@ def test_sharded_forward_with_a_fake_peer(scenario, monkeypatch):
     lo = float(res.loss.detach())
     assert abs(float(loss.detach()) - lo) <= 1e-5 * max(1.0, abs(lo)), (float(loss.detach()), lo)
     assert float((rep_s.grad.cpu() - rep_c.grad).norm() / rep_c.grad.norm()) <= 1e-5
+
+
+@pytest.mark.parametrize("scenario", ["same", "replanned"])
+def test_sharded_steps_replay_as_graphs(scenario, monkeypatch):
+    """The multi-GPU step through arco_forward's replay cache: the exchange buffer carries a step word, replayed steps take
+    their sequence number from it (no launch parameter changes from step to step).  Ten steps with fresh contents under
+    fixed addresses, cache on vs cache off: bit-identical loss, gradient, keys, ring rows; the sequence word follows."""
+    import ctypes as C
+    from arco_b200 import _cabi
+    dev = torch.device("cuda", 0)
+    spec = CaseSpec("shard_replay", 2, 2, 4, (32, 32), 16, queries=32, negatives=8, bank_init="fill:60", caps=[80, 70, 70, 70],
+                    label_mode="absent:1" if scenario == "replanned" else "iid", seed=43)
+    Cn, D = spec.classes, spec.feat
+    peer_sums = torch.zeros(Cn, D + 1, dtype=torch.float64)
+    if scenario == "replanned":
+        gen = torch.Generator().manual_seed(3)
+        peer_sums[:, :D] = torch.randn(Cn, D, generator=gen, dtype=torch.float64) * 5
+        peer_sums[:, D] = torch.tensor([7.0, 5.0, 9.0, 4.0], dtype=torch.float64)
+    kw = dict(delta_n=0.97, func="smc", num_queries=spec.queries, num_negatives=spec.negatives, temp=0.5, seed=5)
+
+    def stats():
+        buf = (C.c_int64 * 3)()
+        _cabi.check(_cabi.lib.arco_forward_replay_stats(buf), "arco_forward_replay_stats")
+        return list(buf)
+
+    def run(replay_on, steps=10):
+        n = Cn * (D + 1)
+        slot = (n + 63) // 64 * 64
+        mine = torch.zeros(2 * slot + 64 + 8, dtype=torch.float64, device=dev)        # two slots, 64 flags, the step word
+        peer = torch.zeros(2 * slot + 64 + 8, dtype=torch.float64, device=dev)
+        for s in range(2):
+            peer[s * slot: s * slot + n] = peer_sums.flatten().to(dev)
+        mine.view(torch.int64)[2 * slot + 1] = 1 << 60
+        state = dict(buf=mine, peer_buf=peer, hdl=None, rank=0, world=2, slot=slot, seq=0, seq_flags=1 << 63,
+                     peers=torch.tensor([mine.data_ptr(), peer.data_ptr()], dtype=torch.int64, device=dev))
+        monkeypatch.setattr(contra, "_p2p_exchange", lambda group, d, n_: state)
+        prev = _cabi.lib.arco_forward_replay(1 if replay_on else 0)
+        try:
+            bank, ptr, caps = make_bank(spec)
+            g = {k: v.to(dev) for k, v in exact_case(spec, 0).items()}
+            rep = g["rep"].clone().requires_grad_(True)
+            before = stats()
+            out = []
+            for step in range(steps):
+                x = exact_case(spec, step)
+                with torch.no_grad():
+                    for k, v in x.items():
+                        (rep if k == "rep" else g[k]).copy_(v)
+                rep.grad = None
+                nk, loss = arco_b200.compute_contra_memobank_loss(rep, g["label_l"], g["label_u"], g["prob_l"], g["prob_u"],
+                                                                  g["low_mask"], g["high_mask"], bank, ptr, caps, g["rep_teacher"],
+                                                                  process_group=object(), **kw)
+                loss.backward()
+                torch.cuda.synchronize()
+                arco_b200.synchronize_bank(bank)
+                assert int(mine.view(torch.int64)[2 * slot + 64]) == step + 1          # the device's step word follows
+                out.append((loss.detach().clone(), rep.grad.clone(), [int(k) for k in nk],
+                            [bank[c][0].cpu().clone() for c in range(Cn)], int(bank[0].bank.last_plan.replanned)))
+            return out, [a - b for a, b in zip(stats(), before)]
+        finally:
+            _cabi.lib.arco_forward_replay(prev)
+
+    on, d_on = run(True)
+    off, d_off = run(False)
+    assert d_off[0] == 0 and d_off[1] == 0
+    assert d_on[0] >= 2, d_on                                    # (graphs captured by an earlier test at the same addresses count too)
+    for a, b in zip(on, off):
+        assert torch.equal(a[0], b[0]) and a[2] == b[2] and a[4] == b[4]
+        assert float((a[1] - b[1]).abs().max()) <= 1e-6 * max(1e-30, float(b[1].abs().max()))   # float atomics for duplicates
+        for ra, rb in zip(a[3], b[3]):
+            assert torch.equal(ra, rb)
+    if scenario == "replanned":
+        assert all(o[4] == 1 for o in on)
