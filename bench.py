@@ -281,9 +281,16 @@ def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, grou
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    def replay_stats():
+        import ctypes
+        buf = (ctypes.c_int64 * 3)()
+        _cabi.check(_cabi.lib.arco_forward_replay_stats(buf), "arco_forward_replay_stats")
+        return list(buf)
+
     for _ in range(max(3, warmup)):
         step()
     sync_all()
+    rs0 = replay_stats()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     sync_all()
@@ -296,6 +303,7 @@ def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, grou
         ends[i].record()
     sync_all()
     t_end = time.perf_counter()
+    rs1 = replay_stats()
     per_step = sorted(s.elapsed_time(e) for s, e in zip(starts, ends))
     total_ms = sum(per_step)
     t = torch.tensor([total_ms, per_step[len(per_step) // 2]], dtype=torch.float64, device=dev)
@@ -309,6 +317,9 @@ def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, grou
         # eager processes a short step (0.2 ms) picks up host-launch outliers of 0.5 ms+
         "ms_per_step_median": median_ms,
         "pixels_per_gpu": P, "rep_storage": spec.dtype, "l2": l2_note,
+        # how arco_forward issued the timed steps' launches (rank 0): replayed as a captured CUDA graph (small shapes, see
+        # DESIGN.md "Replay cache"), captured on the second sighting of a parameter tuple, or launched one by one
+        "forward_issue": dict(zip(("graph_replays", "graphs_captured", "direct"), (a - b for a, b in zip(rs1, rs0)))),
     }
     if graph and world == 1:
         # The same public call, captured ONCE with torch.cuda.graph (forward + backward) and replayed: no launch parameter

@@ -309,7 +309,8 @@ ARCO_API int arco_forward(const arco_dims* dims, const arco_step_io* io, const a
  * Only steps whose representation tensor is <= 512 MiB replay (the host-bound ones; an HBM-bound step does not hide a graph
  * launch's start-up cost), unless forced.  arco_forward_replay(1 / 0 / 2) switches the cache on / off / on for every size
  * for the process and returns whether it was on (-1 only queries; default 1, ARCO_FWD_GRAPH=0 / 2 in the environment).  arco_forward_replay_stats fills, for the calling
- * thread and current device, stats[0] = steps replayed, stats[1] = graphs captured, stats[2] = first sightings run directly. */
+ * thread and current device, stats[0] = steps replayed, stats[1] = graphs captured, stats[2] = steps launched
+ * directly (first sightings, cache off, too large, or an exchange buffer without a step word). */
 ARCO_API int arco_forward_replay(int32_t on);
 ARCO_API int arco_forward_replay_stats(int64_t* stats);
 
