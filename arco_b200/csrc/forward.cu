@@ -170,13 +170,20 @@ extern "C" int arco_forward(const arco_dims* dims, const arco_step_io* io, const
     cudaStream_t main_st = (cudaStream_t)stream;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     int dev = -1;
-    const bool sharded_ok = io->exchange_peers == nullptr || (io->exchange_seq & ARCO_XCHG_STEP_WORD);
-    if (!arco::replay_enabled() || !arco::replay_worthwhile(*dims) || !sharded_ok || cudaStreamIsCapturing(main_st, &cap) != cudaSuccess ||
-        cap != cudaStreamCaptureStatusNone || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
         cudaGetLastError();
         return forward_launches(dims, io, bank, workspace, main_st);
     }
     arco::FwdCache& fc = arco::fwd_cache(dev);
+    const bool sharded_ok = io->exchange_peers == nullptr || (io->exchange_seq & ARCO_XCHG_STEP_WORD);
+    if (cudaStreamIsCapturing(main_st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();                                          // the caller is capturing: its step is not counted
+        return forward_launches(dims, io, bank, workspace, main_st);
+    }
+    if (!arco::replay_enabled() || !arco::replay_worthwhile(*dims) || !sharded_ok) {
+        ++fc.n_direct;
+        return forward_launches(dims, io, bank, workspace, main_st);
+    }
     arco::FwdKey* key = arco::make_key(dims, io, bank, workspace);
     if (!key) return forward_launches(dims, io, bank, workspace, main_st);
     ++fc.tick;

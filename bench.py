@@ -371,7 +371,8 @@ def measure_workload(torch, dist, arco_b200, _cabi, name, dev, rank, world, grou
                                   "global_low_valid_pixels": counts, "exchange": __import__("arco_b200.contra", fromlist=["x"]).EXCHANGE_PLANE}
         assert same, "global prototype sums differ between ranks"
     if with_stages and rank == 0:
-        stages, roof = stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush)
+        stages, roof = stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush,
+                                    traffic_key=spec.name + ("+coherent_masks" if coherent else ""))
         out["stages"], out["roofline"] = stages, roof
         m = stages["_measured"]
         e_t = 2 if spec.dtype == "bf16" else 4
@@ -515,7 +516,8 @@ def main_ours(args):
             "clocks": clk, "gpu_launches": args.steps * (KERNELS_PER_STEP + (3 if world > 1 else 0)),   # N>1: + sample_scan / sample_emit / InfoNCE again, gated on a changed plan (early exit)
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "aten_gpu_baseline": aten, "stages": stages,
             "step_alg_bytes": head.get("step_alg_bytes"), "step_frac_hbm": head.get("step_frac_hbm"),
-            "multi_gpu_check": head.get("multi_gpu_check"), "cuda_graph_replay": head.get("cuda_graph_replay"), "configs": configs,
+            "multi_gpu_check": head.get("multi_gpu_check"), "cuda_graph_replay": head.get("cuda_graph_replay"),
+            "forward_issue": head.get("forward_issue"), "configs": configs,
             "acdc2d_fullstep": fullstep, "producers": producers_blk,
         }
         print(json.dumps(line))
@@ -541,7 +543,7 @@ def run_fullstep(steps):
         return {"error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}
 
 
-def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush, iters=10):
+def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, dev, flush, iters=10, traffic_key=None):
     """Time every C-ABI stage on its own (CUDA events on the launching stream) and build the roofline
     entry of the dominant kernel from the algorithmic bytes of SURVEY.md section 8(d)."""
     C = ctypes
@@ -616,7 +618,7 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get(spec.name, {}).get("proto_enqueue")
+                traffic = json.load(f).get(traffic_key or spec.name, {}).get("proto_enqueue")
         except Exception:
             traffic = None
     k = "proto_enqueue"
@@ -630,7 +632,9 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
             "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg[k], "ms_per_launch": ms[k],
             "bytes_formula": "P_lv*D*e_t + K*D*(e_t+e_bank) + P  (SURVEY.md section 8(d) teacher-read and key terms + 1 code byte per pixel)",
             "note": "rep_teacher is channel-first, so every 32-byte sector that holds one low-valid pixel must be fetched: "
-                    "with the iid 20% masks of this workload that is ALL of P*D*e_t; 'traffic' is the ncu-measured DRAM bytes"}
+                    "with the iid 20% masks of this workload that is ALL of P*D*e_t (coherent masks: steps without a needed pixel "
+                    "are skipped); 'traffic' is the ncu-measured DRAM bytes of this kernel on this workload (profiles/traffic.json, "
+                    "recorded, not live)"}
     if traffic:
         # the same launch against the DRAM bytes ncu counted for it (what the kernel really moved), next to the contract's
         # algorithmic figure

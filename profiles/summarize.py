@@ -56,7 +56,8 @@ def main():
                     lines.append(f"| {m} | {d[m]} |")
             # DRAM bytes of the prototype kernel per launch -> profiles/traffic.json (bench.py's roofline.traffic)
             base = os.path.basename(rep)
-            wl = ("acdc2d_trainstep" if "trainstep" in base else "cityscapes" if "city" in base else
+            wl = ("acdc2d_trainstep" if "trainstep" in base else "cityscapes+coherent_masks" if "city" in base and "coherent" in base else
+                  "cityscapes" if "city" in base else
                   "la3d" if "la3d" in base else "acdc2d_loss" if "acdc" in base else None)
             if wl and "proto_" in d["kernel"] and "finalize" not in d["kernel"]:
                 def num(m):
