@@ -582,11 +582,17 @@ def stage_timing(torch, _cabi, arco_b200, spec, x, rep, memobank, ptrs, caps, de
         ("grad_scatter", lambda: lib.arco_grad_scatter(d, g_anchor.data_ptr(), pix.data_ptr(), go.data_ptr(), grad.data_ptr(), sp)),
     ]
     acc = {name: 0.0 for name, _ in calls}
+    # A stage is timed as the device sees it: start event, launch(es) and stop event are all ENQUEUED behind a ~100 us
+    # device-side delay, so the interval holds the kernel(s) and their launch gaps but not the host's time to issue the call
+    # (ctypes + cuTensorMapEncode + cudaLaunch, 10-20 us -- as much as a small kernel runs).  ncu's gpu__time_duration of the
+    # same kernels (profiles/rNN_kernel_shares.md) is the cross-check.
+    delay_cycles = int(100e-6 * 1.9e9)
     for it in range(iters + 2):
         for name, fn in calls:
             if flush is not None:
                 flush.fill_(it & 0xff)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(delay_cycles)
             e0.record()
             rc = fn()
             e1.record()

@@ -34,7 +34,7 @@ def main():
     out = [f"# {tag}: kernel shares of one step -- ncu launch list vs live CUDA-event stage timing\n",
            f"`profiles/{tag}_launches_<workload>.csv` (ncu `--metrics gpu__time_duration.sum --clock-control none`, serialised, cold caches) "
            f"against the `stages` block of the driver-format bench line (`profiles/{tag}_bench_lines.md`; CUDA events on the launching "
-           "stream, each C-ABI stage timed alone, so a stage includes ~3-5 us of launch latency that a pipelined step does not pay).\n"]
+           "stream, each C-ABI stage timed alone with its events and launches enqueued behind a device-side delay, so the host's issue time is not in the interval).\n"]
     for wl, blk in blocks.items():
         agg = launches(os.path.join(ROOT, "profiles", f"{tag}_launches_{wl}.csv"))
         step = sum(sum(v) / len(v) for v in agg.values())
