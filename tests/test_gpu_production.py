@@ -29,6 +29,10 @@ PRODUCTION = [
     ("acdc2d_trainstep", "smc"),     # config 2: 12+12, C=4, 256x256, D=496 bf16 -- the bench.py headline
     ("la3d", "asmc"),                # config 3: 2+2, C=2, 112x112x80, D=16 fp32
     ("cityscapes", "smc"),           # config 4: 8+8, C=19, 512x512, D=256 fp32
+    # the same two tensor-core shapes with spatially coherent entropy masks: whole 32- / 64-pixel steps of the unlabelled
+    # images are skipped by the prototype pass (per-tile step masks), which must not change a single count, key or ring row
+    ("acdc2d_trainstep+coherent", "smc"),
+    ("cityscapes+coherent", "smc"),
 ]
 
 
@@ -41,11 +45,12 @@ def _rel(a, b):
 def test_benchmarked_configuration_against_oracle(workload, func):
     import arco_b200
     dev = torch.device("cuda", 0)
+    workload, _, variant = workload.partition("+")
     cfg = WORKLOADS[workload]
     spec = None
     bank_g = bank_c = None
     for step in range(2):
-        spec, x = bench_inputs(workload, dev, seed=101 + step)
+        spec, x = bench_inputs(workload, dev, seed=101 + step, coherent=variant == "coherent")
         assert (spec.n_lab, spec.n_unlab) == (cfg["n_lab"], cfg["n_unlab"])          # the FULL batch
         if bank_g is None:
             bank_g, ptr_g, caps = bench_bank(spec, seed=3)

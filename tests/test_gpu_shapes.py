@@ -50,6 +50,27 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+def _check_step_masks(dbg, spec):
+    """tile_flagged[t] bit g  <=>  the 32-pixel group g of tile t holds a low-valid (0x20) or key (0x80) code: the bits the
+    tensor-core prototype kernels walk instead of every step (classify.cu, all three classify kernels)."""
+    L, ws = dbg["layout"], dbg["ws"]
+    S = 1
+    for s_ in spec.spatial:
+        S *= s_
+    B, tpi = spec.batch, int(L.tiles_per_image)
+    codes = ws[L.codes: L.codes + B * S].view(B, S)
+    flagged = ws[L.tile_flagged: L.tile_flagged + 4 * B * tpi].view(torch.int32).view(B, tpi).cpu()
+    need = ((codes & 0xA0) != 0)
+    pad = tpi * 1024 - S
+    if pad:
+        need = torch.nn.functional.pad(need, (0, pad))
+    groups = need.view(B, tpi, 32, 32).any(dim=-1).cpu()                                   # [B, tile, group]
+    weights = (torch.ones(32, dtype=torch.int64) << torch.arange(32))
+    want = (groups.long() * weights).sum(dim=-1)
+    got = flagged.long() & 0xFFFFFFFF
+    assert torch.equal(got, want), "per-tile step masks disagree with the code bytes"
+
+
 @pytest.mark.parametrize("spec", SPECS, ids=lambda s: s.name)
 @pytest.mark.parametrize("index_labels", [False, True], ids=["onehot", "indexlabels"])
 def test_shape(spec, index_labels):
@@ -90,6 +111,7 @@ def test_shape(spec, index_labels):
             temp=spec.temp)
         res.loss.backward()
         Cn = spec.classes
+        _check_step_masks(dbg, spec)
         assert list(new_keys) == res.new_keys
         assert [int(plan.lv_count[c]) for c in range(Cn)] == res.low_valid_counts
         assert [int(plan.n_anchor[c]) for c in range(Cn)] == [len(a) for a in res.anchor_lists]
