@@ -140,13 +140,13 @@ def main():
         g = {k: v.to(dev) for k, v in exact_case(spec, 0).items()}
         n_sum = 4 * 17
         slot = (n_sum + 63) // 64 * 64
-        mine = torch.zeros(2 * slot + 64, dtype=torch.float64, device=dev)
-        peer = torch.zeros(2 * slot + 64, dtype=torch.float64, device=dev)
+        mine = torch.zeros(2 * slot + 64 + 8, dtype=torch.float64, device=dev)      # two slots, 64 flags, the step word
+        peer = torch.zeros(2 * slot + 64 + 8, dtype=torch.float64, device=dev)
         ps = torch.rand(4, 17, dtype=torch.float64) * 5 + 1
         for sl in range(2):
             peer[sl * slot: sl * slot + n_sum] = ps.flatten().to(dev)
         mine.view(torch.int64)[2 * slot + 1] = 1 << 60
-        state = dict(buf=mine, peer_buf=peer, hdl=None, rank=0, world=2, slot=slot, seq=0,
+        state = dict(buf=mine, peer_buf=peer, hdl=None, rank=0, world=2, slot=slot, seq=0, seq_flags=1 << 63,
                      peers=torch.tensor([mine.data_ptr(), peer.data_ptr()], dtype=torch.int64, device=dev))
         orig = contra._p2p_exchange
         contra._p2p_exchange = lambda group, d, n: state
@@ -158,6 +158,7 @@ def main():
                                                              num_queries=32, num_negatives=8, seed=5, process_group=object())
             loss.backward()
             torch.cuda.synchronize()
+            assert int(mine.view(torch.int64)[2 * slot + 64]) == 1          # the exchange stored its sequence number in the step word
         finally:
             contra._p2p_exchange = orig
         print("ok sharded", float(loss))
